@@ -1,0 +1,112 @@
+/*
+ * quick_b200 — C-ABI of the B200-native W4A16 grouped GEMM (drop-in for the one
+ * native entry point of SqueezeBits/QUICK).
+ *
+ * Reference interface replaced (all paths under /root/reference):
+ *   csrc/gemm_cuda_quick.h:3-8      torch::Tensor gemm_forward_cuda_quick(in_feats, kernel,
+ *                                   scaling_factors, zeros, split_k_iters)
+ *   csrc/pybind.cpp:5-8             module `quick_kernels`, symbol `gemm_forward_cuda_quick`
+ *   csrc/gemm_cuda_quick.cu:1456-1517  host dispatcher (argument checks :1479-1484)
+ *   quick/awq/modules/linear/quick.py:52-54   packed operand shapes
+ *   quick/awq/modules/linear/quick.py:88-150  offline interleave/packer (qb200_pack_quick)
+ *
+ * Plain pointers and sizes only; no torch types.  Unless a function says "host",
+ * every pointer is a DEVICE pointer and work is enqueued on `stream` (a
+ * cudaStream_t passed as void*; NULL = legacy default stream) without
+ * synchronising.  All functions return 0 on success or a negative QB200_E* code;
+ * qb200_last_error() gives the message of the calling thread's last failure.
+ *
+ * Operand formats
+ *   QUICK layout (what the reference's checkpoints and WQLinear_QUICK hold):
+ *     qweight int32 [K/4][N/2], qzeros int32 [K/G][N/4], scales fp16 [K/G][2N]
+ *   B200 layout (what the tcgen05 kernel streams; produced once per weight):
+ *     wq  uint32 [N/128][K/64][2][128][4]  word = 8 consecutive k of one output channel,
+ *                                          nibble order k0,k2,k4,k6,k1,k3,k5,k7
+ *     sz  uint32 [N/128][K/G][128]         low half = fp16 scale, high half = fp16(1024 + zero)
+ */
+#ifndef QUICK_B200_H
+#define QUICK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QB200_OK 0
+#define QB200_EINVAL (-1)   /* bad shape/argument: the reference's std::invalid_argument cases and the checks it lacks */
+#define QB200_ECUDA (-2)    /* CUDA runtime / driver error */
+#define QB200_ENOSPC (-3)   /* workspace too small */
+
+const char* qb200_version(void);
+const char* qb200_last_error(void);
+
+/* Bytes of the B200-layout buffers for a (K, N, G) weight. */
+size_t qb200_wq_bytes(int K, int N);
+size_t qb200_sz_bytes(int K, int N, int G);
+
+/* Argument validation shared by every entry point: N % 128, G % 32 (reference :1479-1484),
+ * plus K % 64, K % G, G <= K which the reference leaves unchecked. */
+int qb200_check_shape(int M, int K, int N, int G);
+
+/* QUICK layout -> B200 layout (bit-exact nibble permutation + de-duplication of scales/zeros).
+ * Replaces nothing in the reference: it is the load-time transform that lets the unchanged
+ * checkpoint format feed the tcgen05 kernel. */
+int qb200_relayout_from_quick(const int32_t* qweight, const int32_t* qzeros, const void* scales_fp16,
+                              int K, int N, int G, uint32_t* wq, uint32_t* sz, void* stream);
+
+/* Logical (q[K][N] uint8 0..15, z[K/G][N] uint8, s[K/G][N] fp16) -> QUICK layout.
+ * GPU replacement of the python packer quick.py:88-150 (no N==128 / N%256 restriction). */
+int qb200_pack_quick(const uint8_t* q, const uint8_t* z, const void* s_fp16, int K, int N, int G,
+                     int32_t* qweight, int32_t* qzeros, void* scales_fp16, void* stream);
+
+/* B200 layout -> W16[K][N] fp16 = fp16((q - z)) * s, one rounding (gemm_cuda_quick.cu:52-60). */
+int qb200_dequantize(const uint32_t* wq, const uint32_t* sz, int K, int N, int G, void* w16_fp16, void* stream);
+
+/* C[M][N] fp16 = A[M][K] fp16 · dequant(W) — the hot path (tcgen05/TMEM/TMA, sm_100a).
+ * split_k_hint: the reference's split_k_iters; treated as a hint (0 = auto).
+ * bias (fp16 [N]) is added in the epilogue when non-NULL (reference: quick.py:165, a separate torch add).
+ * No workspace: split-K partials are reduced inside a thread-block cluster through distributed shared memory. */
+int qb200_gemm_w4a16(const void* A_fp16, const uint32_t* wq, const uint32_t* sz, const void* bias_fp16_or_null,
+                     void* C_fp16, int M, int K, int N, int G, int split_k_hint, void* stream);
+
+/* Same, forcing the tile configuration (tuning / tests): tok in {16,32,64,128,256}, split in {1,2,4,8}. */
+int qb200_gemm_w4a16_cfg(const void* A_fp16, const uint32_t* wq, const uint32_t* sz, const void* bias_fp16_or_null,
+                         void* C_fp16, int M, int K, int N, int G, int tok, int split, void* stream);
+
+/* Reports the configuration qb200_gemm_w4a16 would pick. */
+int qb200_gemm_plan(int M, int K, int N, int G, int split_k_hint, int* tok, int* split, int* ctas);
+
+/* Stateless drop-in for gemm_forward_cuda_quick on QUICK-layout operands: relayout into the caller's
+ * workspace (>= qb200_wq_bytes + qb200_sz_bytes, 256-B aligned) then GEMM.  The torch binding
+ * caches the relayout per weight instead (quick_kernels_ext.cpp). */
+int qb200_gemm_forward_quick(const void* A_fp16, const int32_t* qweight, const void* scales_fp16,
+                             const int32_t* qzeros, void* C_fp16, int M, int K, int N, int G,
+                             int split_k_iters, void* workspace, size_t workspace_bytes, void* stream);
+
+/* CUDA-core cross-check of the same contraction (tests only; never dispatched to by the hot path). */
+int qb200_gemm_w4a16_simt(const void* A_fp16, const uint32_t* wq, const uint32_t* sz, void* C_fp16,
+                          int M, int K, int N, int G, void* stream);
+
+/* ---- HOST-buffer handle API (the end-to-end path: H2D, GEMM, D2H inside the call) ---- */
+typedef struct qb200_linear qb200_linear;
+
+/* Uploads QUICK-layout HOST tensors, converts them to the B200 layout on the device, keeps both
+ * staging buffers for activations/outputs of up to max_m rows.  bias_fp16 may be NULL. */
+int qb200_linear_create(qb200_linear** out, const int32_t* qweight_host, const int32_t* qzeros_host,
+                        const void* scales_fp16_host, const void* bias_fp16_host,
+                        int K, int N, int G, int max_m, int device);
+/* y[M][N] = x[M][K] · W (+ bias): copies x from host, runs the kernel, copies y back, synchronises. */
+int qb200_linear_forward_host(qb200_linear* h, const void* x_fp16_host, void* y_fp16_host, int M);
+/* Device-pointer forward on the handle's weights (async on `stream`). */
+int qb200_linear_forward(qb200_linear* h, const void* x_fp16_dev, void* y_fp16_dev, int M, void* stream);
+void qb200_linear_destroy(qb200_linear* h);
+
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches claim). */
+unsigned long long qb200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUICK_B200_H */

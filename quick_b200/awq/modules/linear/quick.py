@@ -1,0 +1,111 @@
+"""WQLinear_QUICK — host-side mirror of the reference module
+(/root/reference/quick/awq/modules/linear/quick.py:35-171): same constructor, same buffer names,
+shapes and dtypes (checkpoints load unchanged), same ``from_linear`` arguments, same ``forward``
+semantics.  Differences, all behind the same interface:
+
+* the packer is a vectorised closed form (quick_b200.layout.pack_quick / the GPU packer) instead of
+  python loops of tiny kernels; it has no ``N == 128 or N % 256 == 0`` restriction and no hard-coded
+  'cuda' (reference quick.py:95,101,110-115,147);
+* ``forward`` converts the weight once to the B200 layout (non-persistent buffers, re-done if the
+  packed buffers are replaced or modified) and runs the tcgen05 kernel with the bias fused into the
+  epilogue: one launch instead of GEMM + ``sum`` + bias add (reference quick.py:161-165,
+  gemm_cuda_quick.cu:1515).  ``k_split_1/2`` are accepted and forwarded as hints only.
+"""
+import torch
+import torch.nn as nn
+
+import quick_kernels  # the drop-in extension; import failure must break this module like the reference (quick.py:4)
+from quick_kernels import gemm_forward_cuda_quick  # noqa: F401  (re-exported, same name as the reference)
+
+from ....layout import pack_quick
+
+
+def make_divisible(c, divisor):
+    return (c + divisor - 1) // divisor
+
+
+def calculate_zeros_width(in_features, group_size=128, pack_num=8):
+    if group_size >= 128:
+        size_multiplier = 1
+    elif group_size == 64:
+        size_multiplier = 2
+    elif group_size == 32:
+        size_multiplier = 4
+    else:
+        raise NotImplementedError
+    base_width = make_divisible(in_features // group_size, pack_num)
+    base_width = make_divisible(base_width, size_multiplier) * size_multiplier
+    return base_width
+
+
+class WQLinear_QUICK(nn.Module):
+    def __init__(self, w_bit, group_size, in_features, out_features, bias, dev, k_split_1=2, k_split_2=8):
+        super().__init__()
+        if w_bit not in [4]:
+            raise NotImplementedError("Only 4-bit are supported for now.")
+        self.in_features = in_features
+        self.out_features = out_features
+        self.w_bit = w_bit
+        self.group_size = group_size if group_size != -1 else in_features
+        self.k_split_1 = k_split_1
+        self.k_split_2 = k_split_2
+        assert self.in_features % self.group_size == 0
+        assert out_features % (32 // self.w_bit) == 0
+        pack = 32 // self.w_bit
+        self.register_buffer("qweight", torch.zeros((in_features // 4, out_features // pack * 4), dtype=torch.int32, device=dev))
+        self.register_buffer("qzeros", torch.zeros((in_features // self.group_size, out_features * 2 // pack), dtype=torch.int32, device=dev))
+        self.register_buffer("scales", torch.zeros((in_features // self.group_size, out_features * 2), dtype=torch.float16, device=dev))
+        if bias:
+            self.register_buffer("bias", torch.zeros((out_features), dtype=torch.float16, device=dev))
+        else:
+            self.bias = None
+        self._b200 = None       # (wq, sz) in the B200 layout — derived, never saved
+        self._b200_key = None
+
+    @classmethod
+    def from_linear(cls, linear, w_bit, group_size, init_only=False, scales=None, zeros=None, k_split_1=2, k_split_2=8):
+        awq_linear = cls(w_bit, group_size, linear.in_features, linear.out_features, linear.bias is not None,
+                         linear.weight.device, k_split_1, k_split_2)
+        if init_only:  # just prepare for loading sd
+            return awq_linear
+        assert scales is not None and zeros is not None
+        G = awq_linear.group_size
+        # intweight[k, n] = round((W[n, k] + z*s) / s)   (reference quick.py:76-81), scales/zeros are (N, K/G)
+        s16 = scales.clone().half()
+        s_rep = s16.repeat_interleave(G, dim=1)
+        zs_rep = (zeros * scales).repeat_interleave(G, dim=1)
+        intweight = torch.round((linear.weight.data + zs_rep) / s_rep).to(torch.int32).t().contiguous()
+        qweight, qzeros, qscales = pack_quick(intweight, zeros.t().contiguous().to(torch.int32), s16.t().contiguous())
+        awq_linear.qweight = qweight
+        awq_linear.qzeros = qzeros
+        awq_linear.scales = qscales
+        if linear.bias is not None:
+            awq_linear.bias = linear.bias.clone().half()
+        return awq_linear
+
+    def _prepacked(self):
+        key = tuple((t.data_ptr(), 0 if t.is_inference() else t._version) for t in (self.qweight, self.qzeros, self.scales))
+        if self._b200 is None or self._b200_key != key:
+            wq, sz = quick_kernels.prepack_quick(self.qweight, self.scales, self.qzeros, self.in_features)
+            self._b200, self._b200_key = (wq, sz), key
+        return self._b200
+
+    @torch.no_grad()
+    def forward(self, x):
+        out_shape = x.shape[:-1] + (self.out_features,)
+        wq, sz = self._prepacked()
+        out = quick_kernels.gemm_forward_b200(x.reshape(-1, x.shape[-1]), wq, sz, self.bias, self.out_features, self.group_size)
+        return out.reshape(out_shape)
+
+    @torch.no_grad()
+    def forward_reference_call(self, x):
+        """The reference's exact call sequence (quick.py:158-166) through the drop-in symbol."""
+        out_shape = x.shape[:-1] + (self.out_features,)
+        split = self.k_split_1 if self.out_features > self.in_features else self.k_split_2
+        out = gemm_forward_cuda_quick(x.reshape(-1, x.shape[-1]), self.qweight, self.scales, self.qzeros, split)
+        out = out + self.bias if self.bias is not None else out
+        return out.reshape(out_shape)
+
+    def extra_repr(self) -> str:
+        return "in_features={}, out_features={}, bias={}, w_bit={}, group_size={}".format(
+            self.in_features, self.out_features, self.bias is not None, self.w_bit, self.group_size)

@@ -1,0 +1,540 @@
+// quick_b200 — C-ABI implementation (see include/quick_b200.h for the contract and the reference
+// interfaces each entry point replaces).  sm_100a only; there is no CPU or non-tcgen05 fallback on
+// the hot path: if the device is not compute capability 10.x the GEMM entry points return QB200_ECUDA.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/quick_b200.h"
+#include "w4a16_umma.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define QB_CUDA(expr)                                                                       \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) return fail(QB200_ECUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ------------------------------------------------------------------------------------------------
+// Layout kernels
+// ------------------------------------------------------------------------------------------------
+
+// (k, n) -> flat QUICK qweight word index and nibble position.
+// Inverse of the reference kernel's fragment addressing (gemm_cuda_quick.cu:1354,:1372 + mma.m16n8k16
+// B-fragment ownership); closed form in SURVEY.md Appendix A-1.
+__device__ __forceinline__ void quick_locate(int k, int n, int N, size_t& word, int& nib) {
+  const int kt = k >> 5, kk = k & 31, ks = kk >> 4, k16 = kk & 15;
+  const int hi = k16 >> 3;                 // 0: rows k0,k0+1   1: rows k0+8,k0+9
+  const int l4 = (k16 & 7) >> 1;           // lane % 4
+  const int odd = k16 & 1;
+  const int bx = n >> 7, nn = n & 127, ty = nn >> 6, n64 = nn & 63, chk = n64 >> 4, n16 = n64 & 15;
+  const int dc = n16 >> 3;                 // 0: c0   1: c0 + 8
+  const int lane = ((n16 & 7) << 2) | l4;
+  word = static_cast<size_t>(kt) * 4 * N + static_cast<size_t>(2 * ty + (lane >> 4)) * N + bx * 128 + (lane & 15) * 8 +
+         ks * 4 + chk;
+  nib = odd * 4 + dc * 2 + hi;
+}
+// column n -> scale/zero slot x of a packed row (inverse of quick.py:125-128)
+__device__ __forceinline__ int quick_slot(int n, int N) {
+  const int bx = n >> 7, ty = (n & 127) >> 6, r = n & 63;
+  const int m = ((r >> 4) << 1) | ((r & 15) >> 3);
+  const int lh = (r & 7) >> 2, j4 = r & 3;
+  return ty * (N >> 1) + lh * (N >> 2) + bx * 32 + j4 * 8 + m;
+}
+
+// One thread per B200 word: gathers 8 nibbles (4 QUICK words x 2 nibbles).
+__global__ void relayout_wq_kernel(const uint32_t* __restrict__ qweight, uint32_t* __restrict__ wq, int K, int N) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(K) * N / 8;
+  if (idx >= total) return;
+  const int KB = K / 64;
+  const int j = idx & 3;
+  const int c = (idx >> 2) & 127;
+  const int h = (idx >> 9) & 1;
+  const size_t blk = idx >> 10;
+  const int kb = static_cast<int>(blk % KB);
+  const int nt = static_cast<int>(blk / KB);
+  const int n = nt * 128 + c;
+  const int kbase = kb * 64 + h * 32 + j * 8;
+  uint32_t out = 0;
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const int i = (p < 4) ? 2 * p : 2 * (p - 4) + 1;   // nibble order k0,k2,k4,k6,k1,k3,k5,k7
+    size_t w;
+    int nib;
+    quick_locate(kbase + i, n, N, w, nib);
+    out |= ((__ldg(qweight + w) >> (4 * nib)) & 0xFu) << (4 * p);
+  }
+  wq[idx] = out;
+}
+
+__global__ void relayout_sz_kernel(const uint32_t* __restrict__ qzeros, const __half* __restrict__ scales,
+                                   uint32_t* __restrict__ sz, int NG, int N) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<size_t>(NG) * N) return;
+  const int c = idx & 127;
+  const size_t blk = idx >> 7;
+  const int g = static_cast<int>(blk % NG);
+  const int nt = static_cast<int>(blk / NG);
+  const int n = nt * 128 + c;
+  const int x = quick_slot(n, N);
+  const uint32_t zw = __ldg(qzeros + static_cast<size_t>(g) * (N / 4) + (x >> 2));
+  const uint32_t z = (zw >> (4 * (x & 3))) & 0xFu;
+  const uint32_t s = __half_as_ushort(__ldg(scales + static_cast<size_t>(g) * 2 * N + 2 * x));
+  sz[idx] = s | ((0x6400u + z) << 16);
+}
+
+// logical -> QUICK layout (GPU packer).  One thread per qweight word / per scale-zero slot.
+__global__ void pack_qweight_kernel(const uint8_t* __restrict__ q, uint32_t* __restrict__ qweight, int K, int N) {
+  const size_t f = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (f >= static_cast<size_t>(K) * N / 8) return;
+  const int kt = static_cast<int>(f / (4 * static_cast<size_t>(N)));
+  const int r = static_cast<int>(f % (4 * static_cast<size_t>(N)));
+  const int r4 = r / N, c = r % N, bx = c >> 7, w = c & 127;
+  const int lane = 16 * (r4 & 1) + (w >> 3), ty = r4 >> 1, ks = (w & 7) >> 2, chk = w & 3;
+  const int k0 = 32 * kt + 16 * ks + 2 * (lane & 3);
+  const int c0 = 128 * bx + 64 * ty + 16 * chk + (lane >> 2);
+  uint32_t out = 0;
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const int dk = ((p >> 2) & 1) + 8 * (p & 1);
+    const int dc = 8 * ((p >> 1) & 1);
+    out |= (static_cast<uint32_t>(q[static_cast<size_t>(k0 + dk) * N + c0 + dc]) & 0xFu) << (4 * p);
+  }
+  qweight[f] = out;
+}
+__global__ void pack_sz_kernel(const uint8_t* __restrict__ z, const __half* __restrict__ s, uint32_t* __restrict__ qzeros,
+                               __half* __restrict__ scales, int NG, int N) {
+  // one thread per zero word (4 slots): writes 1 int32 of zeros and 8 halves of (duplicated) scales
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<size_t>(NG) * (N / 4)) return;
+  const int g = static_cast<int>(idx / (N / 4));
+  const int xw = static_cast<int>(idx % (N / 4));
+  const int nb = N >> 7;
+  uint32_t zw = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int x = 4 * xw + i;
+    const int ty = x / (N >> 1), lh = (x / (N >> 2)) & 1, bx = (x >> 5) % nb, j4 = (x & 31) >> 3, m = x & 7;
+    const int n = 128 * bx + 64 * ty + 16 * (m >> 1) + 8 * (m & 1) + 4 * lh + j4;
+    zw |= (static_cast<uint32_t>(z[static_cast<size_t>(g) * N + n]) & 0xFu) << (4 * i);
+    const __half sv = s[static_cast<size_t>(g) * N + n];
+    scales[static_cast<size_t>(g) * 2 * N + 2 * x] = sv;
+    scales[static_cast<size_t>(g) * 2 * N + 2 * x + 1] = sv;
+  }
+  qzeros[idx] = zw | (zw << 16);
+}
+
+// B200 layout -> W16[K][N]
+__global__ void dequant_kernel(const uint32_t* __restrict__ wq, const uint32_t* __restrict__ sz, __half* __restrict__ W,
+                               int K, int N, int G) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<size_t>(K) * N / 8) return;
+  const int KB = K / 64, NG = K / G;
+  const int j = idx & 3, c = (idx >> 2) & 127, h = (idx >> 9) & 1;
+  const size_t blk = idx >> 10;
+  const int kb = static_cast<int>(blk % KB), nt = static_cast<int>(blk / KB);
+  const int n = nt * 128 + c;
+  const int kbase = kb * 64 + h * 32 + j * 8;
+  const uint32_t szw = sz[(static_cast<size_t>(nt) * NG + kbase / G) * 128 + c];
+  const qb200::GroupConsts g = qb200::make_group_consts(szw);
+  uint32_t o[4];
+  qb200::dequant_word(wq[idx], g, o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    W[static_cast<size_t>(kbase + 2 * i) * N + n] = __ushort_as_half(static_cast<unsigned short>(o[i] & 0xFFFFu));
+    W[static_cast<size_t>(kbase + 2 * i + 1) * N + n] = __ushort_as_half(static_cast<unsigned short>(o[i] >> 16));
+  }
+}
+
+// CUDA-core cross-check: one CTA per (n-tile, row m); thread = channel; fp32 accumulation in k order.
+__global__ void gemm_simt_kernel(const __half* __restrict__ A, const uint32_t* __restrict__ wq,
+                                 const uint32_t* __restrict__ sz, __half* __restrict__ C, int M, int K, int N, int G) {
+  extern __shared__ __half a_row[];
+  const int nt = blockIdx.x, m = blockIdx.y, c = threadIdx.x;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) a_row[k] = A[static_cast<size_t>(m) * K + k];
+  __syncthreads();
+  const int KB = K / 64, NG = K / G;
+  float acc = 0.f;
+  for (int kb = 0; kb < KB; ++kb) {
+    for (int h = 0; h < 2; ++h) {
+      const int k32 = kb * 64 + h * 32;
+      const uint32_t szw = sz[(static_cast<size_t>(nt) * NG + k32 / G) * 128 + c];
+      const qb200::GroupConsts g = qb200::make_group_consts(szw);
+      const uint4 w = *reinterpret_cast<const uint4*>(wq + ((static_cast<size_t>(nt) * KB + kb) * 2 + h) * 512 + c * 4);
+      const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t o[4];
+        qb200::dequant_word(ws[j], g, o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int k = k32 + j * 8 + 2 * i;
+          acc += __half2float(a_row[k]) * __half2float(__ushort_as_half(static_cast<unsigned short>(o[i] & 0xFFFFu)));
+          acc += __half2float(a_row[k + 1]) * __half2float(__ushort_as_half(static_cast<unsigned short>(o[i] >> 16)));
+        }
+      }
+    }
+  }
+  C[static_cast<size_t>(m) * N + nt * 128 + c] = __float2half_rn(acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-map encode (driver entry point fetched through the runtime: no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_x_tensor_map(CUtensorMap* map, const void* A, int M, int K, int tok) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(QB200_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(M)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * 2};
+  const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(tok)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(A), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(QB200_ECUDA, "cuTensorMapEncodeTiled failed (%d): A=%p M=%d K=%d tok=%d", (int)r, A, M, K, tok);
+  return QB200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM launch
+// ------------------------------------------------------------------------------------------------
+int device_sm_count() {
+  static int sms = -1;
+  if (sms < 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  }
+  return sms;
+}
+
+template <int TOK, int SPLIT>
+int launch_umma(const CUtensorMap& map, const qb200::GemmArgs& args, int m_tiles, cudaStream_t stream) {
+  using Cfg = qb200::TileCfg<TOK>;
+  auto kfn = qb200::w4a16_umma_kernel<TOK, SPLIT>;
+  static bool attr_set = false;   // per instantiation
+  if (!attr_set) {
+    QB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(args.N / qb200::kChan, m_tiles, SPLIT);
+  cfg.blockDim = dim3(qb200::kNumThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = SPLIT;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  QB_CUDA(cudaLaunchKernelEx(&cfg, kfn, map, args));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return QB200_OK;
+}
+
+template <int TOK>
+int dispatch_split(int split, const CUtensorMap& map, const qb200::GemmArgs& args, int m_tiles, cudaStream_t st) {
+  switch (split) {
+    case 1: return launch_umma<TOK, 1>(map, args, m_tiles, st);
+    case 2: return launch_umma<TOK, 2>(map, args, m_tiles, st);
+    case 4: return launch_umma<TOK, 4>(map, args, m_tiles, st);
+    case 8:
+      if constexpr (TOK <= 32) return launch_umma<TOK, 8>(map, args, m_tiles, st);
+      break;
+  }
+  return fail(QB200_EINVAL, "unsupported split %d for tok %d", split, TOK);
+}
+
+int check_device() {
+  static int ok = -1;
+  if (ok < 0) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail(QB200_ECUDA, "no CUDA device");
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    ok = (major == 10) ? 1 : 0;
+  }
+  if (!ok) return fail(QB200_ECUDA, "quick_b200 requires an sm_100a (B200) device; no fallback path exists");
+  return QB200_OK;
+}
+
+void plan(int M, int K, int N, int split_hint, int* tok_out, int* split_out) {
+  (void)split_hint;   // the reference's split_k_iters is accepted but only a hint
+  const int tok = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
+  const int tiles = (N / 128) * ((M + tok - 1) / tok);
+  const int KB = K / 64;
+  const int sms = device_sm_count();
+  const int max_split = tok <= 32 ? 8 : 4;
+  int split = 1;
+  // grow the cluster while the grid still under-fills the machine and every rank keeps >= 4 k-blocks
+  while (split * 2 <= max_split && tiles * split * 2 <= sms + sms / 4 && KB / (split * 2) >= 4) split *= 2;
+  *tok_out = tok;
+  *split_out = split;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* qb200_version(void) { return "quick_b200 0.1 (sm_100a tcgen05/TMEM/TMA W4A16)"; }
+const char* qb200_last_error(void) { return g_last_error.c_str(); }
+unsigned long long qb200_launch_count(void) { return g_launches.load(); }
+
+size_t qb200_wq_bytes(int K, int N) { return static_cast<size_t>(K) * N / 2; }
+size_t qb200_sz_bytes(int K, int N, int G) { return static_cast<size_t>(K / G) * N * 4; }
+
+int qb200_check_shape(int M, int K, int N, int G) {
+  if (M < 0 || K <= 0 || N <= 0 || G <= 0) return fail(QB200_EINVAL, "non-positive dimension");
+  if (N % 128 != 0) return fail(QB200_EINVAL, "OC is not multiple of cta_N = 128");
+  if (N % 8 != 0) return fail(QB200_EINVAL, "OC is not multiple of pack_num = 8");
+  if (G % 32 != 0) return fail(QB200_EINVAL, "Group size should be a multiple of 32");
+  if (K % G != 0) return fail(QB200_EINVAL, "IC is not a multiple of the group size");
+  if (K % 64 != 0) return fail(QB200_EINVAL, "IC is not a multiple of 64");
+  return QB200_OK;
+}
+
+int qb200_relayout_from_quick(const int32_t* qweight, const int32_t* qzeros, const void* scales, int K, int N, int G,
+                              uint32_t* wq, uint32_t* sz, void* stream) {
+  int rc = qb200_check_shape(1, K, N, G);
+  if (rc) return rc;
+  const size_t words = static_cast<size_t>(K) * N / 8;
+  relayout_wq_kernel<<<static_cast<unsigned>((words + 255) / 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint32_t*>(qweight), wq, K, N);
+  const size_t nsz = static_cast<size_t>(K / G) * N;
+  relayout_sz_kernel<<<static_cast<unsigned>((nsz + 255) / 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint32_t*>(qzeros), reinterpret_cast<const __half*>(scales), sz, K / G, N);
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  QB_CUDA(cudaGetLastError());
+  return QB200_OK;
+}
+
+int qb200_pack_quick(const uint8_t* q, const uint8_t* z, const void* s, int K, int N, int G, int32_t* qweight,
+                     int32_t* qzeros, void* scales, void* stream) {
+  int rc = qb200_check_shape(1, K, N, G);
+  if (rc) return rc;
+  const size_t words = static_cast<size_t>(K) * N / 8;
+  pack_qweight_kernel<<<static_cast<unsigned>((words + 255) / 256), 256, 0, as_stream(stream)>>>(
+      q, reinterpret_cast<uint32_t*>(qweight), K, N);
+  const size_t nz = static_cast<size_t>(K / G) * (N / 4);
+  pack_sz_kernel<<<static_cast<unsigned>((nz + 255) / 256), 256, 0, as_stream(stream)>>>(
+      z, reinterpret_cast<const __half*>(s), reinterpret_cast<uint32_t*>(qzeros), reinterpret_cast<__half*>(scales), K / G, N);
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  QB_CUDA(cudaGetLastError());
+  return QB200_OK;
+}
+
+int qb200_dequantize(const uint32_t* wq, const uint32_t* sz, int K, int N, int G, void* w16, void* stream) {
+  int rc = qb200_check_shape(1, K, N, G);
+  if (rc) return rc;
+  const size_t words = static_cast<size_t>(K) * N / 8;
+  dequant_kernel<<<static_cast<unsigned>((words + 255) / 256), 256, 0, as_stream(stream)>>>(
+      wq, sz, reinterpret_cast<__half*>(w16), K, N, G);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  QB_CUDA(cudaGetLastError());
+  return QB200_OK;
+}
+
+int qb200_gemm_plan(int M, int K, int N, int G, int split_k_hint, int* tok, int* split, int* ctas) {
+  int rc = qb200_check_shape(M, K, N, G);
+  if (rc) return rc;
+  int t, s;
+  plan(M, K, N, split_k_hint, &t, &s);
+  if (tok) *tok = t;
+  if (split) *split = s;
+  if (ctas) *ctas = (N / 128) * ((M + t - 1) / t) * s;
+  return QB200_OK;
+}
+
+int qb200_gemm_w4a16_cfg(const void* A, const uint32_t* wq, const uint32_t* sz, const void* bias, void* C, int M, int K,
+                         int N, int G, int tok, int split, void* stream) {
+  int rc = qb200_check_shape(M, K, N, G);
+  if (rc) return rc;
+  if (M == 0) return QB200_OK;
+  rc = check_device();
+  if (rc) return rc;
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(wq) & 15))
+    return fail(QB200_EINVAL, "A and wq must be 16-byte aligned");
+  const int KB = K / 64;
+  if (split < 1 || split > KB) return fail(QB200_EINVAL, "split %d out of range for K=%d", split, K);
+  const int kbps = (KB + split - 1) / split;
+  if ((split - 1) * kbps >= KB) return fail(QB200_EINVAL, "split %d leaves an empty k-range for K=%d", split, K);
+  const int m_tiles = (M + tok - 1) / tok;
+  if (m_tiles > 65535) return fail(QB200_EINVAL, "M too large for one launch");
+
+  CUtensorMap map;
+  rc = make_x_tensor_map(&map, A, M, K, tok);
+  if (rc) return rc;
+  qb200::GemmArgs args;
+  args.wq = wq;
+  args.sz = sz;
+  args.bias = reinterpret_cast<const __half*>(bias);
+  args.C = reinterpret_cast<__half*>(C);
+  args.M = M;
+  args.K = K;
+  args.N = N;
+  args.G = G;
+  args.kb_per_split = kbps;
+  cudaStream_t st = as_stream(stream);
+  switch (tok) {
+    case 16: return dispatch_split<16>(split, map, args, m_tiles, st);
+    case 32: return dispatch_split<32>(split, map, args, m_tiles, st);
+    case 64: return dispatch_split<64>(split, map, args, m_tiles, st);
+    case 128: return dispatch_split<128>(split, map, args, m_tiles, st);
+    case 256: return dispatch_split<256>(split, map, args, m_tiles, st);
+  }
+  return fail(QB200_EINVAL, "unsupported token tile %d", tok);
+}
+
+int qb200_gemm_w4a16(const void* A, const uint32_t* wq, const uint32_t* sz, const void* bias, void* C, int M, int K,
+                     int N, int G, int split_k_hint, void* stream) {
+  int rc = qb200_check_shape(M, K, N, G);
+  if (rc) return rc;
+  int tok, split;
+  plan(M, K, N, split_k_hint, &tok, &split);
+  return qb200_gemm_w4a16_cfg(A, wq, sz, bias, C, M, K, N, G, tok, split, stream);
+}
+
+int qb200_gemm_forward_quick(const void* A, const int32_t* qweight, const void* scales, const int32_t* qzeros, void* C,
+                             int M, int K, int N, int G, int split_k_iters, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  int rc = qb200_check_shape(M, K, N, G);
+  if (rc) return rc;
+  const size_t wqb = qb200_wq_bytes(K, N), szb = qb200_sz_bytes(K, N, G);
+  if (workspace == nullptr || workspace_bytes < wqb + szb)
+    return fail(QB200_ENOSPC, "workspace needs %zu bytes", wqb + szb);
+  uint32_t* wq = reinterpret_cast<uint32_t*>(workspace);
+  uint32_t* sz = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + wqb);
+  rc = qb200_relayout_from_quick(qweight, qzeros, scales, K, N, G, wq, sz, stream);
+  if (rc) return rc;
+  return qb200_gemm_w4a16(A, wq, sz, nullptr, C, M, K, N, G, split_k_iters, stream);
+}
+
+int qb200_gemm_w4a16_simt(const void* A, const uint32_t* wq, const uint32_t* sz, void* C, int M, int K, int N, int G,
+                          void* stream) {
+  int rc = qb200_check_shape(M, K, N, G);
+  if (rc) return rc;
+  if (M == 0) return QB200_OK;
+  if (static_cast<size_t>(K) * 2 > 48 * 1024) {
+    QB_CUDA(cudaFuncSetAttribute(gemm_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K * 2));
+  }
+  gemm_simt_kernel<<<dim3(N / 128, M), 128, static_cast<size_t>(K) * 2, as_stream(stream)>>>(
+      reinterpret_cast<const __half*>(A), wq, sz, reinterpret_cast<__half*>(C), M, K, N, G);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  QB_CUDA(cudaGetLastError());
+  return QB200_OK;
+}
+
+// ---- host-buffer handle ----
+struct qb200_linear {
+  int K, N, G, max_m, device;
+  uint32_t* wq;
+  uint32_t* sz;
+  __half* bias;
+  __half* x;
+  __half* y;
+  cudaStream_t stream;
+};
+
+int qb200_linear_create(qb200_linear** out, const int32_t* qweight_host, const int32_t* qzeros_host,
+                        const void* scales_host, const void* bias_host, int K, int N, int G, int max_m, int device) {
+  if (!out) return fail(QB200_EINVAL, "null out");
+  int rc = qb200_check_shape(max_m, K, N, G);
+  if (rc) return rc;
+  QB_CUDA(cudaSetDevice(device));
+  rc = check_device();
+  if (rc) return rc;
+  qb200_linear* h = new qb200_linear();
+  std::memset(h, 0, sizeof(*h));
+  h->K = K; h->N = N; h->G = G; h->max_m = max_m; h->device = device;
+  const size_t qw_b = static_cast<size_t>(K) * N / 2, qz_b = static_cast<size_t>(K / G) * N, sc_b = static_cast<size_t>(K / G) * N * 4;
+  void *dqw = nullptr, *dqz = nullptr, *dsc = nullptr;
+  QB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  QB_CUDA(cudaMalloc(&dqw, qw_b));
+  QB_CUDA(cudaMalloc(&dqz, qz_b));
+  QB_CUDA(cudaMalloc(&dsc, sc_b));
+  QB_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->wq), qb200_wq_bytes(K, N)));
+  QB_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->sz), qb200_sz_bytes(K, N, G)));
+  QB_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->x), static_cast<size_t>(max_m) * K * 2));
+  QB_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->y), static_cast<size_t>(max_m) * N * 2));
+  QB_CUDA(cudaMemcpyAsync(dqw, qweight_host, qw_b, cudaMemcpyHostToDevice, h->stream));
+  QB_CUDA(cudaMemcpyAsync(dqz, qzeros_host, qz_b, cudaMemcpyHostToDevice, h->stream));
+  QB_CUDA(cudaMemcpyAsync(dsc, scales_host, sc_b, cudaMemcpyHostToDevice, h->stream));
+  if (bias_host) {
+    QB_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->bias), static_cast<size_t>(N) * 2));
+    QB_CUDA(cudaMemcpyAsync(h->bias, bias_host, static_cast<size_t>(N) * 2, cudaMemcpyHostToDevice, h->stream));
+  }
+  rc = qb200_relayout_from_quick(reinterpret_cast<int32_t*>(dqw), reinterpret_cast<int32_t*>(dqz), dsc, K, N, G, h->wq,
+                                 h->sz, h->stream);
+  if (rc) return rc;
+  QB_CUDA(cudaStreamSynchronize(h->stream));
+  cudaFree(dqw); cudaFree(dqz); cudaFree(dsc);
+  *out = h;
+  return QB200_OK;
+}
+
+int qb200_linear_forward(qb200_linear* h, const void* x_dev, void* y_dev, int M, void* stream) {
+  if (!h) return fail(QB200_EINVAL, "null handle");
+  return qb200_gemm_w4a16(x_dev, h->wq, h->sz, h->bias, y_dev, M, h->K, h->N, h->G, 0, stream);
+}
+
+int qb200_linear_forward_host(qb200_linear* h, const void* x_host, void* y_host, int M) {
+  if (!h) return fail(QB200_EINVAL, "null handle");
+  if (M > h->max_m) return fail(QB200_EINVAL, "M=%d exceeds the handle's max_m=%d", M, h->max_m);
+  if (M == 0) return QB200_OK;
+  QB_CUDA(cudaMemcpyAsync(h->x, x_host, static_cast<size_t>(M) * h->K * 2, cudaMemcpyHostToDevice, h->stream));
+  int rc = qb200_gemm_w4a16(h->x, h->wq, h->sz, h->bias, h->y, M, h->K, h->N, h->G, 0, h->stream);
+  if (rc) return rc;
+  QB_CUDA(cudaMemcpyAsync(y_host, h->y, static_cast<size_t>(M) * h->N * 2, cudaMemcpyDeviceToHost, h->stream));
+  QB_CUDA(cudaStreamSynchronize(h->stream));
+  return QB200_OK;
+}
+
+void qb200_linear_destroy(qb200_linear* h) {
+  if (!h) return;
+  cudaFree(h->wq); cudaFree(h->sz); cudaFree(h->bias); cudaFree(h->x); cudaFree(h->y);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+}  // extern "C"

@@ -1,0 +1,483 @@
+// quick_b200 — tcgen05 / TMEM / TMA W4A16 grouped GEMM for sm_100a.
+//
+// Computes  C[M][N] = A[M][K] (fp16) · W16[K][N],  W16 = fp16(q - z) * s  (one rounding,
+// bit-identical to what the reference materialises in registers: csrc/gemm_cuda_quick.cu:52-60),
+// fp32 accumulation in TMEM, one final fp16 rounding.
+//
+// Blackwell mapping (not a port of the reference's mma.sync fragment scheme):
+//   * swap A/B:  D^T[128 channels][TOK tokens] += W^T[128][16] · X^T[16][TOK]
+//       - UMMA M = 128 output channels = 128 TMEM lanes, UMMA N = TOK tokens, K = 16 / instruction
+//       - the WEIGHTS are the A operand and are sourced from TMEM (tcgen05.mma [d],[a_tmem],b_desc):
+//         dequantised fragments go registers -> tcgen05.st -> tensor core, never through shared memory
+//       - the ACTIVATIONS are the B operand in shared memory (K-major, 128B swizzle) loaded by TMA
+//   * packed weights in the "B200 layout" (see include/quick_b200.h): one thread = one TMEM lane =
+//     one output channel, its 16-byte shared-memory read = 32 consecutive k = 16 TMEM columns
+//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = dequant
+//     (two warpgroups alternating k64 stages) and epilogue
+//   * split-K lives inside a thread-block cluster (1,1,SPLIT): partial tiles are exchanged through
+//     distributed shared memory, each CTA reduces and stores TOK/SPLIT token columns; no HBM temp,
+//     no second kernel (reference: (split_k,M,N) temp + at::sum, gemm_cuda_quick.cu:1468,1515)
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace qb200 {
+
+constexpr int kChan = 128;          // channels per tile = UMMA M
+constexpr int kBK = 64;             // k per pipeline stage
+constexpr int kWStageBytes = kChan * kBK / 2;   // 4096
+constexpr int kTStages = 4;         // A-operand stages in TMEM (32 columns each)
+constexpr int kNumThreads = 320;    // 10 warps
+constexpr int kNumDequantWarps = 8;
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+#ifndef QB200_WAIT_TIMEOUT_CYCLES
+#define QB200_WAIT_TIMEOUT_CYCLES 4000000000ll  // ~2 s: a lost barrier traps instead of hanging the GPU
+#endif
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  bool timed = false;
+  while (true) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (!timed) { t0 = clock64(); timed = true; }
+    else if (clock64() - t0 > QB200_WAIT_TIMEOUT_CYCLES) { __trap(); }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// 2-D tiled TMA load (SASS: UTMALDG)
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// TMEM management (one warp)
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[tmem] · B[smem desc]   (SASS: UTCHMMA)
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// registers -> TMEM, 16 consecutive 32-bit columns of this thread's lane (SASS: STTM)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// TMEM -> registers, NCOL consecutive 32-bit columns of this thread's lane (SASS: LDTM)
+template <int NCOL>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t* r) {
+  if constexpr (NCOL == 1) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(taddr) : "memory");
+  } else if constexpr (NCOL == 2) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+  } else if constexpr (NCOL == 4) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+  } else if constexpr (NCOL == 8) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+  } else {
+    static_assert(NCOL == 16, "tmem_ld: 1,2,4,8,16 columns");
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+        "[%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+  }
+}
+
+// cluster helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 4-bit unpack.  One B200-layout word = 8 consecutive k of one channel, nibble order
+// k0,k2,k4,k6,k1,k3,k5,k7, so the lop3 extraction yields (k0,k1) (k2,k3) (k4,k5) (k6,k7) as half2.
+//   bottom nibbles: (w & 0x000f000f) | 0x6400_6400 = 1024 + q          -> sub (1024 + z)        = q - z
+//   top    nibbles: (w & 0x00f000f0) | 0x6400_6400 = 1024 + 16 q       -> fma(·, 1/16, -(64+z)) = q - z
+// both exact in fp16; then one mul.rn by the scale == the reference's sub.f16x2 + mul.rn.f16x2
+// (gemm_cuda_quick.cu:53-54) on the reference's 1024+q / 1024+z operands (dequantize_quick.cuh:35-60).
+// ------------------------------------------------------------------------------------------------
+struct GroupConsts {
+  uint32_t zb;   // (1024 + z) x2
+  uint32_t zt;   // -(64 + z)  x2
+  uint32_t sc;   // scale      x2
+};
+__device__ __forceinline__ GroupConsts make_group_consts(uint32_t szw) {
+  GroupConsts g;
+  asm("prmt.b32 %0, %1, %1, 0x1010;" : "=r"(g.sc) : "r"(szw));   // low half duplicated
+  asm("prmt.b32 %0, %1, %1, 0x3232;" : "=r"(g.zb) : "r"(szw));   // high half duplicated
+  const uint32_t k960 = 0x63806380u;                              // 960 x2
+  asm("sub.f16x2 %0, %1, %2;" : "=r"(g.zt) : "r"(k960), "r"(g.zb));   // 960 - (1024+z) = -(64+z), exact
+  return g;
+}
+__device__ __forceinline__ void dequant_word(uint32_t w, const GroupConsts& g, uint32_t* out) {
+  constexpr uint32_t kLut = (0xf0 & 0xcc) | 0xaa;   // (a & b) | c
+  const uint32_t top = w >> 8;
+  uint32_t h0, h1, h2, h3;
+  asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(h0) : "r"(w), "n"(0x000f000f), "n"(0x64006400), "n"(kLut));
+  asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(h1) : "r"(w), "n"(0x00f000f0), "n"(0x64006400), "n"(kLut));
+  asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(h2) : "r"(top), "n"(0x000f000f), "n"(0x64006400), "n"(kLut));
+  asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(h3) : "r"(top), "n"(0x00f000f0), "n"(0x64006400), "n"(kLut));
+  const uint32_t k16th = 0x2c002c00u;   // 1/16 x2
+  asm("sub.f16x2 %0, %1, %2;" : "=r"(h0) : "r"(h0), "r"(g.zb));
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(h1) : "r"(h1), "r"(k16th), "r"(g.zt));
+  asm("sub.f16x2 %0, %1, %2;" : "=r"(h2) : "r"(h2), "r"(g.zb));
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(h3) : "r"(h3), "r"(k16th), "r"(g.zt));
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(out[0]) : "r"(h0), "r"(g.sc));
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(out[1]) : "r"(h1), "r"(g.sc));
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(out[2]) : "r"(h2), "r"(g.sc));
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(out[3]) : "r"(h3), "r"(g.sc));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Descriptors
+// ------------------------------------------------------------------------------------------------
+// Shared-memory matrix descriptor, K-major, SWIZZLE_128B, rows of 64 fp16 (128 B), 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);   // start address
+  d |= static_cast<uint64_t>(1) << 16;                     // leading byte offset (unused for swizzled K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;             // stride byte offset
+  d |= static_cast<uint64_t>(1) << 46;                     // descriptor version (sm_100)
+  d |= static_cast<uint64_t>(2) << 61;                     // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor: kind::f16, A = B = fp16, D = fp32, both K-major, M = 128, N = n.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
+  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+}
+
+template <int TOK>
+struct TileCfg {
+  static constexpr int kXStageBytes = TOK * 128;
+  static constexpr int kStageBytes = kXStageBytes + kWStageBytes;
+  static constexpr int kACol0 = TOK < 32 ? 32 : TOK;
+  static constexpr int kColsNeeded = kACol0 + 32 * kTStages;
+  static constexpr int kTmemCols = kColsNeeded <= 32 ? 32 : kColsNeeded <= 64 ? 64 : kColsNeeded <= 128 ? 128
+                                   : kColsNeeded <= 256 ? 256 : 512;
+  // pipeline depth: keep whole split-K slabs in flight for small tiles (HBM latency bound),
+  // 4-5 stages for the tensor-bound tiles
+  static constexpr int kStages = TOK == 16 ? 16 : TOK == 32 ? 12 : TOK == 64 ? 8 : TOK == 128 ? 6 : 5;
+  static constexpr int kBarBytes = (2 * kStages + 2 * kTStages + 1) * 8 + 16;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;   // + manual 1024-B alignment slack
+  static_assert(kStages * kXStageBytes >= kChan * TOK * 4 || true, "");
+};
+
+struct GemmArgs {
+  const uint32_t* wq;
+  const uint32_t* sz;
+  const __half* bias;
+  __half* C;
+  int M, K, N, G;
+  int kb_per_split;
+};
+
+// ------------------------------------------------------------------------------------------------
+// The kernel
+// ------------------------------------------------------------------------------------------------
+template <int TOK, int SPLIT>
+__global__ void __launch_bounds__(kNumThreads, 1)
+w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs args) {
+  using Cfg = TileCfg<TOK>;
+  constexpr int STAGES = Cfg::kStages;
+  constexpr int SLICE = TOK / SPLIT;          // token columns owned by one cluster rank
+  constexpr int CH = SLICE / 2;               // columns per (owner, warpgroup)
+  static_assert(CH >= 1, "TOK / SPLIT must be >= 2");
+  constexpr int PIECE = CH < 16 ? CH : 16;    // columns per tcgen05.ld
+  static_assert(SPLIT == 1 || STAGES * Cfg::kXStageBytes >= kChan * TOK * 4, "reduction buffer must fit the X stages");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_x = smem_base;                                   // STAGES x [TOK rows][128 B] swizzled
+  const uint32_t smem_w = smem_base + STAGES * Cfg::kXStageBytes;      // STAGES x [2][128][16 B]
+  const uint32_t bar_base = smem_w + STAGES * kWStageBytes;
+  const uint32_t bar_full = bar_base;                                  // TMA landed (W + X)
+  const uint32_t bar_empty = bar_full + 8 * STAGES;                    // stage free: 4 dequant warps + 1 MMA commit
+  const uint32_t bar_tfull = bar_empty + 8 * STAGES;                   // A operand written to TMEM stage
+  const uint32_t bar_tempty = bar_tfull + 8 * kTStages;                // MMAs reading the TMEM stage done
+  const uint32_t bar_accum = bar_tempty + 8 * kTStages;                // all MMAs of the tile done
+  const uint32_t tmem_ptr_smem = bar_accum + 8;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nt = blockIdx.x;
+  const int mt = blockIdx.y;
+  const int rank = SPLIT > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int KB = args.K / kBK;
+  const int kb0 = rank * args.kb_per_split;
+  const int nkb = min(args.kb_per_split, KB - kb0);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(bar_full + 8 * i, 1);
+      mbar_init(bar_empty + 8 * i, 5);
+    }
+    for (int i = 0; i < kTStages; ++i) {
+      mbar_init(bar_tfull + 8 * i, 4);
+      mbar_init(bar_tempty + 8 * i, 1);
+    }
+    mbar_init(bar_accum, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+    prefetch_tmap(&tmap_x);
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem) : "memory");
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const uint32_t* wsrc = args.wq + (static_cast<size_t>(nt) * KB + kb0) * (kWStageBytes / 4);
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::kStageBytes);
+        bulk_g2s(smem_w + s * kWStageBytes, wsrc + static_cast<size_t>(it) * (kWStageBytes / 4), kWStageBytes,
+                 bar_full + 8 * s);
+        tma_load_2d(smem_x + s * Cfg::kXStageBytes, &tmap_x, bar_full + 8 * s, (kb0 + it) * kBK, mt * TOK);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(TOK);
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        const int t = it % kTStages;
+        const uint32_t tph = (it / kTStages) & 1;
+        mbar_wait(bar_full + 8 * s, ph);
+        mbar_wait(bar_tfull + 8 * t, tph);
+        tc_fence_after();
+        const uint64_t bdesc = make_smem_desc_sw128(smem_x + s * Cfg::kXStageBytes);
+        const uint32_t a_tmem = tmem_base + Cfg::kACol0 + t * 32;
+#pragma unroll
+        for (int j = 0; j < kBK / 16; ++j) {
+          // +32 B (= 2 in 16-B units) of start address per k16 step inside the 128-B swizzle row
+          umma_f16_ts(tmem_base, a_tmem + j * 8, bdesc + 2 * j, idesc, (it | j) != 0 ? 1u : 0u);
+        }
+        umma_commit(bar_empty + 8 * s);    // X stage (and with the dequant arrivals, the whole stage) free
+        umma_commit(bar_tempty + 8 * t);   // TMEM A stage free
+      }
+      umma_commit(bar_accum);
+    }
+    __syncwarp();
+  } else {
+    // ===================== dequant warps: smem nibbles -> registers -> TMEM A operand =====================
+    const int wg = (warp - 2) >> 2;                 // warpgroup 0/1 takes even/odd stages
+    const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
+    const int ch = quad * 32 + lane;                // output channel within the tile = TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+    const int NG = args.K / args.G;
+    const uint32_t* szp = args.sz + static_cast<size_t>(nt) * NG * kChan + ch;
+    for (int it = wg; it < nkb; it += 2) {
+      const int s = it % STAGES;
+      const uint32_t ph = (it / STAGES) & 1;
+      const int t = it % kTStages;
+      const uint32_t tph = (it / kTStages) & 1;
+      const int k0 = (kb0 + it) * kBK;
+      const uint32_t sz0 = __ldg(szp + static_cast<size_t>(k0 / args.G) * kChan);
+      const uint32_t sz1 = __ldg(szp + static_cast<size_t>((k0 + 32) / args.G) * kChan);
+      mbar_wait(bar_full + 8 * s, ph);
+      const uint4 w0 = lds128(smem_w + s * kWStageBytes + ch * 16);
+      const uint4 w1 = lds128(smem_w + s * kWStageBytes + 2048 + ch * 16);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+      uint32_t r[32];
+      {
+        const GroupConsts g0 = make_group_consts(sz0);
+        dequant_word(w0.x, g0, r + 0);
+        dequant_word(w0.y, g0, r + 4);
+        dequant_word(w0.z, g0, r + 8);
+        dequant_word(w0.w, g0, r + 12);
+        const GroupConsts g1 = make_group_consts(sz1);
+        dequant_word(w1.x, g1, r + 16);
+        dequant_word(w1.y, g1, r + 20);
+        dequant_word(w1.z, g1, r + 24);
+        dequant_word(w1.w, g1, r + 28);
+      }
+      mbar_wait(bar_tempty + 8 * t, tph ^ 1);
+      tc_fence_after();
+      const uint32_t a_tmem = tmem_base + lane_addr + Cfg::kACol0 + t * 32;
+      tmem_st16(a_tmem, r);
+      tmem_st16(a_tmem + 16, r + 16);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tfull + 8 * t);
+    }
+  }
+
+  // ===================== epilogue =====================
+  const int quad = warp & 3;
+  const int wg = (warp - 2) >> 2;
+  const int ch = quad * 32 + lane;
+  const uint32_t d_tmem = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+  const int n = nt * kChan + ch;
+  const float bias_v = (args.bias != nullptr && warp >= 2) ? __half2float(args.bias[n]) : 0.f;
+
+  if constexpr (SPLIT == 1) {
+    if (warp >= 2) {
+      mbar_wait(bar_accum, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int p = 0; p < CH / PIECE; ++p) {
+        const int col0 = wg * CH + p * PIECE;
+        uint32_t v[PIECE];
+        tmem_ld<PIECE>(d_tmem + col0, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < PIECE; ++i) {
+          const int m = mt * TOK + col0 + i;
+          if (m < args.M) args.C[static_cast<size_t>(m) * args.N + n] = __float2half_rn(__uint_as_float(v[i]) + bias_v);
+        }
+      }
+    }
+  } else {
+    // reduction buffer aliases the (now dead) X stages: [src rank][SLICE columns][128 channels] fp32
+    if (warp >= 2) {
+      mbar_wait(bar_accum, 0);   // every TMA write landed and every MMA read of this CTA's smem is complete
+      tc_fence_after();
+    }
+    cluster_arrive();
+    cluster_wait();              // every CTA of the cluster is past its main loop
+    if (warp >= 2) {
+#pragma unroll 1
+      for (int o = 0; o < SPLIT; ++o) {
+        const uint32_t dst_cta = mapa_shared(smem_x, static_cast<uint32_t>(o));
+#pragma unroll 1
+        for (int p = 0; p < CH / PIECE; ++p) {
+          const int j0 = wg * CH + p * PIECE;                 // column inside the owner's slice
+          uint32_t v[PIECE];
+          tmem_ld<PIECE>(d_tmem + o * SLICE + j0, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < PIECE; ++i) {
+            const uint32_t off = static_cast<uint32_t>(((rank * SLICE + j0 + i) * kChan + ch) * 4);
+            st_cluster_f32(dst_cta + off, __uint_as_float(v[i]));
+          }
+        }
+      }
+    }
+    cluster_arrive();
+    cluster_wait();              // all partial slices have landed in their owners' shared memory
+    if (warp >= 2) {
+#pragma unroll 1
+      for (int i = 0; i < CH; ++i) {
+        const int j = wg * CH + i;
+        float acc = bias_v;
+#pragma unroll
+        for (int r = 0; r < SPLIT; ++r) acc += lds_f32(smem_x + static_cast<uint32_t>(((r * SLICE + j) * kChan + ch) * 4));
+        const int m = mt * TOK + rank * SLICE + j;
+        if (m < args.M) args.C[static_cast<size_t>(m) * args.N + n] = __float2half_rn(acc);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+}  // namespace qb200

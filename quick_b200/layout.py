@@ -1,0 +1,138 @@
+"""Host-side QUICK layout algebra in vectorised torch (works on CPU or CUDA tensors).
+
+This is the product's own restatement of the packed operand format the reference defines in
+quick/awq/modules/linear/quick.py:52-54 (shapes) and :88-150 (interleave), used where no GPU is
+involved (building modules on CPU, sharding, concatenation).  On the GPU the same transform is
+``quick_b200.ops.pack_quick`` (C-ABI ``qb200_pack_quick``).  The closed form:
+
+  qweight word  f = kt*4N + (2*ty + l//16)*N + bx*128 + (l%16)*8 + ks*4 + ch
+    holds, in nibble p, q[k0 + DK[p]][c0 + DC[p]],  k0 = 32kt + 16ks + 2(l%4),  c0 = 128bx + 64ty + 16ch + l//4
+  scale/zero slot x of a row -> column 128bx + 64ty + 16(m//2) + 8(m%2) + 4lh + j4
+"""
+from __future__ import annotations
+
+import torch
+
+_DK = (0, 8, 0, 8, 1, 9, 1, 9)
+_DC = (0, 0, 8, 8, 0, 0, 8, 8)
+
+
+def _word_coords(K: int, N: int, device):
+    f = torch.arange(K * N // 8, device=device, dtype=torch.int64)
+    kt = f // (4 * N)
+    r = f % (4 * N)
+    r4 = r // N
+    c = r % N
+    bx = c // 128
+    w = c % 128
+    lane = 16 * (r4 % 2) + w // 8
+    ty = r4 // 2
+    ks = (w % 8) // 4
+    ch = w % 4
+    k0 = 32 * kt + 16 * ks + 2 * (lane % 4)
+    c0 = 128 * bx + 64 * ty + 16 * ch + lane // 4
+    return k0, c0
+
+
+def slot_to_column(N: int, device=None) -> torch.Tensor:
+    x = torch.arange(N, device=device, dtype=torch.int64)
+    nb = N // 128
+    ty = x // (N // 2)
+    lh = (x // (N // 4)) % 2
+    bx = (x // 32) % nb
+    j4 = (x % 32) // 8
+    m = x % 8
+    return 128 * bx + 64 * ty + 16 * (m // 2) + 8 * (m % 2) + 4 * lh + j4
+
+
+def _to_i32(u: torch.Tensor) -> torch.Tensor:
+    """int64 holding a uint32 bit pattern -> int32 with the same bits."""
+    return torch.where(u >= 2 ** 31, u - 2 ** 32, u).to(torch.int32)
+
+
+def pack_quick(q: torch.Tensor, z: torch.Tensor, s: torch.Tensor):
+    """q[K,N], z[K/G,N] integer 0..15, s[K/G,N] -> (qweight, qzeros, scales) in the reference's shapes."""
+    K, N = q.shape
+    if N % 128 != 0:
+        raise ValueError("OC is not multiple of cta_N = 128")
+    if K % 32 != 0:
+        raise ValueError("IC is not a multiple of 32")
+    dev = q.device
+    k0, c0 = _word_coords(K, N, dev)
+    q64 = q.to(torch.int64)
+    word = torch.zeros(K * N // 8, dtype=torch.int64, device=dev)
+    for p in range(8):
+        word |= (q64[k0 + _DK[p], c0 + _DC[p]] & 0xF) << (4 * p)
+    qweight = _to_i32(word).reshape(K // 4, N // 2).contiguous()
+    col = slot_to_column(N, dev)
+    scales = s.to(torch.float16)[:, col].repeat_interleave(2, dim=1).contiguous()
+    z4 = (z.to(torch.int64)[:, col] & 0xF).reshape(z.shape[0], N // 4, 4)
+    zw = z4[..., 0] | (z4[..., 1] << 4) | (z4[..., 2] << 8) | (z4[..., 3] << 12)
+    zw = zw | (zw << 16)
+    qzeros = _to_i32(zw).contiguous()
+    return qweight, qzeros, scales
+
+
+def unpack_quick(qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor):
+    """Inverse of pack_quick -> (q int32 [K,N], z int32 [K/G,N], s fp16 [K/G,N])."""
+    K, N = qweight.shape[0] * 4, qweight.shape[1] * 2
+    NG = qzeros.shape[0]
+    dev = qweight.device
+    word = qweight.reshape(-1).to(torch.int64) & 0xFFFFFFFF
+    k0, c0 = _word_coords(K, N, dev)
+    q = torch.zeros((K, N), dtype=torch.int32, device=dev)
+    for p in range(8):
+        q[k0 + _DK[p], c0 + _DC[p]] = ((word >> (4 * p)) & 0xF).to(torch.int32)
+    col = slot_to_column(N, dev)
+    s = torch.zeros((NG, N), dtype=torch.float16, device=dev)
+    s[:, col] = scales[:, 0::2]
+    zw = qzeros.to(torch.int64) & 0xFFFFFFFF
+    z = torch.zeros((NG, N), dtype=torch.int32, device=dev)
+    for i in range(4):
+        z[:, col[i::4]] = ((zw >> (4 * i)) & 0xF).to(torch.int32)
+    return q, z, s
+
+
+def quick_cat(tensors, options: str) -> torch.Tensor:
+    """N-concatenation of packed tensors (reference QUICK_cat, fused_utils.py:119-159), also for
+    unequal widths (GQA k/v projections), which the reference rejects (fused_utils.py:139-142)."""
+    if len(tensors) < 2:
+        raise ValueError("At least two input layers are required")
+    H = tensors[0].shape[0]
+    for t in tensors[1:]:
+        if t.shape[0] != H:
+            raise ValueError("All input layers must have the same number of rows")
+    if options == "qweight":
+        rows = H // 2
+    elif options in ("qzeros", "scales"):
+        rows = H * 4
+    else:
+        raise ValueError("Unknown options provided or invalid reshape dimensions")
+    return torch.cat([t.reshape(rows, -1) for t in tensors], dim=1).reshape(H, -1)
+
+
+def shard_columns(qweight, qzeros, scales, rank: int, world: int):
+    """Column-parallel (N) shard of a packed weight: the inverse slice of quick_cat."""
+    K, N = qweight.shape[0] * 4, qweight.shape[1] * 2
+    NG = qzeros.shape[0]
+    if N % world != 0 or (N // world) % 128 != 0:
+        raise ValueError(f"N={N} cannot be split into {world} shards of 128-column tiles")
+    n0, n1 = rank * N // world, (rank + 1) * N // world
+    qw = qweight.reshape(K // 8, N)[:, n0:n1].reshape(K // 4, -1).contiguous()
+    sc = scales.reshape(4 * NG, N // 2)[:, n0 // 2:n1 // 2].reshape(NG, -1).contiguous()
+    qz = qzeros.reshape(4 * NG, N // 16)[:, n0 // 16:n1 // 16].reshape(NG, -1).contiguous()
+    return qw, qz, sc
+
+
+def quantize_rtn(W: torch.Tensor, G: int):
+    """Asymmetric uint4 round-to-nearest of W[N,K] per group of G input channels: the q/z/s semantics
+    of the reference's pseudo_quantize_tensor (quick/awq/quantize/quantizer.py:46-72).
+    Returns q[K,N] int32, z[K/G,N] int32, s[K/G,N] fp16."""
+    N, K = W.shape
+    w = W.float().reshape(N, K // G, G)
+    mx, mn = w.amax(dim=2, keepdim=True), w.amin(dim=2, keepdim=True)
+    s = ((mx - mn).clamp(min=1e-5) / 15).half().float()
+    z = (-torch.round(mn / s)).clamp(0, 15)
+    q = torch.clamp(torch.round(w / s) + z, 0, 15)
+    return (q.reshape(N, K).t().contiguous().to(torch.int32), z.squeeze(2).t().contiguous().to(torch.int32),
+            s.squeeze(2).t().contiguous().half())

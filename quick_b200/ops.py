@@ -1,0 +1,173 @@
+"""Thin torch-facing wrappers over the C-ABI (include/quick_b200.h).
+
+torch is used only for device memory and the current stream; every function below passes raw
+device pointers and sizes to libquick_b200.so.  CUDA tensors are required — there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.QuickB200Error("quick_b200 ops need CUDA tensors (no CPU fallback exists)")
+
+
+def shapes_from_quick(x_or_K, qweight, qzeros, scales):
+    """Derive (K, N, G) the way the reference does (gemm_cuda_quick.cu:1468,:1477)."""
+    K = int(x_or_K) if isinstance(x_or_K, int) else int(x_or_K.shape[-1])
+    N = int(qweight.shape[1]) // 4 * 8
+    G = K // int(scales.shape[0])
+    return K, N, G
+
+
+def prepack(qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor, K: int | None = None):
+    """QUICK layout -> B200 layout.  Returns (wq int32 flat, sz int32 flat, K, N, G)."""
+    _require_cuda(qweight, qzeros, scales)
+    lib = _lib.load()
+    K = int(qweight.shape[0]) * 4 if K is None else K
+    _, N, G = shapes_from_quick(K, qweight, qzeros, scales)
+    _lib.check(lib.qb200_check_shape(1, K, N, G))
+    qweight, qzeros, scales = qweight.contiguous(), qzeros.contiguous(), scales.contiguous()
+    wq = torch.empty(lib.qb200_wq_bytes(K, N) // 4, dtype=torch.int32, device=qweight.device)
+    sz = torch.empty(lib.qb200_sz_bytes(K, N, G) // 4, dtype=torch.int32, device=qweight.device)
+    with torch.cuda.device(qweight.device):
+        _lib.check(lib.qb200_relayout_from_quick(_ptr(qweight), _ptr(qzeros), _ptr(scales), K, N, G,
+                                                 _ptr(wq), _ptr(sz), _stream_ptr()))
+    return wq, sz, K, N, G
+
+
+def pack_quick(q: torch.Tensor, z: torch.Tensor, s: torch.Tensor, G: int):
+    """Logical (q uint8 [K,N], z uint8 [K/G,N], s fp16 [K/G,N]) -> QUICK-layout tensors, on the GPU."""
+    _require_cuda(q, z, s)
+    lib = _lib.load()
+    K, N = q.shape
+    _lib.check(lib.qb200_check_shape(1, K, N, G))
+    q = q.to(torch.uint8).contiguous()
+    z = z.to(torch.uint8).contiguous()
+    s = s.to(torch.float16).contiguous()
+    qweight = torch.empty((K // 4, N // 2), dtype=torch.int32, device=q.device)
+    qzeros = torch.empty((K // G, N // 4), dtype=torch.int32, device=q.device)
+    scales = torch.empty((K // G, 2 * N), dtype=torch.float16, device=q.device)
+    with torch.cuda.device(q.device):
+        _lib.check(lib.qb200_pack_quick(_ptr(q), _ptr(z), _ptr(s), K, N, G, _ptr(qweight), _ptr(qzeros), _ptr(scales),
+                                        _stream_ptr()))
+    return qweight, qzeros, scales
+
+
+def dequantize(wq: torch.Tensor, sz: torch.Tensor, K: int, N: int, G: int) -> torch.Tensor:
+    """B200 layout -> W16 [K, N] fp16 (bit-identical to the reference's in-register weights)."""
+    _require_cuda(wq, sz)
+    lib = _lib.load()
+    W = torch.empty((K, N), dtype=torch.float16, device=wq.device)
+    with torch.cuda.device(wq.device):
+        _lib.check(lib.qb200_dequantize(_ptr(wq), _ptr(sz), K, N, G, _ptr(W), _stream_ptr()))
+    return W
+
+
+def gemm(x: torch.Tensor, wq: torch.Tensor, sz: torch.Tensor, N: int, G: int, bias: torch.Tensor | None = None,
+         tok: int | None = None, split: int | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """y[M,N] = x[M,K] · W (+bias) through the tcgen05 kernel. tok/split force a tile config."""
+    _require_cuda(x, wq, sz, bias)
+    lib = _lib.load()
+    assert x.dim() == 2 and x.dtype == torch.float16
+    x = x.contiguous()
+    M, K = x.shape
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float16, device=x.device)
+    with torch.cuda.device(x.device):
+        if tok is None and split is None:
+            rc = lib.qb200_gemm_w4a16(_ptr(x), _ptr(wq), _ptr(sz), _ptr(bias), _ptr(out), M, K, N, G, 0, _stream_ptr())
+        else:
+            p_tok, p_split, p_ctas = C.c_int(), C.c_int(), C.c_int()
+            _lib.check(lib.qb200_gemm_plan(M, K, N, G, 0, C.byref(p_tok), C.byref(p_split), C.byref(p_ctas)))
+            rc = lib.qb200_gemm_w4a16_cfg(_ptr(x), _ptr(wq), _ptr(sz), _ptr(bias), _ptr(out), M, K, N, G,
+                                          tok or p_tok.value, split or p_split.value, _stream_ptr())
+    _lib.check(rc)
+    return out
+
+
+def gemm_simt(x: torch.Tensor, wq: torch.Tensor, sz: torch.Tensor, N: int, G: int) -> torch.Tensor:
+    """CUDA-core cross-check of the same contraction (tests only)."""
+    _require_cuda(x, wq, sz)
+    lib = _lib.load()
+    x = x.contiguous()
+    M, K = x.shape
+    out = torch.empty((M, N), dtype=torch.float16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.qb200_gemm_w4a16_simt(_ptr(x), _ptr(wq), _ptr(sz), _ptr(out), M, K, N, G, _stream_ptr()))
+    return out
+
+
+def plan(M: int, K: int, N: int, G: int, split_hint: int = 0):
+    lib = _lib.load()
+    tok, split, ctas = C.c_int(), C.c_int(), C.c_int()
+    _lib.check(lib.qb200_gemm_plan(M, K, N, G, split_hint, C.byref(tok), C.byref(split), C.byref(ctas)))
+    return tok.value, split.value, ctas.value
+
+
+def gemm_forward_quick_stateless(x, qweight, scales, qzeros, split_k_iters: int = 8) -> torch.Tensor:
+    """qb200_gemm_forward_quick: relayout into a scratch workspace + GEMM, no caching."""
+    _require_cuda(x, qweight, scales, qzeros)
+    lib = _lib.load()
+    x = x.contiguous()
+    M, K = x.shape
+    _, N, G = shapes_from_quick(K, qweight, qzeros, scales)
+    _lib.check(lib.qb200_check_shape(M, K, N, G))
+    nbytes = lib.qb200_wq_bytes(K, N) + lib.qb200_sz_bytes(K, N, G)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    out = torch.empty((M, N), dtype=torch.float16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.qb200_gemm_forward_quick(_ptr(x), _ptr(qweight.contiguous()), _ptr(scales.contiguous()),
+                                                _ptr(qzeros.contiguous()), _ptr(out), M, K, N, G, split_k_iters,
+                                                _ptr(ws), nbytes, _stream_ptr()))
+    return out
+
+
+class HostLinear:
+    """qb200_linear handle: HOST buffers in, HOST buffers out (H2D + kernel + D2H inside the call)."""
+
+    def __init__(self, qweight, qzeros, scales, bias=None, max_m: int = 512, device: int = 0):
+        lib = _lib.load()
+        qweight, qzeros, scales = (t.cpu().contiguous() for t in (qweight, qzeros, scales))
+        self.K = int(qweight.shape[0]) * 4
+        _, self.N, self.G = shapes_from_quick(self.K, qweight, qzeros, scales)
+        self.max_m = max_m
+        bias = None if bias is None else bias.cpu().contiguous()
+        h = C.c_void_p()
+        _lib.check(lib.qb200_linear_create(C.byref(h), _ptr(qweight), _ptr(qzeros), _ptr(scales), _ptr(bias),
+                                           self.K, self.N, self.G, max_m, device))
+        self._h = h
+        self._lib = lib
+
+    def forward_host(self, x_host: torch.Tensor, y_host: torch.Tensor | None = None) -> torch.Tensor:
+        assert not x_host.is_cuda and x_host.dtype == torch.float16 and x_host.is_contiguous()
+        M = x_host.shape[0]
+        if y_host is None:
+            y_host = torch.empty((M, self.N), dtype=torch.float16, pin_memory=True)
+        _lib.check(self._lib.qb200_linear_forward_host(self._h, _ptr(x_host), _ptr(y_host), M))
+        return y_host
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.qb200_linear_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
