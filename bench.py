@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py — W4A16 GEMM TOPS vs M (K=N=4096, g=128), the metric of BASELINE.json (configs[1]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of synthetic input: the full sweep
+M in {1,8,16,64,128,256,512} against each of 40 distinct packed weight sets (≈360 MB of weights,
+larger than the 126 MB L2, so every GEMM streams its weights from HBM — "cold").  280 GEMM launches.
+
+  value  whole-job TOPS (sum of 2·M·N·K over the step / device time), inputs resident in HBM,
+         CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+  e2e    the same metric through the C-ABI host-buffer call (qb200_linear_forward_host): activations
+         copied from pinned host memory and results copied back inside the timed region, every GEMM.
+  roofline / sweep   per-M device time (events between the M groups), achieved TFLOP/s or GB/s against
+         MEASURED_PEAKS.json.
+  cpu_baseline  dequantize + torch.matmul on the host cores (oracle "port"), bounded sample, rank 0, N=1.
+
+--impl reference times the UNMODIFIED reference CUDA kernel (oracle/_ref, built from
+/root/reference/csrc by oracle/build_ref.py) on this GPU through its own pybind API, same workload.
+If that binary is absent it falls back to the CPU oracle port and says so.
+
+N > 1 (torchrun): every rank owns its own 4096 output columns of a column-parallel (4096 x 4096·N)
+linear (independent units, no data-path collective) -> weak scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch
+
+K = N = 4096
+G = 128
+MS = [1, 8, 16, 64, 128, 256, 512]
+NSETS = 40
+METRIC = "W4A16 GEMM TOPS vs M (K=N=4096 g128)"
+WORKLOAD = ("single-GEMM sweep M in {1,8,16,64,128,256,512} K=N=4096 g=128, 40 rotating weight sets "
+            "(360 MB > L2: cold weights), 280 GEMMs per step")
+
+
+def flops(M):
+    return 2.0 * M * N * K
+
+
+def alg_bytes(M):
+    # int4 weights + fp16 scales + 4-bit zeros + A + C  (no credit for duplicated scales/zeros)
+    return K * N / 2 + (K // G) * N * 2.5 + 2 * M * K + 2 * M * N
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
+                "source": "MEASURED_PEAKS.json"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while work runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.p = index, None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                                       "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill(); out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def rand_b200_weights(seed, dev):
+    """Random B200-layout weights (valid nibbles / fp16 scales / zero points) — synthetic, random-init."""
+    g = torch.Generator(device=dev); g.manual_seed(seed)
+    wq = torch.randint(-2 ** 31, 2 ** 31 - 1, (K * N // 8,), device=dev, dtype=torch.int32, generator=g)
+    s = (torch.rand(K // G * N, device=dev, generator=g) * 0.01 + 0.002).half().view(torch.int16).to(torch.int32) & 0xFFFF
+    z = torch.randint(0, 16, (K // G * N,), device=dev, generator=g, dtype=torch.int32)
+    return wq, (s | ((0x6400 + z) << 16)).to(torch.int32)
+
+
+def rand_quick_weights(seed, dev):
+    """Random QUICK-layout tensors (what the reference kernel consumes): pack random q/z/s on the GPU."""
+    from quick_b200 import ops
+    g = torch.Generator(device=dev); g.manual_seed(seed)
+    q = torch.randint(0, 16, (K, N), device=dev, generator=g, dtype=torch.int32)
+    z = torch.randint(0, 16, (K // G, N), device=dev, generator=g, dtype=torch.int32)
+    s = (torch.rand(K // G, N, device=dev, generator=g) * 0.01 + 0.002).half()
+    return ops.pack_quick(q, z, s, G)
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world):
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item()
+
+
+def cpu_baseline(sample_sets=1):
+    """dequantize + torch.matmul on the host cores (pattern of the reference's only CPU path,
+    packing_utils.py:82-96 + gemm.py:174-181, restated for QUICK operands by the oracle)."""
+    import numpy as np
+    from oracle import quick_oracle as qo
+    q, z, s = qo.make_case(K, N, G, 1234)
+    tq, tz, ts = torch.from_numpy(q), torch.from_numpy(z), torch.from_numpy(s.astype(np.float32))
+    xs = {M: torch.from_numpy(qo.make_activations(M, K, M).astype(np.float32)) for M in MS}
+
+    def one(M):
+        W = (tq - tz.repeat_interleave(G, 0)).float() * ts.repeat_interleave(G, 0)
+        return xs[M] @ W
+
+    one(1)
+    t0 = time.perf_counter()
+    for _ in range(sample_sets):
+        for M in MS:
+            one(M)
+    dt = time.perf_counter() - t0
+    return {"value": sum(flops(M) for M in MS) * sample_sets / dt / 1e12, "unit": "TOPS", "cores": torch.get_num_threads(),
+            "kind": "port", "sample": f"{sample_sets} pass(es) of the M sweep on one weight set, fp32 dequantize + torch.matmul each GEMM",
+            "seconds": dt}
+
+
+def run_mine(args):
+    from quick_b200 import _lib, ops
+    rank, world, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    lib = _lib.load()
+    sets = [rand_b200_weights(1000 * rank + i, dev) for i in range(NSETS)]
+    xs = {M: torch.randn(M, K, device=dev).half() for M in MS}
+    outs = {M: torch.empty(M, N, device=dev, dtype=torch.float16) for M in MS}
+
+    def step(ev=None):
+        for j, M in enumerate(MS):
+            if ev is not None:
+                ev[j].record()
+            for i in range(NSETS):
+                ops.gemm(xs[M], sets[i][0], sets[i][1], N, G, out=outs[M])
+        if ev is not None:
+            ev[len(MS)].record()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier(world)
+    sampler = ClockSampler(local); sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(MS) + 1)] for _ in range(args.steps)]
+    l0 = lib.qb200_launch_count()
+    barrier(world)
+    for k in range(args.steps):
+        step(evs[k])
+    barrier(world)
+    launches = lib.qb200_launch_count() - l0
+    total_ms = sum(evs[k][0].elapsed_time(evs[k][-1]) for k in range(args.steps))
+    # keep the same work running ~1.5 s so nvidia-smi sees clocks under this load
+    t_end = time.time() + 1.5
+    while time.time() < t_end:
+        step(); torch.cuda.synchronize()
+    clocks = sampler.stop()
+    total_ms = max_over_ranks(total_ms, world)
+    ms_per_step = total_ms / args.steps
+    step_flops = sum(flops(M) for M in MS) * NSETS
+    value = step_flops * world / (ms_per_step * 1e-3) / 1e12
+
+    pk = peaks()
+    sweep = []
+    for j, M in enumerate(MS):
+        us = sum(evs[k][j].elapsed_time(evs[k][j + 1]) for k in range(args.steps)) / args.steps / NSETS * 1e3
+        tops = flops(M) / us / 1e6
+        gbs = alg_bytes(M) / us / 1e3
+        t_mem = alg_bytes(M) / pk["hbm_gbs"] / 1e3          # us at the HBM roof
+        t_tc = flops(M) / pk["tf_sustained"] / 1e6           # us at the tensor roof
+        bound = "hbm" if t_mem >= t_tc else "tensor"
+        tok, split, ctas = ops.plan(M, K, N, G)
+        sweep.append({"M": M, "us": round(us, 3), "TOPS": round(tops, 2), "GBs": round(gbs, 1), "bound": bound,
+                      "frac": round(max(t_mem, t_tc) / us, 4), "tile": [tok, split, ctas]})
+    dom = max(sweep, key=lambda r: r["us"])
+    if dom["bound"] == "tensor":
+        roof = {"bound": "tensor", "achieved": dom["TOPS"], "peak": pk["tf_sustained"], "unit": "TFLOP/s"}
+    else:
+        roof = {"bound": "hbm", "achieved": dom["GBs"], "peak": pk["hbm_gbs"], "unit": "GB/s"}
+    roof.update({"frac": round(roof["achieved"] / roof["peak"], 4), "traffic": None, "kernel": "w4a16_umma_kernel",
+                 "at_M": dom["M"], "share_of_step": round(dom["us"] / sum(r["us"] for r in sweep), 3),
+                 "peak_source": pk["source"] + (" (sustained bf16 cuBLAS)" if roof["bound"] == "tensor" else " (copy)")})
+    m1 = sweep[0]
+    roof_m1 = {"bound": "hbm", "achieved": m1["GBs"], "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": round(m1["GBs"] / pk["hbm_gbs"], 4), "at_M": 1}
+
+    # ---- end to end through the C-ABI host-buffer call ----
+    e2e = None
+    if args.e2e:
+        nh = 16
+        handles = []
+        for i in range(nh):
+            qw, qz, sc = rand_quick_weights(5000 + 100 * rank + i, dev)
+            handles.append(ops.HostLinear(qw, qz, sc, max_m=max(MS), device=local))
+            del qw, qz, sc
+        hx = {M: torch.randn(M, K).half().pin_memory() for M in MS}
+        hy = {M: torch.empty(M, N, dtype=torch.float16).pin_memory() for M in MS}
+
+        def e2e_step():
+            for M in MS:
+                for i in range(nh):
+                    handles[i].forward_host(hx[M], hy[M])
+
+        e2e_step()
+        barrier(world)
+        t0 = time.perf_counter()
+        reps = max(2, args.steps // 4)
+        for _ in range(reps):
+            e2e_step()
+        barrier(world)
+        dt = max_over_ranks(time.perf_counter() - t0, world)
+        e2e = {"value": round(sum(flops(M) for M in MS) * nh * reps * world / dt / 1e12, 3), "unit": "TOPS",
+               "h2d_bytes_per_step": sum(2 * M * K for M in MS) * nh, "d2h_bytes_per_step": sum(2 * M * N for M in MS) * nh,
+               "api": "qb200_linear_forward_host (C-ABI, pinned host x -> device GEMM -> pinned host y, synchronous)",
+               "gemms_per_step": len(MS) * nh, "note": "weights are module state resident in HBM, as in WQLinear_QUICK"}
+        for h in handles:
+            h.close()
+
+    cpu = cpu_baseline() if (rank == 0 and world == 1 and args.cpu_baseline) else None
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(value, 3), "unit": "TOPS", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "K": K, "N": N, "G": G, "M_sweep": MS, "weight_sets": NSETS,
+                           "l2_policy": "inputs larger than L2 (360 MB of packed weights rotate)",
+                           "parallelism": f"{world} x independent column shards of 4096 outputs (no collective)"},
+                "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "roofline_m1": roof_m1,
+                "sweep": sweep, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    if rank != 0:
+        return
+    from oracle.build_ref import load_ref
+    ref = load_ref() if torch.cuda.is_available() else None
+    cpu = cpu_baseline()
+    base = {"metric": METRIC, "unit": "TOPS", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOAD, "K": K, "N": N, "G": G, "M_sweep": MS, "weight_sets": NSETS}}
+    if ref is None:
+        # no reference binary: the oracle port on the host cores stands in (bounded sample)
+        base.update({"value": round(cpu["value"], 4), "ms_per_step": round(cpu["seconds"] * 1e3 * NSETS, 2), "cpu_baseline": cpu,
+                     "reference_kind": "oracle/_ref absent -> CPU oracle port (dequantize + torch.matmul)",
+                     "e2e": {"value": round(cpu["value"], 4), "unit": "TOPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        print(json.dumps(base), flush=True)
+        return
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    sets = [rand_quick_weights(i, dev) for i in range(NSETS)]
+    xs = {M: torch.randn(M, K, device=dev).half() for M in MS}
+    SK = 8   # module default for K >= N (quick.py:36,161-164)
+
+    def step(ev=None):
+        for j, M in enumerate(MS):
+            if ev is not None:
+                ev[j].record()
+            for i in range(NSETS):
+                ref.gemm_forward_cuda_quick(xs[M], sets[i][0], sets[i][2], sets[i][1], SK)
+        if ev is not None:
+            ev[len(MS)].record()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(MS) + 1)] for _ in range(args.steps)]
+    for k in range(args.steps):
+        step(evs[k])
+    torch.cuda.synchronize()
+    ms_per_step = sum(evs[k][0].elapsed_time(evs[k][-1]) for k in range(args.steps)) / args.steps
+    step_flops = sum(flops(M) for M in MS) * NSETS
+    sweep = []
+    for j, M in enumerate(MS):
+        us = sum(evs[k][j].elapsed_time(evs[k][j + 1]) for k in range(args.steps)) / args.steps / NSETS * 1e3
+        sweep.append({"M": M, "us": round(us, 3), "TOPS": round(flops(M) / us / 1e6, 2)})
+    # e2e through the reference's own API with host buffers
+    hx = {M: torch.randn(M, K).half().pin_memory() for M in MS}
+    nh = 16
+
+    def e2e_step():
+        for M in MS:
+            for i in range(nh):
+                y = ref.gemm_forward_cuda_quick(hx[M].cuda(non_blocking=True), sets[i][0], sets[i][2], sets[i][1], SK).cpu()
+        return y
+
+    e2e_step(); torch.cuda.synchronize()
+    reps = max(2, args.steps // 4)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    base.update({"value": round(step_flops / (ms_per_step * 1e-3) / 1e12, 3), "ms_per_step": round(ms_per_step, 4),
+                 "reference_kind": "unmodified reference CUDA kernel (oracle/_ref, /root/reference/csrc built for sm_100a), "
+                                   "gemm_forward_cuda_quick + its at::sum split-K reduce, split_k_iters=8, timed as called (2 launches per GEMM)",
+                 "sweep": sweep, "cpu_baseline": cpu,
+                 "e2e": {"value": round(sum(flops(M) for M in MS) * nh * reps / dt / 1e12, 3), "unit": "TOPS",
+                         "h2d_bytes_per_step": sum(2 * M * K for M in MS) * nh, "d2h_bytes_per_step": sum(2 * M * N for M in MS) * nh}})
+    print(json.dumps(base), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="quick_b200", choices=["quick_b200", "reference"])
+    ap.add_argument("--no-e2e", dest="e2e", action="store_false")
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: quick_b200 has no CPU path (use --impl reference for the CPU oracle timing)")
+        run_mine(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -71,10 +71,11 @@ class WQLinear_QUICK(nn.Module):
         assert scales is not None and zeros is not None
         G = awq_linear.group_size
         # intweight[k, n] = round((W[n, k] + z*s) / s)   (reference quick.py:76-81), scales/zeros are (N, K/G)
+        # (computed in fp32: with fp16 weights the reference's own-dtype division can land on .5 ties)
         s16 = scales.clone().half()
-        s_rep = s16.repeat_interleave(G, dim=1)
-        zs_rep = (zeros * scales).repeat_interleave(G, dim=1)
-        intweight = torch.round((linear.weight.data + zs_rep) / s_rep).to(torch.int32).t().contiguous()
+        s_rep = s16.float().repeat_interleave(G, dim=1)
+        zs_rep = (zeros.float() * scales.float()).repeat_interleave(G, dim=1)
+        intweight = torch.round((linear.weight.data.float() + zs_rep) / s_rep).clamp_(0, 15).to(torch.int32).t().contiguous()
         qweight, qzeros, qscales = pack_quick(intweight, zeros.t().contiguous().to(torch.int32), s16.t().contiguous())
         awq_linear.qweight = qweight
         awq_linear.qzeros = qzeros

@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -15,6 +16,7 @@ namespace {
 
 thread_local std::string g_last_error;
 std::atomic<unsigned long long> g_launches{0};
+long long* g_trace = nullptr;   // debug trace buffer (qb200_debug_set_trace)
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -245,10 +247,10 @@ int device_sm_count() {
   return sms;
 }
 
-template <int TOK, int SPLIT>
+template <int TOK, int SPLIT, int KT = qb200::default_tstages<TOK>()>
 int launch_umma(const CUtensorMap& map, const qb200::GemmArgs& args, int m_tiles, cudaStream_t stream) {
-  using Cfg = qb200::TileCfg<TOK>;
-  auto kfn = qb200::w4a16_umma_kernel<TOK, SPLIT>;
+  using Cfg = qb200::TileCfg<TOK, KT>;
+  auto kfn = qb200::w4a16_umma_kernel<TOK, SPLIT, KT>;
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
     QB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -271,8 +273,24 @@ int launch_umma(const CUtensorMap& map, const qb200::GemmArgs& args, int m_tiles
   return QB200_OK;
 }
 
+int experiment_kt() {   // QB200_KT: tuning experiments only
+  static int kt = -1;
+  if (kt < 0) { const char* e = getenv("QB200_KT"); kt = e ? atoi(e) : 0; }
+  return kt;
+}
+
 template <int TOK>
 int dispatch_split(int split, const CUtensorMap& map, const qb200::GemmArgs& args, int m_tiles, cudaStream_t st) {
+  const int kt = experiment_kt();
+  if constexpr (TOK == 16) {
+    if (kt == 4 && split == 4) return launch_umma<16, 4, 4>(map, args, m_tiles, st);
+    if (kt == 14 && split == 4) return launch_umma<16, 4, 14>(map, args, m_tiles, st);
+    if (kt == 4 && split == 1) return launch_umma<16, 1, 4>(map, args, m_tiles, st);
+    if (kt == 14 && split == 1) return launch_umma<16, 1, 14>(map, args, m_tiles, st);
+  }
+  if constexpr (TOK == 256) {
+    if (kt == 4 && split == 1) return launch_umma<256, 1, 4>(map, args, m_tiles, st);
+  }
   switch (split) {
     case 1: return launch_umma<TOK, 1>(map, args, m_tiles, st);
     case 2: return launch_umma<TOK, 2>(map, args, m_tiles, st);
@@ -320,6 +338,7 @@ extern "C" {
 const char* qb200_version(void) { return "quick_b200 0.1 (sm_100a tcgen05/TMEM/TMA W4A16)"; }
 const char* qb200_last_error(void) { return g_last_error.c_str(); }
 unsigned long long qb200_launch_count(void) { return g_launches.load(); }
+void qb200_debug_set_trace(void* device_buffer) { g_trace = reinterpret_cast<long long*>(device_buffer); }
 
 size_t qb200_wq_bytes(int K, int N) { return static_cast<size_t>(K) * N / 2; }
 size_t qb200_sz_bytes(int K, int N, int G) { return static_cast<size_t>(K / G) * N * 4; }
@@ -415,6 +434,7 @@ int qb200_gemm_w4a16_cfg(const void* A, const uint32_t* wq, const uint32_t* sz, 
   args.N = N;
   args.G = G;
   args.kb_per_split = kbps;
+  args.trace = g_trace;
   cudaStream_t st = as_stream(stream);
   switch (tok) {
     case 16: return dispatch_split<16>(split, map, args, m_tiles, st);

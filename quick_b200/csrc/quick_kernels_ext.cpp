@@ -108,6 +108,7 @@ std::pair<torch::Tensor, torch::Tensor> get_prepacked(const torch::Tensor& kerne
 // (x2d, qweight, scales, qzeros, split_k)  (quick/awq/modules/linear/quick.py:162,164).
 torch::Tensor gemm_forward_cuda_quick(torch::Tensor _in_feats, torch::Tensor _kernel, torch::Tensor _scaling_factors,
                                       torch::Tensor _zeros, int split_k_iters) {
+  TORCH_CHECK(_in_feats.is_cuda(), "quick_kernels: all operands must be CUDA tensors (there is no CPU path)");
   const at::cuda::OptionalCUDAGuard device_guard(device_of(_in_feats));
   const Shapes s = derive_shapes(_in_feats, _kernel, _scaling_factors, _zeros);
   if (split_k_iters < 1) throw std::invalid_argument("split_k_iters must be >= 1");
@@ -128,8 +129,8 @@ torch::Tensor gemm_forward_cuda_quick(torch::Tensor _in_feats, torch::Tensor _ke
 
 // Explicit one-time conversion for callers that hold weights for a long time (WQLinear_QUICK).
 std::vector<torch::Tensor> prepack_quick(torch::Tensor kernel, torch::Tensor scales, torch::Tensor zeros, int64_t K) {
+  TORCH_CHECK(kernel.is_cuda() && scales.is_cuda() && zeros.is_cuda(), "prepack_quick: CUDA tensors required (there is no CPU path)");
   const at::cuda::OptionalCUDAGuard device_guard(device_of(kernel));
-  TORCH_CHECK(kernel.is_cuda() && scales.is_cuda() && zeros.is_cuda(), "prepack_quick: CUDA tensors required");
   const int N = static_cast<int>(kernel.size(1) / 4 * 8);
   const int G = static_cast<int>(K / scales.size(0));
   check(qb200_check_shape(1, static_cast<int>(K), N, G));
@@ -140,8 +141,8 @@ std::vector<torch::Tensor> prepack_quick(torch::Tensor kernel, torch::Tensor sca
 // GEMM on already-converted weights, bias fused into the epilogue.
 torch::Tensor gemm_forward_b200(torch::Tensor in_feats, torch::Tensor wq, torch::Tensor sz,
                                 c10::optional<torch::Tensor> bias, int64_t N, int64_t G) {
+  TORCH_CHECK(in_feats.dim() == 2 && in_feats.is_cuda(), "in_feats must be a 2-D CUDA tensor (there is no CPU path)");
   const at::cuda::OptionalCUDAGuard device_guard(device_of(in_feats));
-  TORCH_CHECK(in_feats.dim() == 2 && in_feats.is_cuda(), "in_feats must be a 2-D CUDA tensor");
   torch::Tensor x = in_feats.contiguous();
   const int M = static_cast<int>(x.size(0)), K = static_cast<int>(x.size(1));
   check(qb200_check_shape(M, K, static_cast<int>(N), static_cast<int>(G)));

@@ -12,7 +12,7 @@
 //       - the ACTIVATIONS are the B operand in shared memory (K-major, 128B swizzle) loaded by TMA
 //   * packed weights in the "B200 layout" (see include/quick_b200.h): one thread = one TMEM lane =
 //     one output channel, its 16-byte shared-memory read = 32 consecutive k = 16 TMEM columns
-//   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = dequant
+//   * warp roles: warps 0..7 = dequant, warp 8 = TMA producer, warp 9 = MMA issuer (+TMEM alloc)
 //     (two warpgroups alternating k64 stages) and epilogue
 //   * split-K lives inside a thread-block cluster (1,1,SPLIT): partial tiles are exchanged through
 //     distributed shared memory, each CTA reduces and stores TOK/SPLIT token columns; no HBM temp,
@@ -28,9 +28,13 @@ namespace qb200 {
 constexpr int kChan = 128;          // channels per tile = UMMA M
 constexpr int kBK = 64;             // k per pipeline stage
 constexpr int kWStageBytes = kChan * kBK / 2;   // 4096
-constexpr int kTStages = 4;         // A-operand stages in TMEM (32 columns each)
 constexpr int kNumThreads = 320;    // 10 warps
 constexpr int kNumDequantWarps = 8;
+// Warp roles.  The single-thread issuers get the HIGHEST warp ids: the SM's warp arbiter favours
+// higher warp ids, and a starved TMA/MMA issuer stalls the whole pipeline (measured: with the
+// issuers on warps 0/1 every already-complete mbarrier wait cost ~300 cycles).
+constexpr int kProducerWarp = 8;
+constexpr int kMmaWarp = 9;
 
 // ------------------------------------------------------------------------------------------------
 // PTX helpers
@@ -65,6 +69,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (!timed) { t0 = clock64(); timed = true; }
     else if (clock64() - t0 > QB200_WAIT_TIMEOUT_CYCLES) { __trap(); }
   }
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -242,8 +255,13 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
   return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
 }
 
+// default depth of the TMEM A-operand ring (32 columns per stage)
 template <int TOK>
+constexpr int default_tstages() { return TOK == 256 ? 8 : TOK == 128 ? 4 : 6; }
+
+template <int TOK, int KT = default_tstages<TOK>()>
 struct TileCfg {
+  static constexpr int kTStages = KT;
   static constexpr int kXStageBytes = TOK * 128;
   static constexpr int kStageBytes = kXStageBytes + kWStageBytes;
   static constexpr int kACol0 = TOK < 32 ? 32 : TOK;
@@ -265,15 +283,22 @@ struct GemmArgs {
   __half* C;
   int M, K, N, G;
   int kb_per_split;
+  long long* trace;   // debug: per-role clock64 stamps of CTA (0,0,0); nullptr in production
 };
+#define QB_TRACE(slot, it, k)                                                                  \
+  do {                                                                                         \
+    if (args.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)         \
+      args.trace[((slot) * 256 + (it)) * 4 + (k)] = clock64();                                 \
+  } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------
-template <int TOK, int SPLIT>
+template <int TOK, int SPLIT, int KT = default_tstages<TOK>()>
 __global__ void __launch_bounds__(kNumThreads, 1)
 w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs args) {
-  using Cfg = TileCfg<TOK>;
+  using Cfg = TileCfg<TOK, KT>;
+  constexpr int kTStages = KT;
   constexpr int STAGES = Cfg::kStages;
   constexpr int SLICE = TOK / SPLIT;          // token columns owned by one cluster rank
   constexpr int CH = SLICE / 2;               // columns per (owner, warpgroup)
@@ -302,6 +327,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
   const int kb0 = rank * args.kb_per_split;
   const int nkb = min(args.kb_per_split, KB - kb0);
 
+  if (threadIdx.x == 0) QB_TRACE(3, 0, 0);
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(bar_full + 8 * i, 1);
@@ -316,14 +342,15 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
     fence_proxy_async();
     prefetch_tmap(&tmap_x);
   }
-  if (warp == 1) tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
+  if (warp == kMmaWarp) tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem) : "memory");
+  if (threadIdx.x == 0) QB_TRACE(3, 0, 1);
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       const uint32_t* wsrc = args.wq + (static_cast<size_t>(nt) * KB + kb0) * (kWStageBytes / 4);
@@ -331,14 +358,16 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        QB_TRACE(0, it, 0);
         mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::kStageBytes);
         bulk_g2s(smem_w + s * kWStageBytes, wsrc + static_cast<size_t>(it) * (kWStageBytes / 4), kWStageBytes,
                  bar_full + 8 * s);
         tma_load_2d(smem_x + s * Cfg::kXStageBytes, &tmap_x, bar_full + 8 * s, (kb0 + it) * kBK, mt * TOK);
+        QB_TRACE(0, it, 1);
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(TOK);
@@ -348,7 +377,9 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
         const int t = it % kTStages;
         const uint32_t tph = (it / kTStages) & 1;
         mbar_wait(bar_full + 8 * s, ph);
+        QB_TRACE(1, it, 0);
         mbar_wait(bar_tfull + 8 * t, tph);
+        QB_TRACE(1, it, 1);
         tc_fence_after();
         const uint64_t bdesc = make_smem_desc_sw128(smem_x + s * Cfg::kXStageBytes);
         const uint32_t a_tmem = tmem_base + Cfg::kACol0 + t * 32;
@@ -356,71 +387,110 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
         for (int j = 0; j < kBK / 16; ++j) {
           // +32 B (= 2 in 16-B units) of start address per k16 step inside the 128-B swizzle row
           umma_f16_ts(tmem_base, a_tmem + j * 8, bdesc + 2 * j, idesc, (it | j) != 0 ? 1u : 0u);
+          if (j == 0) QB_TRACE(1, it, 2);
         }
+        QB_TRACE(1, it, 3);
         umma_commit(bar_empty + 8 * s);    // X stage (and with the dequant arrivals, the whole stage) free
+        QB_TRACE(0, it, 2);
         umma_commit(bar_tempty + 8 * t);   // TMEM A stage free
+        QB_TRACE(0, it, 3);
       }
       umma_commit(bar_accum);
     }
     __syncwarp();
   } else {
     // ===================== dequant warps: smem nibbles -> registers -> TMEM A operand =====================
-    const int wg = (warp - 2) >> 2;                 // warpgroup 0/1 takes even/odd stages
+    const int wg = warp >> 2;                       // warpgroup 0/1 takes even/odd stages
     const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
     const int ch = quad * 32 + lane;                // output channel within the tile = TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const int NG = args.K / args.G;
     const uint32_t* szp = args.sz + static_cast<size_t>(nt) * NG * kChan + ch;
-    for (int it = wg; it < nkb; it += 2) {
+    // Software-pipelined: the scale/zero words of the next stage are prefetched one iteration ahead and
+    // the TMEM hand-off of stage i (wait::st + arrive) is deferred until stage i+2 has been unpacked,
+    // so neither the global-load latency nor the tcgen05.st latency sits on the per-stage chain.
+    int it = wg;
+    uint32_t sz0 = 0, sz1 = 0;
+    if (it < nkb) {
+      const int k0 = (kb0 + it) * kBK;
+      sz0 = __ldg(szp + static_cast<size_t>(k0 / args.G) * kChan);
+      sz1 = __ldg(szp + static_cast<size_t>((k0 + 32) / args.G) * kChan);
+    }
+    bool pending = false;
+    int t_prev = 0;
+    for (; it < nkb; it += 2) {
       const int s = it % STAGES;
       const uint32_t ph = (it / STAGES) & 1;
       const int t = it % kTStages;
       const uint32_t tph = (it / kTStages) & 1;
-      const int k0 = (kb0 + it) * kBK;
-      const uint32_t sz0 = __ldg(szp + static_cast<size_t>(k0 / args.G) * kChan);
-      const uint32_t sz1 = __ldg(szp + static_cast<size_t>((k0 + 32) / args.G) * kChan);
+      if (pending && !mbar_try(bar_full + 8 * s, ph)) {   // starved: do not sit on a finished stage
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tfull + 8 * t_prev);
+        pending = false;
+      }
       mbar_wait(bar_full + 8 * s, ph);
+      if (lane == 0 && quad == 2) QB_TRACE(2, it, 0);
       const uint4 w0 = lds128(smem_w + s * kWStageBytes + ch * 16);
       const uint4 w1 = lds128(smem_w + s * kWStageBytes + 2048 + ch * 16);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_empty + 8 * s);
-      uint32_t r[32];
-      {
-        const GroupConsts g0 = make_group_consts(sz0);
-        dequant_word(w0.x, g0, r + 0);
-        dequant_word(w0.y, g0, r + 4);
-        dequant_word(w0.z, g0, r + 8);
-        dequant_word(w0.w, g0, r + 12);
-        const GroupConsts g1 = make_group_consts(sz1);
-        dequant_word(w1.x, g1, r + 16);
-        dequant_word(w1.y, g1, r + 20);
-        dequant_word(w1.z, g1, r + 24);
-        dequant_word(w1.w, g1, r + 28);
+      const GroupConsts g0 = make_group_consts(sz0);
+      const GroupConsts g1 = make_group_consts(sz1);
+      if (it + 2 < nkb) {
+        const int k0n = (kb0 + it + 2) * kBK;
+        sz0 = __ldg(szp + static_cast<size_t>(k0n / args.G) * kChan);
+        sz1 = __ldg(szp + static_cast<size_t>((k0n + 32) / args.G) * kChan);
       }
+      uint32_t r[32];
+      dequant_word(w0.x, g0, r + 0);
+      dequant_word(w0.y, g0, r + 4);
+      dequant_word(w0.z, g0, r + 8);
+      dequant_word(w0.w, g0, r + 12);
+      dequant_word(w1.x, g1, r + 16);
+      dequant_word(w1.y, g1, r + 20);
+      dequant_word(w1.z, g1, r + 24);
+      dequant_word(w1.w, g1, r + 28);
+      if (pending) {
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tfull + 8 * t_prev);
+      }
+      if (lane == 0 && quad == 2) QB_TRACE(2, it, 1);
       mbar_wait(bar_tempty + 8 * t, tph ^ 1);
       tc_fence_after();
+      if (lane == 0 && quad == 2) QB_TRACE(2, it, 2);
       const uint32_t a_tmem = tmem_base + lane_addr + Cfg::kACol0 + t * 32;
       tmem_st16(a_tmem, r);
       tmem_st16(a_tmem + 16, r + 16);
+      if (lane == 0 && quad == 2) QB_TRACE(2, it, 3);
+      pending = true;
+      t_prev = t;
+    }
+    if (pending) {
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tfull + 8 * t);
+      if (lane == 0) mbar_arrive(bar_tfull + 8 * t_prev);
     }
   }
 
   // ===================== epilogue =====================
   const int quad = warp & 3;
-  const int wg = (warp - 2) >> 2;
+  const int wg = warp >> 2;
   const int ch = quad * 32 + lane;
+  const bool is_dq = warp < kNumDequantWarps;
   const uint32_t d_tmem = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
   const int n = nt * kChan + ch;
-  const float bias_v = (args.bias != nullptr && warp >= 2) ? __half2float(args.bias[n]) : 0.f;
+  const float bias_v = (args.bias != nullptr && is_dq) ? __half2float(args.bias[n]) : 0.f;
 
   if constexpr (SPLIT == 1) {
-    if (warp >= 2) {
+    if (is_dq) {
       mbar_wait(bar_accum, 0);
       tc_fence_after();
+      if (threadIdx.x == 0) QB_TRACE(3, 0, 2);
 #pragma unroll 1
       for (int p = 0; p < CH / PIECE; ++p) {
         const int col0 = wg * CH + p * PIECE;
@@ -436,13 +506,13 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
     }
   } else {
     // reduction buffer aliases the (now dead) X stages: [src rank][SLICE columns][128 channels] fp32
-    if (warp >= 2) {
+    if (is_dq) {
       mbar_wait(bar_accum, 0);   // every TMA write landed and every MMA read of this CTA's smem is complete
       tc_fence_after();
     }
     cluster_arrive();
     cluster_wait();              // every CTA of the cluster is past its main loop
-    if (warp >= 2) {
+    if (is_dq) {
 #pragma unroll 1
       for (int o = 0; o < SPLIT; ++o) {
         const uint32_t dst_cta = mapa_shared(smem_x, static_cast<uint32_t>(o));
@@ -462,7 +532,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
     }
     cluster_arrive();
     cluster_wait();              // all partial slices have landed in their owners' shared memory
-    if (warp >= 2) {
+    if (is_dq) {
 #pragma unroll 1
       for (int i = 0; i < CH; ++i) {
         const int j = wg * CH + i;
@@ -475,9 +545,11 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
     }
   }
 
+  if (threadIdx.x == 0) QB_TRACE(3, 0, 3);
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (threadIdx.x == kMmaWarp * 32) QB_TRACE(3, 1, 0);
 }
 
 }  // namespace qb200

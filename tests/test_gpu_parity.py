@@ -1,0 +1,268 @@
+"""GPU parity tests (run with -m gpu on a B200).  Every call goes through the C-ABI
+(libquick_b200.so via ctypes) or the drop-in `quick_kernels` module; the oracle
+(oracle/quick_oracle.py, and the unmodified reference kernel in oracle/_ref when present) is only
+the checker.
+
+Tolerances (north_star): bit-exact for the integer unpack / index work (pack, relayout, W16);
+GEMM outputs within rtol = 1e-2, atol = 1e-2 * rms(reference) of the fp64 product of the same fp16
+operands (tensor-core accumulation order is not IEEE-sequential).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import quick_oracle as qo
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+RTOL = 1e-2
+
+
+def assert_close(out, exact, what=""):
+    """out: torch fp16 (GPU); exact: torch fp64 or fp32 (GPU)."""
+    exact = exact.double()
+    rms = exact.pow(2).mean().sqrt().item()
+    ok = torch.allclose(out.double(), exact, rtol=RTOL, atol=RTOL * rms)
+    if not ok:
+        err = (out.double() - exact).abs().max().item()
+        raise AssertionError(f"{what}: max_abs_err={err:.4g} rms={rms:.4g}")
+
+
+@pytest.fixture(scope="module")
+def ops(built):
+    from quick_b200 import ops as _ops
+    assert torch.cuda.get_device_capability()[0] == 10, "these tests need an sm_100 device"
+    return _ops
+
+
+def make_gpu_case(ops, K, N, G, seed=1234):
+    q, z, s = qo.make_case(K, N, G, seed)
+    tq, tz, ts = torch.from_numpy(q).cuda(), torch.from_numpy(z).cuda(), torch.from_numpy(s).cuda()
+    qw, qz, sc = ops.pack_quick(tq, tz, ts, G)
+    W16 = ((tq - tz.repeat_interleave(G, 0)).half() * ts.repeat_interleave(G, 0))   # == oracle dequant_w16 (checked below)
+    return q, z, s, qw, qz, sc, W16
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "pack_*.npz"))), ids=os.path.basename)
+def test_gpu_packer_and_relayout_bitexact_vs_golden(ops, path):
+    """GPU packer == reference packer output; relayout + dequantize == oracle W16, all bit-exact."""
+    d = np.load(path)
+    G = int(d["G"])
+    q, z, s = d["q"].astype(np.int32), d["z"].astype(np.int32), d["s"]
+    qw, qz, sc = ops.pack_quick(torch.from_numpy(q).cuda(), torch.from_numpy(z).cuda(), torch.from_numpy(s).cuda(), G)
+    assert np.array_equal(qw.cpu().numpy(), d["qweight"])
+    assert np.array_equal(qz.cpu().numpy(), d["qzeros"])
+    assert np.array_equal(sc.cpu().numpy().view(np.uint16), d["scales"].view(np.uint16))
+    # relayout of the GOLDEN tensors (identical packed inputs as the reference would see)
+    wq, sz, K, N, G2 = ops.prepack(torch.from_numpy(d["qweight"]).cuda(), torch.from_numpy(d["qzeros"]).cuda(),
+                                   torch.from_numpy(d["scales"]).cuda())
+    assert G2 == G
+    W = ops.dequantize(wq, sz, K, N, G).cpu().numpy()
+    assert np.array_equal(W.view(np.uint16), qo.dequant_w16(q, z, s, G).view(np.uint16))
+    assert np.array_equal(W.view(np.uint16), qo.kernel_view_w16(d["qweight"], d["qzeros"], d["scales"], G).view(np.uint16))
+
+
+def test_identity_probe_reads_w16_through_the_tensor_cores(ops):
+    """A = rows of the identity: the GEMM output must equal W16 rows exactly (products by 1.0 and
+    sums with exact zeros are exact) — the 'bit-exact integer unpack/index' pin through the hot path."""
+    K, N, G = 512, 256, 64
+    q, z, s, qw, qz, sc, W16 = make_gpu_case(ops, K, N, G)
+    assert np.array_equal(W16.cpu().numpy().view(np.uint16), qo.dequant_w16(q, z, s, G).view(np.uint16))
+    wq, sz, *_ = ops.prepack(qw, qz, sc)
+    for k0 in (0, 64, K - 128):
+        A = torch.zeros(128, K, dtype=torch.float16, device="cuda")
+        A[torch.arange(128), k0 + torch.arange(128)] = 1
+        for tok, split in ((16, 1), (128, 1), (128, 2), (256, 4), (None, None)):
+            out = ops.gemm(A, wq, sz, N, G, tok=tok, split=split)
+            assert torch.equal(out, W16[k0:k0 + 128]), (k0, tok, split)
+
+
+CASES = [
+    # (K, N, G, Ms)
+    (512, 512, 128, (1, 2, 8, 16, 17, 33, 100, 256)),          # BASELINE config 1 shape (M=1) + ragged M
+    (256, 768, 64, (1, 7, 64)),
+    (128, 512, 32, (3, 16, 130)),
+    (4096, 4096, 128, (1, 8, 16, 64, 128, 256, 512)),           # BASELINE config 2: the full sweep
+    (4096, 11008, 128, (1, 64)),                                # Llama-2-7B gate/up
+    (11008, 4096, 128, (1, 32, 300)),                           # Llama-2-7B down (K = 172 k-blocks, odd splits)
+    (8192, 1280, 128, (5,)),                                    # Llama-2-70B qkv shard on 8 ranks
+]
+
+
+@pytest.mark.parametrize("K,N,G,Ms", CASES, ids=[f"K{c[0]}_N{c[1]}_G{c[2]}" for c in CASES])
+def test_gemm_parity_auto_config(ops, K, N, G, Ms):
+    q, z, s, qw, qz, sc, W16 = make_gpu_case(ops, K, N, G)
+    wq, sz, *_ = ops.prepack(qw, qz, sc)
+    Wd = W16.double()
+    for M in Ms:
+        A = torch.from_numpy(qo.make_activations(M, K, seed=M)).cuda()
+        out = ops.gemm(A, wq, sz, N, G)
+        assert out.shape == (M, N) and out.dtype == torch.float16
+        assert_close(out, A.double() @ Wd, f"K={K} N={N} G={G} M={M}")
+
+
+@pytest.mark.parametrize("tok", [16, 32, 64, 128, 256])
+@pytest.mark.parametrize("split", [1, 2, 4, 8])
+def test_gemm_every_tile_config_matches_oracle_and_simt(ops, tok, split):
+    """All (token tile, cluster split-K) instantiations against the numpy oracle (small) and the
+    CUDA-core cross-check kernel."""
+    if split == 8 and tok > 32:
+        pytest.skip("split 8 only instantiated for tok <= 32")
+    K, N, G = 1024, 256, 128
+    q, z, s, qw, qz, sc, W16 = make_gpu_case(ops, K, N, G, seed=tok + split)
+    wq, sz, *_ = ops.prepack(qw, qz, sc)
+    for M in sorted({1, tok - 1, tok, tok + 3}):
+        A_np = qo.make_activations(M, K, seed=M)
+        A = torch.from_numpy(A_np).cuda()
+        out = ops.gemm(A, wq, sz, N, G, tok=tok, split=split)
+        exact = torch.from_numpy(qo.gemm_exact(A_np, W16.cpu().numpy())).cuda()
+        assert_close(out, exact, f"tok={tok} split={split} M={M}")
+        assert_close(ops.gemm_simt(A, wq, sz, N, G), exact, "simt cross-check")
+
+
+def test_bias_fused_in_epilogue(ops):
+    K, N, G, M = 512, 256, 128, 9
+    q, z, s, qw, qz, sc, W16 = make_gpu_case(ops, K, N, G)
+    wq, sz, *_ = ops.prepack(qw, qz, sc)
+    A = torch.from_numpy(qo.make_activations(M, K, seed=3)).cuda()
+    bias = (torch.randn(N, device="cuda") * 0.5).half()
+    for tok, split in ((16, 1), (16, 4), (None, None)):
+        out = ops.gemm(A, wq, sz, N, G, bias=bias, tok=tok, split=split)
+        assert_close(out, A.double() @ W16.double() + bias.double(), "bias")
+
+
+def test_drop_in_symbol_matches_reference_contract(ops):
+    """quick_kernels.gemm_forward_cuda_quick: positional (x2d, qweight, scales, qzeros, split_k),
+    (1,M,N) when split_k == 1 (gemm_cuda_quick.cu:1515-1516), ValueError for the reference's checks."""
+    import quick_kernels
+    K, N, G, M = 512, 512, 128, 5
+    q, z, s, qw, qz, sc, W16 = make_gpu_case(ops, K, N, G)
+    A = torch.from_numpy(qo.make_activations(M, K, seed=5)).cuda()
+    exact = A.double() @ W16.double()
+    o8 = quick_kernels.gemm_forward_cuda_quick(A, qw, sc, qz, 8)
+    o1 = quick_kernels.gemm_forward_cuda_quick(A, qw, sc, qz, 1)
+    assert o8.shape == (M, N) and o1.shape == (1, M, N)
+    assert_close(o8, exact, "drop-in sk=8")
+    assert torch.equal(o1[0], o8)
+    # stateless C-ABI entry (relayout + GEMM in one call) agrees bit-for-bit with the cached path
+    assert torch.equal(ops.gemm_forward_quick_stateless(A, qw, sc, qz, 8), o8)
+    with pytest.raises(ValueError, match="cta_N = 128"):
+        quick_kernels.gemm_forward_cuda_quick(A, qw[:, :96].contiguous(), sc[:, :384].contiguous(), qz[:, :48].contiguous(), 8)
+    with pytest.raises(RuntimeError):   # wrong dtype, like the reference's data_ptr<at::Half>()
+        quick_kernels.gemm_forward_cuda_quick(A.float(), qw, sc, qz, 8)
+
+
+def test_prepack_cache_is_never_stale(ops):
+    """The binding caches the B200 relayout per weight storage; freeing / re-allocating / mutating the
+    packed tensors must never serve a stale copy."""
+    import quick_kernels
+    K, N, G, M = 256, 256, 128, 4
+    A = torch.from_numpy(qo.make_activations(M, K, seed=1)).cuda()
+    for seed in range(6):   # same shapes -> the caching allocator hands back the same addresses
+        q, z, s, qw, qz, sc, W16 = make_gpu_case(ops, K, N, G, seed=seed)
+        out = quick_kernels.gemm_forward_cuda_quick(A, qw, sc, qz, 8)
+        assert_close(out, A.double() @ W16.double(), f"fresh weight {seed}")
+        out2 = quick_kernels.gemm_forward_cuda_quick(A, qw, sc, qz, 8)
+        assert torch.equal(out, out2)
+        del q, z, s, qw, qz, sc, W16
+    # in-place update of a live weight bumps its version counter
+    q, z, s, qw, qz, sc, W16 = make_gpu_case(ops, K, N, G, seed=100)
+    quick_kernels.gemm_forward_cuda_quick(A, qw, sc, qz, 8)
+    q2, z2, s2, qw2, qz2, sc2, W16b = make_gpu_case(ops, K, N, G, seed=101)
+    qw.copy_(qw2); qz.copy_(qz2); sc.copy_(sc2)
+    out = quick_kernels.gemm_forward_cuda_quick(A, qw, sc, qz, 8)
+    assert_close(out, A.double() @ W16b.double(), "after in-place update")
+    size, hits, misses = quick_kernels.cache_stats()
+    assert hits >= 6 and misses >= 8
+
+
+def test_wqlinear_quick_forward_and_fused_qkv(ops):
+    from quick_b200 import layout
+    from quick_b200.awq.modules.linear.quick import WQLinear_QUICK
+    from quick_b200.awq.utils.fused_utils import fuse_qkv_quick
+    K, G = 512, 128
+    torch.manual_seed(0)
+    mods, Ws = [], []
+    for n in (512, 128, 128):   # GQA-style widths
+        lin = torch.nn.Linear(K, n, bias=True).half().cuda()
+        q, z, s = layout.quantize_rtn(lin.weight.data.float(), G)
+        # AWQ hands from_linear the pseudo-quantised weight (quantizer.py:154-157), i.e. (q - z) * s
+        lin.weight.data = ((q - z.repeat_interleave(G, 0)).float() * s.float().repeat_interleave(G, 0)).t().contiguous().half()
+        m = WQLinear_QUICK.from_linear(lin, 4, G, False, scales=s.t().contiguous().float(), zeros=z.t().contiguous().float())
+        q2, z2, s2 = layout.unpack_quick(m.qweight, m.qzeros, m.scales)
+        assert torch.equal(q2, q) and torch.equal(z2, z)
+        mods.append(m)
+        Ws.append(((q - z.repeat_interleave(G, 0)).half() * s.repeat_interleave(G, 0)))
+    x = torch.randn(2, 3, K, device="cuda").half()
+    for m, W in zip(mods, Ws):
+        y = m(x)
+        assert y.shape == (2, 3, m.out_features)
+        exact = x.reshape(-1, K).double() @ W.double() + m.bias.double()
+        assert_close(y.reshape(-1, m.out_features), exact, "WQLinear_QUICK.forward")
+        assert_close(m.forward_reference_call(x).reshape(-1, m.out_features), exact, "reference call sequence")
+    fused = fuse_qkv_quick(torch.nn.ModuleList(mods), *mods)
+    y = fused(x).reshape(-1, 768)
+    exact = x.reshape(-1, K).double() @ torch.cat(Ws, 1).double() + torch.cat([m.bias for m in mods]).double()
+    assert_close(y, exact, "fused qkv")
+
+
+def test_host_buffer_handle_end_to_end(ops):
+    K, N, G = 512, 512, 128
+    q, z, s, qw, qz, sc, W16 = make_gpu_case(ops, K, N, G)
+    h = ops.HostLinear(qw, qz, sc, max_m=64)
+    for M in (1, 33, 64):
+        x = torch.from_numpy(qo.make_activations(M, K, seed=M)).pin_memory()
+        y = h.forward_host(x)
+        assert not y.is_cuda
+        assert_close(y.cuda(), x.cuda().double() @ W16.double(), f"host handle M={M}")
+    with pytest.raises(ValueError):
+        h.forward_host(torch.zeros(65, K, dtype=torch.float16))
+    h.close()
+
+
+def test_full_size_properties(ops):
+    """At BASELINE's full sizes: size-independent properties instead of a CPU oracle —
+    linearity in A, row independence (ragged M == prefix of padded M), and agreement of every
+    split-K factor (the cluster reduction) with split 1."""
+    K = N = 4096
+    G = 128
+    q, z, s, qw, qz, sc, W16 = make_gpu_case(ops, K, N, G)
+    wq, sz, *_ = ops.prepack(qw, qz, sc)
+    A1 = torch.from_numpy(qo.make_activations(256, K, seed=11)).cuda()
+    A2 = torch.from_numpy(qo.make_activations(256, K, seed=12)).cuda()
+    y1, y2 = ops.gemm(A1, wq, sz, N, G), ops.gemm(A2, wq, sz, N, G)
+    y12 = ops.gemm((A1.float() + A2.float()).half(), wq, sz, N, G)
+    assert_close(y12, y1.double() + y2.double(), "linearity")
+    # row independence / ragged M
+    for M in (1, 100, 255):
+        yM = ops.gemm(A1[:M].contiguous(), wq, sz, N, G, tok=256, split=1)
+        assert torch.equal(yM, ops.gemm(A1, wq, sz, N, G, tok=256, split=1)[:M])
+    # every split factor against split 1 (same tile): differences only from fp32 summation order
+    base = ops.gemm(A1, wq, sz, N, G, tok=128, split=1)
+    for split in (2, 4):
+        assert_close(ops.gemm(A1, wq, sz, N, G, tok=128, split=split), base.double(), f"split {split}")
+
+
+def test_against_unmodified_reference_kernel(ops):
+    """The real reference (oracle/_ref, built from /root/reference/csrc unmodified) on identical packed
+    inputs: outputs within 1e-2 rel of each other, W16 bit-exact through identity probes."""
+    from oracle.build_ref import load_ref
+    ref = load_ref()
+    if ref is None:
+        pytest.skip("oracle/_ref/quick_kernels_ref.so not built (needs /root/reference at build time)")
+    import quick_kernels
+    for (K, N, G, sk) in [(512, 512, 128, 8), (4096, 4096, 128, 8), (4096, 11008, 128, 2), (256, 768, 64, 2)]:
+        q, z, s, qw, qz, sc, W16 = make_gpu_case(ops, K, N, G)
+        for M in (1, 8, 16, 17, 64, 100, 256):
+            A = torch.from_numpy(qo.make_activations(M, K, seed=M)).cuda()
+            r = ref.gemm_forward_cuda_quick(A, qw, sc, qz, sk).reshape(M, N)
+            mine = quick_kernels.gemm_forward_cuda_quick(A, qw, sc, qz, sk).reshape(M, N)
+            assert_close(mine, r.double(), f"vs reference K={K} N={N} M={M}")
+        A = torch.zeros(64, K, dtype=torch.float16, device="cuda")
+        A[torch.arange(64), torch.arange(64)] = 1
+        r = ref.gemm_forward_cuda_quick(A, qw, sc, qz, 1).reshape(64, N)
+        mine = quick_kernels.gemm_forward_cuda_quick(A, qw, sc, qz, 1).reshape(64, N)
+        assert torch.equal(mine, r), "identity probe: W16 must be bit-identical to the reference kernel's"

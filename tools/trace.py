@@ -1,0 +1,27 @@
+"""Dump the in-kernel clock64 trace of CTA (0,0,0) for one launch (debug tool)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from quick_b200 import ops, _lib
+tok, split, M, K, N = map(int, sys.argv[1:6]); G = 128
+dev = "cuda"
+wq = torch.randint(-2**31, 2**31 - 1, (K * N // 8,), device=dev, dtype=torch.int32)
+sz = torch.full((K // G * N,), 0x64082000, device=dev, dtype=torch.int32)
+x = torch.randn(M, K, device=dev).half()
+for _ in range(3): ops.gemm(x, wq, sz, N, G, tok=tok, split=split)
+torch.cuda.synchronize()
+tr = torch.zeros(4 * 256 * 4, dtype=torch.int64, device=dev)
+lib = _lib.load(); lib.qb200_debug_set_trace(tr.data_ptr())
+ops.gemm(x, wq, sz, N, G, tok=tok, split=split); torch.cuda.synchronize()
+lib.qb200_debug_set_trace(None)
+t = tr.cpu().view(4, 256, 4)
+t0 = int(t[3, 0, 0])
+rel = lambda v: int(v) - t0 if int(v) else None
+nkb = K // 64 // split
+print("cfg", tok, split, M, K, N, "stages", nkb)
+print("setup_done", rel(t[3, 0, 1]), "accum_seen", rel(t[3, 0, 2]), "epi_done", rel(t[3, 0, 3]), "dealloc", rel(t[3, 1, 0]))
+print("it | prod: slot_free issued | mma: full tfull mma1 mma4 commit1 commit2 | deq: full deq_done tempty st_issued")
+for it in range(min(nkb, 40)):
+    print(it, "|", rel(t[0, it, 0]), rel(t[0, it, 1]), "|", rel(t[1, it, 0]), rel(t[1, it, 1]), rel(t[1, it, 2]), rel(t[1, it, 3]), rel(t[0, it, 2]), rel(t[0, it, 3]), "|",
+          rel(t[2, it, 0]), rel(t[2, it, 1]), rel(t[2, it, 2]), rel(t[2, it, 3]))
