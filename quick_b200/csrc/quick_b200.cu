@@ -247,7 +247,7 @@ int device_sm_count() {
   return sms;
 }
 
-template <int TOK, int SPLIT, int KT = qb200::default_tstages<TOK>()>
+template <int TOK, int SPLIT, int KT = qb200::default_depth<TOK>()>
 int launch_umma(const CUtensorMap& map, const qb200::GemmArgs& args, int m_tiles, cudaStream_t stream) {
   using Cfg = qb200::TileCfg<TOK, KT>;
   auto kfn = qb200::w4a16_umma_kernel<TOK, SPLIT, KT>;
@@ -273,24 +273,8 @@ int launch_umma(const CUtensorMap& map, const qb200::GemmArgs& args, int m_tiles
   return QB200_OK;
 }
 
-int experiment_kt() {   // QB200_KT: tuning experiments only
-  static int kt = -1;
-  if (kt < 0) { const char* e = getenv("QB200_KT"); kt = e ? atoi(e) : 0; }
-  return kt;
-}
-
 template <int TOK>
 int dispatch_split(int split, const CUtensorMap& map, const qb200::GemmArgs& args, int m_tiles, cudaStream_t st) {
-  const int kt = experiment_kt();
-  if constexpr (TOK == 16) {
-    if (kt == 4 && split == 4) return launch_umma<16, 4, 4>(map, args, m_tiles, st);
-    if (kt == 14 && split == 4) return launch_umma<16, 4, 14>(map, args, m_tiles, st);
-    if (kt == 4 && split == 1) return launch_umma<16, 1, 4>(map, args, m_tiles, st);
-    if (kt == 14 && split == 1) return launch_umma<16, 1, 14>(map, args, m_tiles, st);
-  }
-  if constexpr (TOK == 256) {
-    if (kt == 4 && split == 1) return launch_umma<256, 1, 4>(map, args, m_tiles, st);
-  }
   switch (split) {
     case 1: return launch_umma<TOK, 1>(map, args, m_tiles, st);
     case 2: return launch_umma<TOK, 2>(map, args, m_tiles, st);

@@ -255,25 +255,25 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
   return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
 }
 
-// default depth of the TMEM A-operand ring (32 columns per stage)
+// Ring depth D: the shared-memory stages (W nibbles + X tile) and the TMEM A-operand stages form ONE
+// ring, so a single "consumed" barrier per slot (4 dequant-warp arrivals + 1 tcgen05.commit) releases
+// both.  Chosen so that TOK + 32*D TMEM columns and D stages of shared memory allow 2 CTAs / SM for
+// TOK <= 128 (latency hiding for the small, HBM-bound tiles).
 template <int TOK>
-constexpr int default_tstages() { return TOK == 256 ? 8 : TOK == 128 ? 4 : 6; }
+constexpr int default_depth() { return TOK <= 32 ? 7 : TOK == 64 ? 6 : TOK == 128 ? 4 : 6; }
 
-template <int TOK, int KT = default_tstages<TOK>()>
+template <int TOK, int D = default_depth<TOK>()>
 struct TileCfg {
-  static constexpr int kTStages = KT;
+  static constexpr int kDepth = D;
   static constexpr int kXStageBytes = TOK * 128;
   static constexpr int kStageBytes = kXStageBytes + kWStageBytes;
   static constexpr int kACol0 = TOK < 32 ? 32 : TOK;
-  static constexpr int kColsNeeded = kACol0 + 32 * kTStages;
+  static constexpr int kColsNeeded = kACol0 + 32 * D;
   static constexpr int kTmemCols = kColsNeeded <= 32 ? 32 : kColsNeeded <= 64 ? 64 : kColsNeeded <= 128 ? 128
                                    : kColsNeeded <= 256 ? 256 : 512;
-  // pipeline depth: keep whole split-K slabs in flight for small tiles (HBM latency bound),
-  // 4-5 stages for the tensor-bound tiles
-  static constexpr int kStages = TOK == 16 ? 16 : TOK == 32 ? 12 : TOK == 64 ? 8 : TOK == 128 ? 6 : 5;
-  static constexpr int kBarBytes = (2 * kStages + 2 * kTStages + 1) * 8 + 16;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;   // + manual 1024-B alignment slack
-  static_assert(kStages * kXStageBytes >= kChan * TOK * 4 || true, "");
+  static_assert(kColsNeeded <= 512, "TMEM budget");
+  static constexpr int kBarBytes = (3 * D + 1) * 8 + 16;
+  static constexpr int kSmemBytes = D * kStageBytes + kBarBytes + 1024;   // + manual 1024-B alignment slack
 };
 
 struct GemmArgs {
@@ -291,32 +291,47 @@ struct GemmArgs {
       args.trace[((slot) * 256 + (it)) * 4 + (k)] = clock64();                                 \
   } while (0)
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, unsigned short v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------
-template <int TOK, int SPLIT, int KT = default_tstages<TOK>()>
+template <int TOK, int SPLIT, int D = default_depth<TOK>()>
 __global__ void __launch_bounds__(kNumThreads, 1)
 w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs args) {
-  using Cfg = TileCfg<TOK, KT>;
-  constexpr int kTStages = KT;
-  constexpr int STAGES = Cfg::kStages;
+  using Cfg = TileCfg<TOK, D>;
   constexpr int SLICE = TOK / SPLIT;          // token columns owned by one cluster rank
   constexpr int CH = SLICE / 2;               // columns per (owner, warpgroup)
   static_assert(CH >= 1, "TOK / SPLIT must be >= 2");
   constexpr int PIECE = CH < 16 ? CH : 16;    // columns per tcgen05.ld
-  static_assert(SPLIT == 1 || STAGES * Cfg::kXStageBytes >= kChan * TOK * 4, "reduction buffer must fit the X stages");
+  // epilogue staging (aliases pipeline buffers that are dead once the accumulator is complete)
+  constexpr int kXRegion = D * Cfg::kXStageBytes;
+  constexpr int kRecvBytes = SPLIT > 1 ? kChan * TOK * 4 : 0;     // [src rank][SLICE][128] fp32
+  constexpr int kOutBytes = SLICE * kChan * 2;                    // [SLICE tokens][128 channels] fp16
+  constexpr bool kOutAfterRecv = kRecvBytes + kOutBytes <= kXRegion;
+  static_assert(kRecvBytes <= kXRegion, "reduction buffer must fit the X stages");
+  static_assert(kOutAfterRecv || kOutBytes <= D * kWStageBytes, "output staging tile does not fit");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t smem_x = smem_base;                                   // STAGES x [TOK rows][128 B] swizzled
-  const uint32_t smem_w = smem_base + STAGES * Cfg::kXStageBytes;      // STAGES x [2][128][16 B]
-  const uint32_t bar_base = smem_w + STAGES * kWStageBytes;
-  const uint32_t bar_full = bar_base;                                  // TMA landed (W + X)
-  const uint32_t bar_empty = bar_full + 8 * STAGES;                    // stage free: 4 dequant warps + 1 MMA commit
-  const uint32_t bar_tfull = bar_empty + 8 * STAGES;                   // A operand written to TMEM stage
-  const uint32_t bar_tempty = bar_tfull + 8 * kTStages;                // MMAs reading the TMEM stage done
-  const uint32_t bar_accum = bar_tempty + 8 * kTStages;                // all MMAs of the tile done
+  const uint32_t smem_x = smem_base;                                   // D x [TOK rows][128 B] swizzled
+  const uint32_t smem_w = smem_base + D * Cfg::kXStageBytes;           // D x [2][128][16 B]
+  const uint32_t bar_full = smem_w + D * kWStageBytes;                 // TMA landed (W + X)
+  const uint32_t bar_tfull = bar_full + 8 * D;                         // A operand written to TMEM slot
+  const uint32_t bar_cons = bar_tfull + 8 * D;                         // slot consumed: 4 dequant warps + MMA commit
+  const uint32_t bar_accum = bar_cons + 8 * D;                         // all MMAs of the tile done
   const uint32_t tmem_ptr_smem = bar_accum + 8;
+  const uint32_t smem_out = kOutAfterRecv ? smem_x + kRecvBytes : smem_w;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -329,13 +344,10 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
 
   if (threadIdx.x == 0) QB_TRACE(3, 0, 0);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) {
+    for (int i = 0; i < D; ++i) {
       mbar_init(bar_full + 8 * i, 1);
-      mbar_init(bar_empty + 8 * i, 5);
-    }
-    for (int i = 0; i < kTStages; ++i) {
       mbar_init(bar_tfull + 8 * i, 4);
-      mbar_init(bar_tempty + 8 * i, 1);
+      mbar_init(bar_cons + 8 * i, 5);
     }
     mbar_init(bar_accum, 1);
     fence_barrier_init();
@@ -351,13 +363,13 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
   if (threadIdx.x == 0) QB_TRACE(3, 0, 1);
 
   if (warp == kProducerWarp) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      const uint32_t* wsrc = args.wq + (static_cast<size_t>(nt) * KB + kb0) * (kWStageBytes / 4);
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+    // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+    const uint32_t* wsrc = args.wq + (static_cast<size_t>(nt) * KB + kb0) * (kWStageBytes / 4);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < nkb; ++it) {
+      mbar_wait(bar_cons + 8 * s, ph ^ 1);
+      if (elect_one()) {
         QB_TRACE(0, it, 0);
         mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::kStageBytes);
         bulk_g2s(smem_w + s * kWStageBytes, wsrc + static_cast<size_t>(it) * (kWStageBytes / 4), kWStageBytes,
@@ -365,39 +377,36 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
         tma_load_2d(smem_x + s * Cfg::kXStageBytes, &tmap_x, bar_full + 8 * s, (kb0 + it) * kBK, mt * TOK);
         QB_TRACE(0, it, 1);
       }
+      __syncwarp();
+      if (++s == D) { s = 0; ph ^= 1; }
     }
-    __syncwarp();
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(TOK);
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        const int t = it % kTStages;
-        const uint32_t tph = (it / kTStages) & 1;
-        mbar_wait(bar_full + 8 * s, ph);
+    // Waits only on "A operand in TMEM": the dequant warps observed the TMA barrier of the same slot before
+    // writing it, so the X tile of the slot is complete (and ordered) by then.
+    constexpr uint32_t idesc = make_idesc_f16(TOK);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < nkb; ++it) {
+      mbar_wait(bar_tfull + 8 * s, ph);
+      tc_fence_after();
+      if (elect_one()) {
         QB_TRACE(1, it, 0);
-        mbar_wait(bar_tfull + 8 * t, tph);
-        QB_TRACE(1, it, 1);
-        tc_fence_after();
         const uint64_t bdesc = make_smem_desc_sw128(smem_x + s * Cfg::kXStageBytes);
-        const uint32_t a_tmem = tmem_base + Cfg::kACol0 + t * 32;
+        const uint32_t a_tmem = tmem_base + Cfg::kACol0 + s * 32;
 #pragma unroll
         for (int j = 0; j < kBK / 16; ++j) {
           // +32 B (= 2 in 16-B units) of start address per k16 step inside the 128-B swizzle row
           umma_f16_ts(tmem_base, a_tmem + j * 8, bdesc + 2 * j, idesc, (it | j) != 0 ? 1u : 0u);
-          if (j == 0) QB_TRACE(1, it, 2);
         }
-        QB_TRACE(1, it, 3);
-        umma_commit(bar_empty + 8 * s);    // X stage (and with the dequant arrivals, the whole stage) free
-        QB_TRACE(0, it, 2);
-        umma_commit(bar_tempty + 8 * t);   // TMEM A stage free
-        QB_TRACE(0, it, 3);
+        QB_TRACE(1, it, 1);
+        umma_commit(bar_cons + 8 * s);     // smem slot + TMEM slot free once these MMAs have completed
+        if (it == nkb - 1) umma_commit(bar_accum);
+        QB_TRACE(1, it, 2);
       }
-      umma_commit(bar_accum);
+      __syncwarp();
+      if (++s == D) { s = 0; ph ^= 1; }
     }
-    __syncwarp();
   } else {
     // ===================== dequant warps: smem nibbles -> registers -> TMEM A operand =====================
     const int wg = warp >> 2;                       // warpgroup 0/1 takes even/odd stages
@@ -405,43 +414,40 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
     const int ch = quad * 32 + lane;                // output channel within the tile = TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
     const int NG = args.K / args.G;
+    const int g32 = args.G >> 5;                    // k32 blocks per group
     const uint32_t* szp = args.sz + static_cast<size_t>(nt) * NG * kChan + ch;
-    // Software-pipelined: the scale/zero words of the next stage are prefetched one iteration ahead and
-    // the TMEM hand-off of stage i (wait::st + arrive) is deferred until stage i+2 has been unpacked,
-    // so neither the global-load latency nor the tcgen05.st latency sits on the per-stage chain.
-    int it = wg;
+    // (group, remainder) of the k32 block this thread handles next, advanced incrementally (no divisions in the loop)
+    int kq = (kb0 + wg) * 2;
+    int grp = kq / g32, rem = kq % g32;
+    auto group_of_next_half = [&](int& g_lo, int& g_hi) {
+      g_lo = grp;
+      g_hi = (rem + 1 >= g32) ? grp + 1 : grp;
+    };
+    int g_lo, g_hi;
+    group_of_next_half(g_lo, g_hi);
     uint32_t sz0 = 0, sz1 = 0;
-    if (it < nkb) {
-      const int k0 = (kb0 + it) * kBK;
-      sz0 = __ldg(szp + static_cast<size_t>(k0 / args.G) * kChan);
-      sz1 = __ldg(szp + static_cast<size_t>((k0 + 32) / args.G) * kChan);
+    if (wg < nkb) {
+      sz0 = __ldg(szp + static_cast<size_t>(g_lo) * kChan);
+      sz1 = __ldg(szp + static_cast<size_t>(g_hi) * kChan);
     }
-    bool pending = false;
-    int t_prev = 0;
-    for (; it < nkb; it += 2) {
-      const int s = it % STAGES;
-      const uint32_t ph = (it / STAGES) & 1;
-      const int t = it % kTStages;
-      const uint32_t tph = (it / kTStages) & 1;
-      if (pending && !mbar_try(bar_full + 8 * s, ph)) {   // starved: do not sit on a finished stage
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tfull + 8 * t_prev);
-        pending = false;
-      }
+    int s = wg % D;
+    uint32_t ph = 0;
+    for (int it = wg; it < nkb; it += 2) {
       mbar_wait(bar_full + 8 * s, ph);
       if (lane == 0 && quad == 2) QB_TRACE(2, it, 0);
       const uint4 w0 = lds128(smem_w + s * kWStageBytes + ch * 16);
       const uint4 w1 = lds128(smem_w + s * kWStageBytes + 2048 + ch * 16);
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+      if (lane == 0) mbar_arrive(bar_cons + 8 * s);     // W nibbles are in registers
       const GroupConsts g0 = make_group_consts(sz0);
       const GroupConsts g1 = make_group_consts(sz1);
+      // advance 4 k32 blocks (two stages) and prefetch the next scale/zero words
+      rem += 4;
+      while (rem >= g32) { rem -= g32; ++grp; }
       if (it + 2 < nkb) {
-        const int k0n = (kb0 + it + 2) * kBK;
-        sz0 = __ldg(szp + static_cast<size_t>(k0n / args.G) * kChan);
-        sz1 = __ldg(szp + static_cast<size_t>((k0n + 32) / args.G) * kChan);
+        group_of_next_half(g_lo, g_hi);
+        sz0 = __ldg(szp + static_cast<size_t>(g_lo) * kChan);
+        sz1 = __ldg(szp + static_cast<size_t>(g_hi) * kChan);
       }
       uint32_t r[32];
       dequant_word(w0.x, g0, r + 0);
@@ -452,28 +458,21 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
       dequant_word(w1.y, g1, r + 20);
       dequant_word(w1.z, g1, r + 24);
       dequant_word(w1.w, g1, r + 28);
-      if (pending) {
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tfull + 8 * t_prev);
-      }
       if (lane == 0 && quad == 2) QB_TRACE(2, it, 1);
-      mbar_wait(bar_tempty + 8 * t, tph ^ 1);
+      // TMEM slot s is free once the MMAs of iteration it - D have completed (the previous phase of bar_cons)
+      mbar_wait(bar_cons + 8 * s, ph ^ 1);
       tc_fence_after();
       if (lane == 0 && quad == 2) QB_TRACE(2, it, 2);
-      const uint32_t a_tmem = tmem_base + lane_addr + Cfg::kACol0 + t * 32;
+      const uint32_t a_tmem = tmem_base + lane_addr + Cfg::kACol0 + s * 32;
       tmem_st16(a_tmem, r);
       tmem_st16(a_tmem + 16, r + 16);
-      if (lane == 0 && quad == 2) QB_TRACE(2, it, 3);
-      pending = true;
-      t_prev = t;
-    }
-    if (pending) {
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tfull + 8 * t_prev);
+      if (lane == 0) mbar_arrive(bar_tfull + 8 * s);
+      if (lane == 0 && quad == 2) QB_TRACE(2, it, 3);
+      s += 2;
+      if (s >= D) { s -= D; ph ^= 1; }
     }
   }
 
@@ -483,35 +482,18 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
   const int ch = quad * 32 + lane;
   const bool is_dq = warp < kNumDequantWarps;
   const uint32_t d_tmem = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-  const int n = nt * kChan + ch;
-  const float bias_v = (args.bias != nullptr && is_dq) ? __half2float(args.bias[n]) : 0.f;
+  const int n0 = nt * kChan;
+  const float bias_v = (args.bias != nullptr && is_dq) ? __half2float(args.bias[n0 + ch]) : 0.f;
 
-  if constexpr (SPLIT == 1) {
-    if (is_dq) {
-      mbar_wait(bar_accum, 0);
-      tc_fence_after();
-      if (threadIdx.x == 0) QB_TRACE(3, 0, 2);
-#pragma unroll 1
-      for (int p = 0; p < CH / PIECE; ++p) {
-        const int col0 = wg * CH + p * PIECE;
-        uint32_t v[PIECE];
-        tmem_ld<PIECE>(d_tmem + col0, v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < PIECE; ++i) {
-          const int m = mt * TOK + col0 + i;
-          if (m < args.M) args.C[static_cast<size_t>(m) * args.N + n] = __float2half_rn(__uint_as_float(v[i]) + bias_v);
-        }
-      }
-    }
-  } else {
-    // reduction buffer aliases the (now dead) X stages: [src rank][SLICE columns][128 channels] fp32
-    if (is_dq) {
-      mbar_wait(bar_accum, 0);   // every TMA write landed and every MMA read of this CTA's smem is complete
-      tc_fence_after();
-    }
+  if (is_dq) {
+    mbar_wait(bar_accum, 0);   // every TMA write landed and every MMA read of this CTA's smem is complete
+    tc_fence_after();
+    if (threadIdx.x == 0) QB_TRACE(3, 0, 2);
+  }
+  if constexpr (SPLIT > 1) {
+    // exchange partial tiles through distributed shared memory: rank o receives columns [o*SLICE, (o+1)*SLICE)
     cluster_arrive();
-    cluster_wait();              // every CTA of the cluster is past its main loop
+    cluster_wait();              // every CTA of the cluster is past its main loop (its X stages are dead)
     if (is_dq) {
 #pragma unroll 1
       for (int o = 0; o < SPLIT; ++o) {
@@ -532,20 +514,47 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
     }
     cluster_arrive();
     cluster_wait();              // all partial slices have landed in their owners' shared memory
-    if (is_dq) {
+  }
+  if (is_dq) {
+    // this thread's CH columns of the owned slice -> fp16 -> staging tile [token][channel]
+    if constexpr (SPLIT == 1) {
+#pragma unroll 1
+      for (int p = 0; p < CH / PIECE; ++p) {
+        const int j0 = wg * CH + p * PIECE;
+        uint32_t v[PIECE];
+        tmem_ld<PIECE>(d_tmem + j0, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < PIECE; ++i)
+          sts_u16(smem_out + static_cast<uint32_t>(((j0 + i) * kChan + ch) * 2),
+                  __half_as_ushort(__float2half_rn(__uint_as_float(v[i]) + bias_v)));
+      }
+    } else {
 #pragma unroll 1
       for (int i = 0; i < CH; ++i) {
         const int j = wg * CH + i;
         float acc = bias_v;
 #pragma unroll
         for (int r = 0; r < SPLIT; ++r) acc += lds_f32(smem_x + static_cast<uint32_t>(((r * SLICE + j) * kChan + ch) * 4));
-        const int m = mt * TOK + rank * SLICE + j;
-        if (m < args.M) args.C[static_cast<size_t>(m) * args.N + n] = __float2half_rn(acc);
+        sts_u16(smem_out + static_cast<uint32_t>((j * kChan + ch) * 2), __half_as_ushort(__float2half_rn(acc)));
       }
     }
+    named_bar_sync(1, kNumDequantWarps * 32);
+    // coalesced 16-byte stores: 16 threads cover one 256-byte token row of the tile
+    const int tid = threadIdx.x;             // 0..255
+    const int chunk = tid & 15;
+    const int m_base = mt * TOK + rank * SLICE;
+#pragma unroll 1
+    for (int row = tid >> 4; row < SLICE; row += (kNumDequantWarps * 32) / 16) {
+      const int m = m_base + row;
+      if (m < args.M) {
+        const uint4 v = lds128(smem_out + static_cast<uint32_t>(row * kChan * 2 + chunk * 16));
+        *reinterpret_cast<uint4*>(args.C + static_cast<size_t>(m) * args.N + n0 + chunk * 8) = v;
+      }
+    }
+    if (threadIdx.x == 0) QB_TRACE(3, 0, 3);
   }
 
-  if (threadIdx.x == 0) QB_TRACE(3, 0, 3);
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, Cfg::kTmemCols);

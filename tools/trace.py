@@ -21,7 +21,7 @@ rel = lambda v: int(v) - t0 if int(v) else None
 nkb = K // 64 // split
 print("cfg", tok, split, M, K, N, "stages", nkb)
 print("setup_done", rel(t[3, 0, 1]), "accum_seen", rel(t[3, 0, 2]), "epi_done", rel(t[3, 0, 3]), "dealloc", rel(t[3, 1, 0]))
-print("it | prod: slot_free issued | mma: full tfull mma1 mma4 commit1 commit2 | deq: full deq_done tempty st_issued")
+print("it | prod: slot_free issued | mma: tfull mmas_issued committed | deq: full deq_done slot_free handed_off")
 for it in range(min(nkb, 40)):
-    print(it, "|", rel(t[0, it, 0]), rel(t[0, it, 1]), "|", rel(t[1, it, 0]), rel(t[1, it, 1]), rel(t[1, it, 2]), rel(t[1, it, 3]), rel(t[0, it, 2]), rel(t[0, it, 3]), "|",
+    print(it, "|", rel(t[0, it, 0]), rel(t[0, it, 1]), "|", rel(t[1, it, 0]), rel(t[1, it, 1]), rel(t[1, it, 2]), "|",
           rel(t[2, it, 0]), rel(t[2, it, 1]), rel(t[2, it, 2]), rel(t[2, it, 3]))
