@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libquick_b200.so")
+LIB_PATH = os.environ.get("QB200_LIB") or os.path.join(_PKG, "libquick_b200.so")   # QB200_LIB: experiment builds only
 
 # every symbol include/quick_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [

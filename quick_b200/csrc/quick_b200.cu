@@ -322,7 +322,12 @@ extern "C" {
 const char* qb200_version(void) { return "quick_b200 0.1 (sm_100a tcgen05/TMEM/TMA W4A16)"; }
 const char* qb200_last_error(void) { return g_last_error.c_str(); }
 unsigned long long qb200_launch_count(void) { return g_launches.load(); }
-void qb200_debug_set_trace(void* device_buffer) { g_trace = reinterpret_cast<long long*>(device_buffer); }
+void qb200_debug_set_trace(void* device_buffer) {
+  g_trace = reinterpret_cast<long long*>(device_buffer);
+  // the same buffer (host-mapped if it should survive a trap) receives the timed-out-wait report
+  unsigned long long* p = reinterpret_cast<unsigned long long*>(device_buffer);
+  cudaMemcpyToSymbol(qb200::g_qb_timeout_report, &p, sizeof(p));
+}
 
 size_t qb200_wq_bytes(int K, int N) { return static_cast<size_t>(K) * N / 2; }
 size_t qb200_sz_bytes(int K, int N, int G) { return static_cast<size_t>(K / G) * N * 4; }

@@ -53,9 +53,12 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
                : "memory");
 }
 #ifndef QB200_WAIT_TIMEOUT_CYCLES
-#define QB200_WAIT_TIMEOUT_CYCLES 4000000000ll  // ~2 s: a lost barrier traps instead of hanging the GPU
+#define QB200_WAIT_TIMEOUT_CYCLES 2000000000ll  // ~1 s: a lost barrier traps instead of hanging the GPU
 #endif
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// Optional host-mapped buffer (qb200_debug_set_trace): a timed-out wait records who was waiting on what
+// before trapping, so a protocol bug is diagnosable after the context is gone.
+__device__ unsigned long long* g_qb_timeout_report = nullptr;
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0, int iter = -1) {
   uint32_t done = 0;
   long long t0 = 0;
   bool timed = false;
@@ -67,7 +70,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     if (done) break;
     if (!timed) { t0 = clock64(); timed = true; }
-    else if (clock64() - t0 > QB200_WAIT_TIMEOUT_CYCLES) { __trap(); }
+    else if (clock64() - t0 > QB200_WAIT_TIMEOUT_CYCLES) {
+      unsigned long long* rep = g_qb_timeout_report;
+      if (rep != nullptr && (threadIdx.x & 31) == 0) {
+        // first block to time out claims the report; each of its warps fills its own row, then lingers so
+        // the other warps of the block (stuck on the same lost event) can report before the trap
+        const unsigned long long me = 1ull + ((static_cast<unsigned long long>(blockIdx.x) << 20) | (blockIdx.y << 10) | blockIdx.z);
+        const unsigned long long prev = atomicCAS(rep, 0ull, me);
+        if (prev == 0ull || prev == me) {
+          unsigned long long st;
+          asm volatile("ld.shared.u64 %0, [%1];" : "=l"(st) : "r"(bar) : "memory");
+          unsigned long long* row = rep + 8 + (threadIdx.x >> 5) * 8;
+          row[0] = tag; row[1] = iter; row[2] = bar; row[3] = parity; row[4] = st; row[5] = 1;
+          __threadfence_system();
+        }
+        const long long t1 = clock64();
+        while (clock64() - t1 < QB200_WAIT_TIMEOUT_CYCLES / 4) { }
+      }
+      __trap();
+    }
   }
 }
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
@@ -255,25 +276,30 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
   return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
 }
 
-// Ring depth D: the shared-memory stages (W nibbles + X tile) and the TMEM A-operand stages form ONE
-// ring, so a single "consumed" barrier per slot (4 dequant-warp arrivals + 1 tcgen05.commit) releases
-// both.  Chosen so that TOK + 32*D TMEM columns and D stages of shared memory allow 2 CTAs / SM for
-// TOK <= 128 (latency hiding for the small, HBM-bound tiles).
+// Pipeline stage = 128 k (two k64 blocks): W nibbles 8 KB, X tile 2 x [TOK][128 B] swizzled panels, TMEM A
+// slot 64 columns.  The shared-memory stages and the TMEM A slots form ONE ring of depth D, so a single
+// "consumed" barrier per slot (4 dequant-warp arrivals + 1 tcgen05.commit) releases both.  Depths are
+// chosen so that TOK <= 64 tiles fit 2 CTAs / SM (TMEM <= 256 columns, smem <= ~110 KB).
+constexpr int kSubPerStage = 2;                          // k64 blocks per stage
+constexpr int kWStageBytesV3 = kSubPerStage * kWStageBytes;   // 8192
 template <int TOK>
-constexpr int default_depth() { return TOK <= 32 ? 7 : TOK == 64 ? 6 : TOK == 128 ? 4 : 6; }
+constexpr int default_depth() { return TOK <= 64 ? 3 : TOK == 128 ? 4 : 3; }
 
 template <int TOK, int D = default_depth<TOK>()>
 struct TileCfg {
   static constexpr int kDepth = D;
-  static constexpr int kXStageBytes = TOK * 128;
-  static constexpr int kStageBytes = kXStageBytes + kWStageBytes;
+  static constexpr int kXPanelBytes = TOK * 128;                      // one k64 panel
+  static constexpr int kXStageBytes = kSubPerStage * kXPanelBytes;
+  static constexpr int kStageBytes = kXStageBytes + kWStageBytesV3;
   static constexpr int kACol0 = TOK < 32 ? 32 : TOK;
-  static constexpr int kColsNeeded = kACol0 + 32 * D;
+  static constexpr int kASlotCols = 32 * kSubPerStage;
+  static constexpr int kColsNeeded = kACol0 + kASlotCols * D;
   static constexpr int kTmemCols = kColsNeeded <= 32 ? 32 : kColsNeeded <= 64 ? 64 : kColsNeeded <= 128 ? 128
                                    : kColsNeeded <= 256 ? 256 : 512;
   static_assert(kColsNeeded <= 512, "TMEM budget");
   static constexpr int kBarBytes = (3 * D + 1) * 8 + 16;
   static constexpr int kSmemBytes = D * kStageBytes + kBarBytes + 1024;   // + manual 1024-B alignment slack
+  static constexpr int kMinBlocks = (TOK <= 64) ? 2 : 1;
 };
 
 struct GemmArgs {
@@ -282,14 +308,18 @@ struct GemmArgs {
   const __half* bias;
   __half* C;
   int M, K, N, G;
-  int kb_per_split;
-  long long* trace;   // debug: per-role clock64 stamps of CTA (0,0,0); nullptr in production
+  int kb_per_split;   // k64 blocks per cluster rank
+  long long* trace;   // debug (QB200_TRACE builds only): clock64 stamps of CTA (0,0,0)
 };
+#ifdef QB200_TRACE
 #define QB_TRACE(slot, it, k)                                                                  \
   do {                                                                                         \
     if (args.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)         \
       args.trace[((slot) * 256 + (it)) * 4 + (k)] = clock64();                                 \
   } while (0)
+#else
+#define QB_TRACE(slot, it, k) do { } while (0)
+#endif
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -302,36 +332,55 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __device__ __forceinline__ void sts_u16(uint32_t addr, unsigned short v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t a) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_half2(uint32_t v) {
+  return __half22float2(*reinterpret_cast<__half2*>(&v));
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 
 // ------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------
 template <int TOK, int SPLIT, int D = default_depth<TOK>()>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(kNumThreads, TileCfg<TOK, D>::kMinBlocks)
 w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs args) {
   using Cfg = TileCfg<TOK, D>;
   constexpr int SLICE = TOK / SPLIT;          // token columns owned by one cluster rank
   constexpr int CH = SLICE / 2;               // columns per (owner, warpgroup)
   static_assert(CH >= 1, "TOK / SPLIT must be >= 2");
   constexpr int PIECE = CH < 16 ? CH : 16;    // columns per tcgen05.ld
-  // epilogue staging (aliases pipeline buffers that are dead once the accumulator is complete)
-  constexpr int kXRegion = D * Cfg::kXStageBytes;
-  constexpr int kRecvBytes = SPLIT > 1 ? kChan * TOK * 4 : 0;     // [src rank][SLICE][128] fp32
-  constexpr int kOutBytes = SLICE * kChan * 2;                    // [SLICE tokens][128 channels] fp16
-  constexpr bool kOutAfterRecv = kRecvBytes + kOutBytes <= kXRegion;
-  static_assert(kRecvBytes <= kXRegion, "reduction buffer must fit the X stages");
-  static_assert(kOutAfterRecv || kOutBytes <= D * kWStageBytes, "output staging tile does not fit");
+  // Epilogue staging aliases pipeline buffers that are dead once the accumulator is complete.
+  //   recv : partial slices from the other SPLIT-1 ranks, fp16, [src][channel][SLICE (+8 pad) halves]
+  //   out  : this CTA's [SLICE tokens][128 channels] fp16 tile, stored with 16-byte coalesced writes
+  constexpr int kRowHalves = SLICE + 8;                                   // +16 B: conflict-free 16-B row stores
+  constexpr int kRecvBytes = SPLIT > 1 ? (SPLIT - 1) * kChan * kRowHalves * 2 : 0;
+  constexpr int kOutBytes = SLICE * kChan * 2;
+  static_assert(kRecvBytes % 16 == 0 && kRecvBytes + kOutBytes <= D * Cfg::kStageBytes,
+                "epilogue staging must fit the (dead) pipeline stages: X stages then W stages are contiguous");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t smem_x = smem_base;                                   // D x [TOK rows][128 B] swizzled
-  const uint32_t smem_w = smem_base + D * Cfg::kXStageBytes;           // D x [2][128][16 B]
-  const uint32_t bar_full = smem_w + D * kWStageBytes;                 // TMA landed (W + X)
+  const uint32_t smem_x = smem_base;                                   // D x 2 x [TOK rows][128 B] swizzled
+  const uint32_t smem_w = smem_base + D * Cfg::kXStageBytes;           // D x 2 x [2][128][16 B]
+  const uint32_t bar_full = smem_w + D * kWStageBytesV3;               // TMA landed (W + X)
   const uint32_t bar_tfull = bar_full + 8 * D;                         // A operand written to TMEM slot
   const uint32_t bar_cons = bar_tfull + 8 * D;                         // slot consumed: 4 dequant warps + MMA commit
   const uint32_t bar_accum = bar_cons + 8 * D;                         // all MMAs of the tile done
   const uint32_t tmem_ptr_smem = bar_accum + 8;
-  const uint32_t smem_out = kOutAfterRecv ? smem_x + kRecvBytes : smem_w;
+  const uint32_t smem_out = smem_x + kRecvBytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -340,7 +389,8 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
   const int rank = SPLIT > 1 ? static_cast<int>(cluster_ctarank()) : 0;
   const int KB = args.K / kBK;
   const int kb0 = rank * args.kb_per_split;
-  const int nkb = min(args.kb_per_split, KB - kb0);
+  const int nkb = min(args.kb_per_split, KB - kb0);            // k64 blocks of this CTA
+  const int nst = (nkb + kSubPerStage - 1) / kSubPerStage;     // pipeline stages (last may hold one block)
 
   if (threadIdx.x == 0) QB_TRACE(3, 0, 0);
   if (threadIdx.x == 0) {
@@ -367,18 +417,29 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
     const uint32_t* wsrc = args.wq + (static_cast<size_t>(nt) * KB + kb0) * (kWStageBytes / 4);
     int s = 0;
     uint32_t ph = 0;
-    for (int it = 0; it < nkb; ++it) {
-      mbar_wait(bar_cons + 8 * s, ph ^ 1);
+    for (int it = 0; it < nst; ++it) {
+      mbar_wait(bar_cons + 8 * s, ph ^ 1, 1, it);
       if (elect_one()) {
         QB_TRACE(0, it, 0);
-        mbar_arrive_expect_tx(bar_full + 8 * s, Cfg::kStageBytes);
-        bulk_g2s(smem_w + s * kWStageBytes, wsrc + static_cast<size_t>(it) * (kWStageBytes / 4), kWStageBytes,
-                 bar_full + 8 * s);
-        tma_load_2d(smem_x + s * Cfg::kXStageBytes, &tmap_x, bar_full + 8 * s, (kb0 + it) * kBK, mt * TOK);
+        const int nsub = min(kSubPerStage, nkb - it * kSubPerStage);
+        const uint32_t bar = bar_full + 8 * s;
+        mbar_arrive_expect_tx(bar, nsub * (kWStageBytes + Cfg::kXPanelBytes));
+        bulk_g2s(smem_w + s * kWStageBytesV3, wsrc + static_cast<size_t>(it) * (kWStageBytesV3 / 4), nsub * kWStageBytes, bar);
+        tma_load_2d(smem_x + s * Cfg::kXStageBytes, &tmap_x, bar, (kb0 + it * kSubPerStage) * kBK, mt * TOK);
+        if (nsub > 1)
+          tma_load_2d(smem_x + s * Cfg::kXStageBytes + Cfg::kXPanelBytes, &tmap_x, bar, (kb0 + it * kSubPerStage + 1) * kBK, mt * TOK);
         QB_TRACE(0, it, 1);
       }
       __syncwarp();
       if (++s == D) { s = 0; ph ^= 1; }
+    }
+    // Tail: observe the final "consumed" phase of every slot that was used.  The tcgen05.commit arrives are
+    // asynchronous; if the CTA exited before they landed they would hit the barrier words of the NEXT CTA
+    // scheduled on this SM (same shared-memory layout) and corrupt its phase accounting (seen as rare hangs
+    // under back-to-back launches).
+    for (int i = 0; i < min(D, nst); ++i) {
+      const int it = nst - 1 - i;
+      mbar_wait(bar_cons + 8 * (it % D), (it / D) & 1, 6, it);
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
@@ -387,21 +448,27 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
     constexpr uint32_t idesc = make_idesc_f16(TOK);
     int s = 0;
     uint32_t ph = 0;
-    for (int it = 0; it < nkb; ++it) {
-      mbar_wait(bar_tfull + 8 * s, ph);
+    for (int it = 0; it < nst; ++it) {
+      mbar_wait(bar_tfull + 8 * s, ph, 2, it);
       tc_fence_after();
       if (elect_one()) {
         QB_TRACE(1, it, 0);
+        const int nsub = min(kSubPerStage, nkb - it * kSubPerStage);
         const uint64_t bdesc = make_smem_desc_sw128(smem_x + s * Cfg::kXStageBytes);
-        const uint32_t a_tmem = tmem_base + Cfg::kACol0 + s * 32;
+        const uint32_t a_tmem = tmem_base + Cfg::kACol0 + s * Cfg::kASlotCols;
 #pragma unroll
         for (int j = 0; j < kBK / 16; ++j) {
           // +32 B (= 2 in 16-B units) of start address per k16 step inside the 128-B swizzle row
           umma_f16_ts(tmem_base, a_tmem + j * 8, bdesc + 2 * j, idesc, (it | j) != 0 ? 1u : 0u);
         }
+        if (nsub > 1) {
+          const uint64_t bdesc1 = bdesc + (Cfg::kXPanelBytes >> 4);
+#pragma unroll
+          for (int j = 0; j < kBK / 16; ++j) umma_f16_ts(tmem_base, a_tmem + 32 + j * 8, bdesc1 + 2 * j, idesc, 1u);
+        }
         QB_TRACE(1, it, 1);
         umma_commit(bar_cons + 8 * s);     // smem slot + TMEM slot free once these MMAs have completed
-        if (it == nkb - 1) umma_commit(bar_accum);
+        if (it == nst - 1) umma_commit(bar_accum);
         QB_TRACE(1, it, 2);
       }
       __syncwarp();
@@ -416,61 +483,78 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
     const int NG = args.K / args.G;
     const int g32 = args.G >> 5;                    // k32 blocks per group
     const uint32_t* szp = args.sz + static_cast<size_t>(nt) * NG * kChan + ch;
-    // (group, remainder) of the k32 block this thread handles next, advanced incrementally (no divisions in the loop)
-    int kq = (kb0 + wg) * 2;
+    // group index of each of the 4 k32 blocks of the next stage, advanced incrementally (no divisions in the loop)
+    int kq = (kb0 + wg * kSubPerStage) * 2;
     int grp = kq / g32, rem = kq % g32;
-    auto group_of_next_half = [&](int& g_lo, int& g_hi) {
-      g_lo = grp;
-      g_hi = (rem + 1 >= g32) ? grp + 1 : grp;
+    uint32_t szw[4];
+    auto load_sz = [&]() {
+      int g = grp, r = rem;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        szw[q] = __ldg(szp + static_cast<size_t>(min(g, NG - 1)) * kChan);
+        if (++r >= g32) { r = 0; ++g; }
+      }
     };
-    int g_lo, g_hi;
-    group_of_next_half(g_lo, g_hi);
-    uint32_t sz0 = 0, sz1 = 0;
-    if (wg < nkb) {
-      sz0 = __ldg(szp + static_cast<size_t>(g_lo) * kChan);
-      sz1 = __ldg(szp + static_cast<size_t>(g_hi) * kChan);
-    }
+    if (wg < nst) load_sz();
     int s = wg % D;
     uint32_t ph = 0;
-    for (int it = wg; it < nkb; it += 2) {
-      mbar_wait(bar_full + 8 * s, ph);
+    for (int it = wg; it < nst; it += 2) {
+      const int nsub = min(kSubPerStage, nkb - it * kSubPerStage);
+      // mbarrier parity waits are only valid one phase ahead.  The other warpgroup consumes stage it-1, and
+      // TMA completions arrive out of order, so this warp must first observe stage it-1's barrier itself:
+      // otherwise, with slot reuse distance D odd, it could test slot s for stage `it` while the slot is
+      // still in the phase of stage it-D and the parity test would alias and pass (seen as rare hangs).
+      if (it > 0) {
+        const int sp = s == 0 ? D - 1 : s - 1;
+        const uint32_t php = s == 0 ? ph ^ 1 : ph;
+        mbar_wait(bar_full + 8 * sp, php, 7, it - 1);
+      }
+      mbar_wait(bar_full + 8 * s, ph, 3, it);
       if (lane == 0 && quad == 2) QB_TRACE(2, it, 0);
-      const uint4 w0 = lds128(smem_w + s * kWStageBytes + ch * 16);
-      const uint4 w1 = lds128(smem_w + s * kWStageBytes + 2048 + ch * 16);
+      const uint32_t wbase = smem_w + s * kWStageBytesV3 + ch * 16;
+      uint4 w[4];
+      w[0] = lds128(wbase);
+      w[1] = lds128(wbase + 2048);
+      if (nsub > 1) {
+        w[2] = lds128(wbase + 4096);
+        w[3] = lds128(wbase + 6144);
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_cons + 8 * s);     // W nibbles are in registers
-      const GroupConsts g0 = make_group_consts(sz0);
-      const GroupConsts g1 = make_group_consts(sz1);
-      // advance 4 k32 blocks (two stages) and prefetch the next scale/zero words
-      rem += 4;
+      GroupConsts gc[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) gc[q] = make_group_consts(szw[q]);
+      // advance two stages (8 k32 blocks) and prefetch the next scale/zero words
+      rem += 4 * kSubPerStage;
       while (rem >= g32) { rem -= g32; ++grp; }
-      if (it + 2 < nkb) {
-        group_of_next_half(g_lo, g_hi);
-        sz0 = __ldg(szp + static_cast<size_t>(g_lo) * kChan);
-        sz1 = __ldg(szp + static_cast<size_t>(g_hi) * kChan);
-      }
-      uint32_t r[32];
-      dequant_word(w0.x, g0, r + 0);
-      dequant_word(w0.y, g0, r + 4);
-      dequant_word(w0.z, g0, r + 8);
-      dequant_word(w0.w, g0, r + 12);
-      dequant_word(w1.x, g1, r + 16);
-      dequant_word(w1.y, g1, r + 20);
-      dequant_word(w1.z, g1, r + 24);
-      dequant_word(w1.w, g1, r + 28);
-      if (lane == 0 && quad == 2) QB_TRACE(2, it, 1);
-      // TMEM slot s is free once the MMAs of iteration it - D have completed (the previous phase of bar_cons)
-      mbar_wait(bar_cons + 8 * s, ph ^ 1);
+      if (it + 2 < nst) load_sz();
+      // TMEM slot s is free once the MMAs of stage it - D have completed (the previous phase of bar_cons);
+      // the producer already observed that phase before refilling the slot, this wait is the acquire.
+      mbar_wait(bar_cons + 8 * s, ph ^ 1, 4, it);
       tc_fence_after();
-      if (lane == 0 && quad == 2) QB_TRACE(2, it, 2);
-      const uint32_t a_tmem = tmem_base + lane_addr + Cfg::kACol0 + s * 32;
-      tmem_st16(a_tmem, r);
-      tmem_st16(a_tmem + 16, r + 16);
+      const uint32_t a_tmem = tmem_base + lane_addr + Cfg::kACol0 + s * Cfg::kASlotCols;
+#pragma unroll
+      for (int sub = 0; sub < kSubPerStage; ++sub) {
+        if (sub < nsub) {
+          uint32_t r[32];
+          dequant_word(w[2 * sub].x, gc[2 * sub], r + 0);
+          dequant_word(w[2 * sub].y, gc[2 * sub], r + 4);
+          dequant_word(w[2 * sub].z, gc[2 * sub], r + 8);
+          dequant_word(w[2 * sub].w, gc[2 * sub], r + 12);
+          dequant_word(w[2 * sub + 1].x, gc[2 * sub + 1], r + 16);
+          dequant_word(w[2 * sub + 1].y, gc[2 * sub + 1], r + 20);
+          dequant_word(w[2 * sub + 1].z, gc[2 * sub + 1], r + 24);
+          dequant_word(w[2 * sub + 1].w, gc[2 * sub + 1], r + 28);
+          tmem_st16(a_tmem + sub * 32, r);
+          tmem_st16(a_tmem + sub * 32 + 16, r + 16);
+        }
+      }
+      if (lane == 0 && quad == 2) QB_TRACE(2, it, 1);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tfull + 8 * s);
-      if (lane == 0 && quad == 2) QB_TRACE(2, it, 3);
+      if (lane == 0 && quad == 2) QB_TRACE(2, it, 2);
       s += 2;
       if (s >= D) { s -= D; ph ^= 1; }
     }
@@ -486,28 +570,43 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
   const float bias_v = (args.bias != nullptr && is_dq) ? __half2float(args.bias[n0 + ch]) : 0.f;
 
   if (is_dq) {
-    mbar_wait(bar_accum, 0);   // every TMA write landed and every MMA read of this CTA's smem is complete
+    mbar_wait(bar_accum, 0, 5, nst);   // every TMA write landed and every MMA read of this CTA's smem is complete
     tc_fence_after();
     if (threadIdx.x == 0) QB_TRACE(3, 0, 2);
   }
   if constexpr (SPLIT > 1) {
-    // exchange partial tiles through distributed shared memory: rank o receives columns [o*SLICE, (o+1)*SLICE)
+    // Exchange partial tiles through distributed shared memory: rank o owns token columns
+    // [o*SLICE, (o+1)*SLICE) and receives the other ranks' partials for them as packed fp16 rows
+    // (16-byte vector stores); its own partial stays in TMEM as fp32.
     cluster_arrive();
     cluster_wait();              // every CTA of the cluster is past its main loop (its X stages are dead)
     if (is_dq) {
 #pragma unroll 1
-      for (int o = 0; o < SPLIT; ++o) {
-        const uint32_t dst_cta = mapa_shared(smem_x, static_cast<uint32_t>(o));
+      for (int oo = 1; oo < SPLIT; ++oo) {
+        const int o = (rank + oo) % SPLIT;                          // staggered so ranks do not all hit one owner
+        const int src_slot = rank < o ? rank : rank - 1;            // my slot among the owner's SPLIT-1 sources
+        const uint32_t dst_row = mapa_shared(smem_x, static_cast<uint32_t>(o)) +
+                                 static_cast<uint32_t>(((src_slot * kChan + ch) * kRowHalves + wg * CH) * 2);
 #pragma unroll 1
         for (int p = 0; p < CH / PIECE; ++p) {
-          const int j0 = wg * CH + p * PIECE;                 // column inside the owner's slice
           uint32_t v[PIECE];
-          tmem_ld<PIECE>(d_tmem + o * SLICE + j0, v);
+          tmem_ld<PIECE>(d_tmem + o * SLICE + wg * CH + p * PIECE, v);
           tmem_wait_ld();
+          if constexpr (PIECE >= 8) {
 #pragma unroll
-          for (int i = 0; i < PIECE; ++i) {
-            const uint32_t off = static_cast<uint32_t>(((rank * SLICE + j0 + i) * kChan + ch) * 4);
-            st_cluster_f32(dst_cta + off, __uint_as_float(v[i]));
+            for (int i = 0; i < PIECE; i += 8)
+              st_cluster_v4(dst_row + (p * PIECE + i) * 2,
+                            pack_half2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
+                            pack_half2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])),
+                            pack_half2(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])),
+                            pack_half2(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
+          } else if constexpr (PIECE >= 2) {
+#pragma unroll
+            for (int i = 0; i < PIECE; i += 2)
+              st_cluster_u32(dst_row + (p * PIECE + i) * 2, pack_half2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+          } else {
+            asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(dst_row + p * 2),
+                         "h"(__half_as_ushort(__float2half_rn(__uint_as_float(v[0])))) : "memory");
           }
         }
       }
@@ -516,28 +615,44 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
     cluster_wait();              // all partial slices have landed in their owners' shared memory
   }
   if (is_dq) {
-    // this thread's CH columns of the owned slice -> fp16 -> staging tile [token][channel]
-    if constexpr (SPLIT == 1) {
+    // this thread's CH columns of the owned slice (+ the other ranks' partials) -> fp16 -> staging tile [token][channel]
 #pragma unroll 1
-      for (int p = 0; p < CH / PIECE; ++p) {
-        const int j0 = wg * CH + p * PIECE;
-        uint32_t v[PIECE];
-        tmem_ld<PIECE>(d_tmem + j0, v);
-        tmem_wait_ld();
+    for (int p = 0; p < CH / PIECE; ++p) {
+      const int j0 = wg * CH + p * PIECE;
+      uint32_t v[PIECE];
+      tmem_ld<PIECE>(d_tmem + rank * SLICE + j0, v);
+      tmem_wait_ld();
+      float acc[PIECE];
 #pragma unroll
-        for (int i = 0; i < PIECE; ++i)
-          sts_u16(smem_out + static_cast<uint32_t>(((j0 + i) * kChan + ch) * 2),
-                  __half_as_ushort(__float2half_rn(__uint_as_float(v[i]) + bias_v)));
-      }
-    } else {
-#pragma unroll 1
-      for (int i = 0; i < CH; ++i) {
-        const int j = wg * CH + i;
-        float acc = bias_v;
+      for (int i = 0; i < PIECE; ++i) acc[i] = __uint_as_float(v[i]) + bias_v;
+      if constexpr (SPLIT > 1) {
 #pragma unroll
-        for (int r = 0; r < SPLIT; ++r) acc += lds_f32(smem_x + static_cast<uint32_t>(((r * SLICE + j) * kChan + ch) * 4));
-        sts_u16(smem_out + static_cast<uint32_t>((j * kChan + ch) * 2), __half_as_ushort(__float2half_rn(acc)));
+        for (int r = 0; r < SPLIT - 1; ++r) {
+          const uint32_t row = smem_x + static_cast<uint32_t>(((r * kChan + ch) * kRowHalves + j0) * 2);
+          if constexpr (PIECE >= 8) {
+#pragma unroll
+            for (int i = 0; i < PIECE; i += 8) {
+              const uint4 q = lds128(row + i * 2);
+              const float2 a = unpack_half2(q.x), b = unpack_half2(q.y), c = unpack_half2(q.z), d = unpack_half2(q.w);
+              acc[i] += a.x; acc[i + 1] += a.y; acc[i + 2] += b.x; acc[i + 3] += b.y;
+              acc[i + 4] += c.x; acc[i + 5] += c.y; acc[i + 6] += d.x; acc[i + 7] += d.y;
+            }
+          } else if constexpr (PIECE >= 2) {
+#pragma unroll
+            for (int i = 0; i < PIECE; i += 2) {
+              const float2 a = unpack_half2(lds_u32(row + i * 2));
+              acc[i] += a.x; acc[i + 1] += a.y;
+            }
+          } else {
+            unsigned short hv;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(row) : "memory");
+            acc[0] += __half2float(__ushort_as_half(hv));
+          }
+        }
       }
+#pragma unroll
+      for (int i = 0; i < PIECE; ++i)
+        sts_u16(smem_out + static_cast<uint32_t>(((j0 + i) * kChan + ch) * 2), __half_as_ushort(__float2half_rn(acc[i])));
     }
     named_bar_sync(1, kNumDequantWarps * 32);
     // coalesced 16-byte stores: 16 threads cover one 256-byte token row of the tile
