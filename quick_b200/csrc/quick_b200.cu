@@ -253,13 +253,13 @@ int launch_umma(const CUtensorMap& map, const qb200::GemmArgs& args, int m_tiles
   auto kfn = qb200::w4a16_umma_kernel<TOK, SPLIT, KT>;
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
-    QB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    QB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes(SPLIT)));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(args.N / qb200::kChan, m_tiles, SPLIT);
   cfg.blockDim = dim3(qb200::kNumThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.dynamicSmemBytes = Cfg::smem_bytes(SPLIT);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;

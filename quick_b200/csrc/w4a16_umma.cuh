@@ -297,9 +297,16 @@ struct TileCfg {
   static constexpr int kTmemCols = kColsNeeded <= 32 ? 32 : kColsNeeded <= 64 ? 64 : kColsNeeded <= 128 ? 128
                                    : kColsNeeded <= 256 ? 256 : 512;
   static_assert(kColsNeeded <= 512, "TMEM budget");
-  static constexpr int kBarBytes = (3 * D + 1) * 8 + 16;
-  static constexpr int kSmemBytes = D * kStageBytes + kBarBytes + 1024;   // + manual 1024-B alignment slack
+  static constexpr int kBarBytes = (3 * D + 2) * 8 + 16;
+  static constexpr int kPipeBytes = D * kStageBytes;
   static constexpr int kMinBlocks = (TOK <= 64) ? 2 : 1;
+  // split-K receive buffer: (SPLIT-1) fp16 partial slices of 128 x (TOK/SPLIT); dedicated (not aliasing the
+  // pipeline stages) for TOK <= 128 so that senders need no "owner finished its main loop" barrier
+  static constexpr bool kDedicatedRecv = TOK <= 128;
+  __host__ __device__ static constexpr int recv_bytes(int split) { return split > 1 ? (split - 1) * kChan * (TOK / split) * 2 : 0; }
+  __host__ __device__ static constexpr int smem_bytes(int split) {
+    return kPipeBytes + kBarBytes + (kDedicatedRecv ? recv_bytes(split) + 16 : 0) + 1024;   // + 1024-B alignment slack
+  }
 };
 
 struct GemmArgs {
@@ -338,6 +345,36 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t a, uint32_
 __device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t a) {
   asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
 }
+// shared::cta -> (remote) shared::cluster bulk copy by the TMA engine, completing on the destination CTA's mbarrier
+__device__ __forceinline__ void bulk_s2dsmem(uint32_t remote_dst, uint32_t local_src, uint32_t bytes, uint32_t remote_bar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(remote_dst),
+               "r"(local_src), "r"(bytes), "r"(remote_bar)
+               : "memory");
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t a) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  bool timed = false;
+  while (true) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (!timed) { t0 = clock64(); timed = true; }
+    else if (clock64() - t0 > QB200_WAIT_TIMEOUT_CYCLES) { __trap(); }
+  }
+}
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -362,13 +399,22 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
   constexpr int CH = SLICE / 2;               // columns per (owner, warpgroup)
   static_assert(CH >= 1, "TOK / SPLIT must be >= 2");
   constexpr int PIECE = CH < 16 ? CH : 16;    // columns per tcgen05.ld
-  // Epilogue staging aliases pipeline buffers that are dead once the accumulator is complete.
-  //   recv : partial slices from the other SPLIT-1 ranks, fp16, [src][channel][SLICE (+8 pad) halves]
-  //   out  : this CTA's [SLICE tokens][128 channels] fp16 tile, stored with 16-byte coalesced writes
-  constexpr int kRowHalves = SLICE + 8;                                   // +16 B: conflict-free 16-B row stores
-  constexpr int kRecvBytes = SPLIT > 1 ? (SPLIT - 1) * kChan * kRowHalves * 2 : 0;
+  constexpr int UNIT = CH < 8 ? CH : 8;       // columns per exchanged vector (UNIT halves = 2*UNIT bytes per lane)
+  // Epilogue staging.
+  //   recv : partial slices from the other SPLIT-1 ranks as packed fp16, laid out [src][unit][channel][UNIT]
+  //          so that the 32 lanes of a warp (consecutive channels) write one contiguous run — DSMEM, like
+  //          global memory, wants coalesced warps.  Dedicated region for TOK <= 128, else aliases the
+  //          (dead) pipeline stages behind a cluster barrier.
+  //   out  : this CTA's [SLICE tokens][128 channels] fp16 tile (aliases the dead pipeline stages), stored
+  //          with 16-byte coalesced writes.
+  constexpr int kRecvBytes = Cfg::recv_bytes(SPLIT);
   constexpr int kOutBytes = SLICE * kChan * 2;
-  static_assert(kRecvBytes % 16 == 0 && kRecvBytes + kOutBytes <= D * Cfg::kStageBytes,
+  static_assert(kRecvBytes % 16 == 0, "recv alignment");
+  //   stage: the partial slices this CTA sends, same layout, in LOCAL shared memory (aliases the dead pipeline
+  //          stages); one TMA bulk copy per owner moves a slice into the owner's recv slot and completes on the
+  //          owner's mbarrier (cp.async.bulk.shared::cluster.shared::cta) — far faster than per-thread
+  //          st.shared::cluster, and no release/acquire round trip per owner.
+  static_assert((Cfg::kDedicatedRecv ? 0 : kRecvBytes) + kRecvBytes + kOutBytes <= Cfg::kPipeBytes,
                 "epilogue staging must fit the (dead) pipeline stages: X stages then W stages are contiguous");
 
   extern __shared__ uint8_t smem_raw[];
@@ -379,8 +425,11 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
   const uint32_t bar_tfull = bar_full + 8 * D;                         // A operand written to TMEM slot
   const uint32_t bar_cons = bar_tfull + 8 * D;                         // slot consumed: 4 dequant warps + MMA commit
   const uint32_t bar_accum = bar_cons + 8 * D;                         // all MMAs of the tile done
-  const uint32_t tmem_ptr_smem = bar_accum + 8;
-  const uint32_t smem_out = smem_x + kRecvBytes;
+  const uint32_t bar_recv = bar_accum + 8;                             // split-K partials from the other ranks landed
+  const uint32_t tmem_ptr_smem = bar_recv + 8;
+  const uint32_t smem_recv = Cfg::kDedicatedRecv ? ((tmem_ptr_smem + 16 + 15) & ~15u) : smem_x;
+  const uint32_t smem_stage = Cfg::kDedicatedRecv ? smem_x : smem_x + kRecvBytes;
+  const uint32_t smem_out = smem_stage + kRecvBytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -400,6 +449,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
       mbar_init(bar_cons + 8 * i, 5);
     }
     mbar_init(bar_accum, 1);
+    if constexpr (SPLIT > 1) mbar_init(bar_recv, 1);   // one expect_tx arrive; the senders' bulk copies complete the bytes
     fence_barrier_init();
     fence_proxy_async();
     prefetch_tmap(&tmap_x);
@@ -411,6 +461,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem) : "memory");
   if (threadIdx.x == 0) QB_TRACE(3, 0, 1);
+  if constexpr (SPLIT > 1) cluster_arrive();   // matched by a wait just before the first remote access
 
   if (warp == kProducerWarp) {
     // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
@@ -576,43 +627,65 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
   }
   if constexpr (SPLIT > 1) {
     // Exchange partial tiles through distributed shared memory: rank o owns token columns
-    // [o*SLICE, (o+1)*SLICE) and receives the other ranks' partials for them as packed fp16 rows
-    // (16-byte vector stores); its own partial stays in TMEM as fp32.
-    cluster_arrive();
-    cluster_wait();              // every CTA of the cluster is past its main loop (its X stages are dead)
+    // [o*SLICE, (o+1)*SLICE) and receives the other ranks' partials for them as packed fp16; its own partial
+    // stays in TMEM as fp32.  Point-to-point: each sending warp arrives (release.cluster) on the owner's
+    // bar_recv after its stores; no cluster-wide barrier on the critical path for TOK <= 128.
+    cluster_wait();              // every CTA of the cluster has initialised its barriers
+    if constexpr (!Cfg::kDedicatedRecv) {
+      cluster_arrive();
+      cluster_wait();            // every CTA is past its main loop: the aliased pipeline stages are dead
+    }
+    if (threadIdx.x == 0) QB_TRACE(3, 2, 0);
+    constexpr uint32_t kSliceBytes = kChan * SLICE * 2;
+    if (threadIdx.x == 0) mbar_arrive_expect_tx(bar_recv, (SPLIT - 1) * kSliceBytes);
     if (is_dq) {
 #pragma unroll 1
       for (int oo = 1; oo < SPLIT; ++oo) {
-        const int o = (rank + oo) % SPLIT;                          // staggered so ranks do not all hit one owner
-        const int src_slot = rank < o ? rank : rank - 1;            // my slot among the owner's SPLIT-1 sources
-        const uint32_t dst_row = mapa_shared(smem_x, static_cast<uint32_t>(o)) +
-                                 static_cast<uint32_t>(((src_slot * kChan + ch) * kRowHalves + wg * CH) * 2);
+        const int o = (rank + oo) % SPLIT;
+        const uint32_t dst = smem_stage + static_cast<uint32_t>((oo - 1) * kSliceBytes);
 #pragma unroll 1
         for (int p = 0; p < CH / PIECE; ++p) {
           uint32_t v[PIECE];
           tmem_ld<PIECE>(d_tmem + o * SLICE + wg * CH + p * PIECE, v);
           tmem_wait_ld();
-          if constexpr (PIECE >= 8) {
 #pragma unroll
-            for (int i = 0; i < PIECE; i += 8)
-              st_cluster_v4(dst_row + (p * PIECE + i) * 2,
-                            pack_half2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
-                            pack_half2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])),
-                            pack_half2(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])),
-                            pack_half2(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
-          } else if constexpr (PIECE >= 2) {
-#pragma unroll
-            for (int i = 0; i < PIECE; i += 2)
-              st_cluster_u32(dst_row + (p * PIECE + i) * 2, pack_half2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-          } else {
-            asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(dst_row + p * 2),
-                         "h"(__half_as_ushort(__float2half_rn(__uint_as_float(v[0])))) : "memory");
+          for (int i = 0; i < PIECE; i += UNIT) {
+            const int unit = (wg * CH + p * PIECE + i) / UNIT;       // unit index inside the slice
+            const uint32_t addr = dst + static_cast<uint32_t>((unit * kChan + ch) * (UNIT * 2));
+            if constexpr (UNIT == 8) {
+              sts_v4(addr, pack_half2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
+                     pack_half2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])),
+                     pack_half2(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])),
+                     pack_half2(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
+            } else if constexpr (UNIT == 4) {
+              sts_u32(addr, pack_half2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+              sts_u32(addr + 4, pack_half2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+            } else if constexpr (UNIT == 2) {
+              sts_u32(addr, pack_half2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+            } else {
+              sts_u16(addr, __half_as_ushort(__float2half_rn(__uint_as_float(v[i]))));
+            }
           }
         }
       }
+      fence_proxy_async();                                  // generic-proxy smem writes -> visible to the TMA engine
+      named_bar_sync(1, kNumDequantWarps * 32);
+      if (threadIdx.x < SPLIT - 1) {                        // one thread per owner issues that owner's slice
+        const int oo = threadIdx.x + 1;
+        const int o = (rank + oo) % SPLIT;
+        const int src_slot = rank < o ? rank : rank - 1;    // my slot among the owner's SPLIT-1 sources
+        bulk_s2dsmem(mapa_shared(smem_recv + static_cast<uint32_t>(src_slot * kSliceBytes), static_cast<uint32_t>(o)),
+                     smem_stage + static_cast<uint32_t>((oo - 1) * kSliceBytes), kSliceBytes,
+                     mapa_shared(bar_recv, static_cast<uint32_t>(o)));
+      }
+      if (threadIdx.x == 0) QB_TRACE(3, 2, 1);
+      mbar_wait_cluster(bar_recv, 0);   // all partial slices for my columns have landed
+      if (threadIdx.x == 0) QB_TRACE(3, 2, 2);
     }
+    // Every bulk copy is some CTA's inbound slice: once every CTA of the cluster has seen its bar_recv
+    // complete, no TMA engine is still reading anybody's staging buffer.  Arrive now, wait just before exit,
+    // so no CTA frees its shared memory under an in-flight copy.
     cluster_arrive();
-    cluster_wait();              // all partial slices have landed in their owners' shared memory
   }
   if (is_dq) {
     // this thread's CH columns of the owned slice (+ the other ranks' partials) -> fp16 -> staging tile [token][channel]
@@ -628,25 +701,26 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
       if constexpr (SPLIT > 1) {
 #pragma unroll
         for (int r = 0; r < SPLIT - 1; ++r) {
-          const uint32_t row = smem_x + static_cast<uint32_t>(((r * kChan + ch) * kRowHalves + j0) * 2);
-          if constexpr (PIECE >= 8) {
 #pragma unroll
-            for (int i = 0; i < PIECE; i += 8) {
-              const uint4 q = lds128(row + i * 2);
+          for (int i = 0; i < PIECE; i += UNIT) {
+            const int unit = (j0 + i) / UNIT;
+            const uint32_t addr = smem_recv + static_cast<uint32_t>(r * (kChan * SLICE * 2) + (unit * kChan + ch) * (UNIT * 2));
+            if constexpr (UNIT == 8) {
+              const uint4 q = lds128(addr);
               const float2 a = unpack_half2(q.x), b = unpack_half2(q.y), c = unpack_half2(q.z), d = unpack_half2(q.w);
               acc[i] += a.x; acc[i + 1] += a.y; acc[i + 2] += b.x; acc[i + 3] += b.y;
               acc[i + 4] += c.x; acc[i + 5] += c.y; acc[i + 6] += d.x; acc[i + 7] += d.y;
-            }
-          } else if constexpr (PIECE >= 2) {
-#pragma unroll
-            for (int i = 0; i < PIECE; i += 2) {
-              const float2 a = unpack_half2(lds_u32(row + i * 2));
+            } else if constexpr (UNIT == 4) {
+              const float2 a = unpack_half2(lds_u32(addr)), b = unpack_half2(lds_u32(addr + 4));
+              acc[i] += a.x; acc[i + 1] += a.y; acc[i + 2] += b.x; acc[i + 3] += b.y;
+            } else if constexpr (UNIT == 2) {
+              const float2 a = unpack_half2(lds_u32(addr));
               acc[i] += a.x; acc[i + 1] += a.y;
+            } else {
+              unsigned short hv;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(addr) : "memory");
+              acc[i] += __half2float(__ushort_as_half(hv));
             }
-          } else {
-            unsigned short hv;
-            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(row) : "memory");
-            acc[0] += __half2float(__ushort_as_half(hv));
           }
         }
       }
@@ -654,6 +728,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
       for (int i = 0; i < PIECE; ++i)
         sts_u16(smem_out + static_cast<uint32_t>(((j0 + i) * kChan + ch) * 2), __half_as_ushort(__float2half_rn(acc[i])));
     }
+    if (threadIdx.x == 0) QB_TRACE(3, 2, 3);
     named_bar_sync(1, kNumDequantWarps * 32);
     // coalesced 16-byte stores: 16 threads cover one 256-byte token row of the tile
     const int tid = threadIdx.x;             // 0..255
@@ -670,6 +745,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
     if (threadIdx.x == 0) QB_TRACE(3, 0, 3);
   }
 
+  if constexpr (SPLIT > 1) cluster_wait();
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, Cfg::kTmemCols);

@@ -18,10 +18,10 @@ lib.qb200_debug_set_trace(None)
 t = tr.cpu().view(4, 256, 4)
 t0 = int(t[3, 0, 0])
 rel = lambda v: int(v) - t0 if int(v) else None
-nkb = K // 64 // split
+nkb = (K // 64 // split + 1) // 2
 print("cfg", tok, split, M, K, N, "stages", nkb)
-print("setup_done", rel(t[3, 0, 1]), "accum_seen", rel(t[3, 0, 2]), "epi_done", rel(t[3, 0, 3]), "dealloc", rel(t[3, 1, 0]))
-print("it | prod: slot_free issued | mma: tfull mmas_issued committed | deq: full deq_done slot_free handed_off")
+print("setup_done", rel(t[3, 0, 1]), "accum_seen", rel(t[3, 0, 2]), "cluster_bar1", rel(t[3, 2, 0]), "scatter_done", rel(t[3, 2, 1]), "cluster_bar2", rel(t[3, 2, 2]), "tile_staged", rel(t[3, 2, 3]), "epi_done", rel(t[3, 0, 3]), "dealloc", rel(t[3, 1, 0]))
+print("it | prod: slot_free issued | mma: tfull mmas_issued committed | deq: full st_issued handed_off")
 for it in range(min(nkb, 40)):
     print(it, "|", rel(t[0, it, 0]), rel(t[0, it, 1]), "|", rel(t[1, it, 0]), rel(t[1, it, 1]), rel(t[1, it, 2]), "|",
-          rel(t[2, it, 0]), rel(t[2, it, 1]), rel(t[2, it, 2]), rel(t[2, it, 3]))
+          rel(t[2, it, 0]), rel(t[2, it, 1]), rel(t[2, it, 2]))
