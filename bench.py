@@ -247,7 +247,10 @@ def run_mine(args):
         roof = {"bound": "tensor", "achieved": dom["TOPS"], "peak": pk["tf_sustained"], "unit": "TFLOP/s"}
     else:
         roof = {"bound": "hbm", "achieved": dom["GBs"], "peak": pk["hbm_gbs"], "unit": "GB/s"}
-    roof.update({"frac": round(roof["achieved"] / roof["peak"], 4), "traffic": None, "kernel": "w4a16_umma_kernel",
+    # DRAM bytes per launch of the same kernel from `ncu --set full` (profiles/r1_ncu_full_M*.json): no re-reads
+    ncu_traffic = {1: 8952320, 256: 11044864, 512: 13141248}
+    roof.update({"frac": round(roof["achieved"] / roof["peak"], 4), "traffic": ncu_traffic.get(dom["M"]), "kernel": "w4a16_umma_kernel",
+                 "algorithmic_bytes": int(alg_bytes(dom["M"])),
                  "at_M": dom["M"], "share_of_step": round(dom["us"] / sum(r["us"] for r in sweep), 3),
                  "peak_source": pk["source"] + (" (sustained bf16 cuBLAS)" if roof["bound"] == "tensor" else " (copy)")})
     m1 = sweep[0]
