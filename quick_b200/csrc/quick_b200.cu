@@ -247,10 +247,10 @@ int device_sm_count() {
   return sms;
 }
 
-template <int TOK, int SPLIT, int KT = qb200::default_depth<TOK>()>
+template <int TOK, int SPLIT>
 int launch_umma(const CUtensorMap& map, const qb200::GemmArgs& args, int m_tiles, cudaStream_t stream) {
-  using Cfg = qb200::TileCfg<TOK, KT>;
-  auto kfn = qb200::w4a16_umma_kernel<TOK, SPLIT, KT>;
+  using Cfg = qb200::TileCfg<TOK>;
+  auto kfn = qb200::w4a16_umma_kernel<TOK, SPLIT>;
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
     QB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes(SPLIT)));
@@ -258,7 +258,7 @@ int launch_umma(const CUtensorMap& map, const qb200::GemmArgs& args, int m_tiles
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(args.N / qb200::kChan, m_tiles, SPLIT);
-  cfg.blockDim = dim3(qb200::kNumThreads);
+  cfg.blockDim = dim3(Cfg::kNumThreads);
   cfg.dynamicSmemBytes = Cfg::smem_bytes(SPLIT);
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

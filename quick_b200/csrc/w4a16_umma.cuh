@@ -28,13 +28,13 @@ namespace qb200 {
 constexpr int kChan = 128;          // channels per tile = UMMA M
 constexpr int kBK = 64;             // k per pipeline stage
 constexpr int kWStageBytes = kChan * kBK / 2;   // 4096
-constexpr int kNumThreads = 320;    // 10 warps
-constexpr int kNumDequantWarps = 8;
+constexpr int kEpilogueWarps = 8;    // warps 0..7 run the epilogue
 // Warp roles.  The single-thread issuers get the HIGHEST warp ids: the SM's warp arbiter favours
 // higher warp ids, and a starved TMA/MMA issuer stalls the whole pipeline (measured: with the
 // issuers on warps 0/1 every already-complete mbarrier wait cost ~300 cycles).
-constexpr int kProducerWarp = 8;
-constexpr int kMmaWarp = 9;
+// NWG dequant warpgroups (4 warps each, warp % 4 = TMEM lane quadrant) take pipeline stages round-robin.
+template <int TOK>
+constexpr int default_nwg() { return TOK <= 64 ? 4 : 2; }
 
 // ------------------------------------------------------------------------------------------------
 // PTX helpers
@@ -283,11 +283,18 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
 constexpr int kSubPerStage = 2;                          // k64 blocks per stage
 constexpr int kWStageBytesV3 = kSubPerStage * kWStageBytes;   // 8192
 template <int TOK>
-constexpr int default_depth() { return TOK <= 64 ? 3 : TOK == 128 ? 4 : 3; }
+constexpr int default_depth() { return TOK <= 128 ? 4 : 3; }
 
-template <int TOK, int D = default_depth<TOK>()>
+template <int TOK, int D = default_depth<TOK>(), int NWG = default_nwg<TOK>()>
 struct TileCfg {
   static constexpr int kDepth = D;
+  static constexpr int kNumWG = NWG;
+  static constexpr int kProducerWarp = 4 * NWG;
+  static constexpr int kMmaWarp = 4 * NWG + 1;
+  static constexpr int kNumThreads = (4 * NWG + 2) * 32;
+  // when D is a multiple of NWG a slot is always consumed by the same warpgroup, so its warps see every
+  // phase of "their" full barriers in order; otherwise each warp must also observe the skipped stages
+  static constexpr bool kInOrderWaits = (D % NWG) != 0;
   static constexpr int kXPanelBytes = TOK * 128;                      // one k64 panel
   static constexpr int kXStageBytes = kSubPerStage * kXPanelBytes;
   static constexpr int kStageBytes = kXStageBytes + kWStageBytesV3;
@@ -299,7 +306,6 @@ struct TileCfg {
   static_assert(kColsNeeded <= 512, "TMEM budget");
   static constexpr int kBarBytes = (3 * D + 2) * 8 + 16;
   static constexpr int kPipeBytes = D * kStageBytes;
-  static constexpr int kMinBlocks = (TOK <= 64) ? 2 : 1;
   // split-K receive buffer: (SPLIT-1) fp16 partial slices of 128 x (TOK/SPLIT); dedicated (not aliasing the
   // pipeline stages) for TOK <= 128 so that senders need no "owner finished its main loop" barrier
   static constexpr bool kDedicatedRecv = TOK <= 128;
@@ -391,10 +397,12 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 // ------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------
-template <int TOK, int SPLIT, int D = default_depth<TOK>()>
-__global__ void __launch_bounds__(kNumThreads, TileCfg<TOK, D>::kMinBlocks)
+template <int TOK, int SPLIT, int D = default_depth<TOK>(), int NWG = default_nwg<TOK>()>
+__global__ void __launch_bounds__(TileCfg<TOK, D, NWG>::kNumThreads, 1)
 w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs args) {
-  using Cfg = TileCfg<TOK, D>;
+  using Cfg = TileCfg<TOK, D, NWG>;
+  constexpr int kProducerWarp = Cfg::kProducerWarp;
+  constexpr int kMmaWarp = Cfg::kMmaWarp;
   constexpr int SLICE = TOK / SPLIT;          // token columns owned by one cluster rank
   constexpr int CH = SLICE / 2;               // columns per (owner, warpgroup)
   static_assert(CH >= 1, "TOK / SPLIT must be >= 2");
@@ -469,7 +477,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
     int s = 0;
     uint32_t ph = 0;
     for (int it = 0; it < nst; ++it) {
-      mbar_wait(bar_cons + 8 * s, ph ^ 1, 1, it);
+      if (it >= D) mbar_wait(bar_cons + 8 * s, ph ^ 1, 1, it);   // the first D slots are free by construction
       if (elect_one()) {
         QB_TRACE(0, it, 0);
         const int nsub = min(kSubPerStage, nkb - it * kSubPerStage);
@@ -527,7 +535,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
     }
   } else {
     // ===================== dequant warps: smem nibbles -> registers -> TMEM A operand =====================
-    const int wg = warp >> 2;                       // warpgroup 0/1 takes even/odd stages
+    const int wg = warp >> 2;                       // warpgroup w takes stages w, w + NWG, ...
     const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
     const int ch = quad * 32 + lane;                // output channel within the tile = TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
@@ -549,16 +557,19 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
     if (wg < nst) load_sz();
     int s = wg % D;
     uint32_t ph = 0;
-    for (int it = wg; it < nst; it += 2) {
+    for (int it = wg; it < nst; it += NWG) {
       const int nsub = min(kSubPerStage, nkb - it * kSubPerStage);
       // mbarrier parity waits are only valid one phase ahead.  The other warpgroup consumes stage it-1, and
       // TMA completions arrive out of order, so this warp must first observe stage it-1's barrier itself:
       // otherwise, with slot reuse distance D odd, it could test slot s for stage `it` while the slot is
       // still in the phase of stage it-D and the parity test would alias and pass (seen as rare hangs).
-      if (it > 0) {
-        const int sp = s == 0 ? D - 1 : s - 1;
-        const uint32_t php = s == 0 ? ph ^ 1 : ph;
-        mbar_wait(bar_full + 8 * sp, php, 7, it - 1);
+      if constexpr (Cfg::kInOrderWaits) {
+        static_assert(!Cfg::kInOrderWaits || NWG == 2, "in-order observation is implemented for two warpgroups");
+        if (it > 0) {
+          const int sp = s == 0 ? D - 1 : s - 1;
+          const uint32_t php = s == 0 ? ph ^ 1 : ph;
+          mbar_wait(bar_full + 8 * sp, php, 7, it - 1);
+        }
       }
       mbar_wait(bar_full + 8 * s, ph, 3, it);
       if (lane == 0 && quad == 2) QB_TRACE(2, it, 0);
@@ -575,10 +586,10 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
       GroupConsts gc[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) gc[q] = make_group_consts(szw[q]);
-      // advance two stages (8 k32 blocks) and prefetch the next scale/zero words
-      rem += 4 * kSubPerStage;
+      // advance NWG stages (4 k32 blocks each) and prefetch the next scale/zero words
+      rem += 2 * kSubPerStage * NWG;
       while (rem >= g32) { rem -= g32; ++grp; }
-      if (it + 2 < nst) load_sz();
+      if (it + NWG < nst) load_sz();
       // TMEM slot s is free once the MMAs of stage it - D have completed (the previous phase of bar_cons);
       // the producer already observed that phase before refilling the slot, this wait is the acquire.
       mbar_wait(bar_cons + 8 * s, ph ^ 1, 4, it);
@@ -606,8 +617,8 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tfull + 8 * s);
       if (lane == 0 && quad == 2) QB_TRACE(2, it, 2);
-      s += 2;
-      if (s >= D) { s -= D; ph ^= 1; }
+      s += NWG;
+      while (s >= D) { s -= D; ph ^= 1; }
     }
   }
 
@@ -615,7 +626,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
   const int quad = warp & 3;
   const int wg = warp >> 2;
   const int ch = quad * 32 + lane;
-  const bool is_dq = warp < kNumDequantWarps;
+  const bool is_dq = warp < kEpilogueWarps;   // the first two warpgroups run the epilogue
   const uint32_t d_tmem = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
   const int n0 = nt * kChan;
   const float bias_v = (args.bias != nullptr && is_dq) ? __half2float(args.bias[n0 + ch]) : 0.f;
@@ -669,7 +680,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
         }
       }
       fence_proxy_async();                                  // generic-proxy smem writes -> visible to the TMA engine
-      named_bar_sync(1, kNumDequantWarps * 32);
+      named_bar_sync(1, kEpilogueWarps * 32);
       if (threadIdx.x < SPLIT - 1) {                        // one thread per owner issues that owner's slice
         const int oo = threadIdx.x + 1;
         const int o = (rank + oo) % SPLIT;
@@ -729,13 +740,13 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
         sts_u16(smem_out + static_cast<uint32_t>(((j0 + i) * kChan + ch) * 2), __half_as_ushort(__float2half_rn(acc[i])));
     }
     if (threadIdx.x == 0) QB_TRACE(3, 2, 3);
-    named_bar_sync(1, kNumDequantWarps * 32);
+    named_bar_sync(1, kEpilogueWarps * 32);
     // coalesced 16-byte stores: 16 threads cover one 256-byte token row of the tile
     const int tid = threadIdx.x;             // 0..255
     const int chunk = tid & 15;
     const int m_base = mt * TOK + rank * SLICE;
 #pragma unroll 1
-    for (int row = tid >> 4; row < SLICE; row += (kNumDequantWarps * 32) / 16) {
+    for (int row = tid >> 4; row < SLICE; row += (kEpilogueWarps * 32) / 16) {
       const int m = m_base + row;
       if (m < args.M) {
         const uint4 v = lds128(smem_out + static_cast<uint32_t>(row * kChan * 2 + chunk * 16));
