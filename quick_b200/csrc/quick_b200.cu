@@ -247,6 +247,12 @@ int device_sm_count() {
   return sms;
 }
 
+bool use_pdl() {   // QB200_NO_PDL=1 disables programmatic dependent launch (A/B measurements)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("QB200_NO_PDL"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+
 template <int TOK, int SPLIT>
 int launch_umma(const CUtensorMap& map, const qb200::GemmArgs& args, int m_tiles, cudaStream_t stream) {
   using Cfg = qb200::TileCfg<TOK>;
@@ -261,13 +267,15 @@ int launch_umma(const CUtensorMap& map, const qb200::GemmArgs& args, int m_tiles
   cfg.blockDim = dim3(Cfg::kNumThreads);
   cfg.dynamicSmemBytes = Cfg::smem_bytes(SPLIT);
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = SPLIT;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap our prologue with the previous kernel's tail
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = use_pdl() ? 2 : 1;
   QB_CUDA(cudaLaunchKernelEx(&cfg, kfn, map, args));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return QB200_OK;

@@ -334,6 +334,12 @@ struct GemmArgs {
 #define QB_TRACE(slot, it, k) do { } while (0)
 #endif
 
+// Programmatic dependent launch (PDL): let the next kernel in the stream start its prologue (barrier init,
+// TMEM allocation, weight TMA) while this one is still running, and wait for the previous kernel only where
+// its results (the activations) are first consumed.  No-ops when launched without the PDL attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
@@ -449,6 +455,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
   const int nkb = min(args.kb_per_split, KB - kb0);            // k64 blocks of this CTA
   const int nst = (nkb + kSubPerStage - 1) / kSubPerStage;     // pipeline stages (last may hold one block)
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) QB_TRACE(3, 0, 0);
   if (threadIdx.x == 0) {
     for (int i = 0; i < D; ++i) {
@@ -484,6 +491,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
         const uint32_t bar = bar_full + 8 * s;
         mbar_arrive_expect_tx(bar, nsub * (kWStageBytes + Cfg::kXPanelBytes));
         bulk_g2s(smem_w + s * kWStageBytesV3, wsrc + static_cast<size_t>(it) * (kWStageBytesV3 / 4), nsub * kWStageBytes, bar);
+        if (it == 0) pdl_wait_prior_grid();   // weights are constants; the activations come from the previous kernel
         tma_load_2d(smem_x + s * Cfg::kXStageBytes, &tmap_x, bar, (kb0 + it * kSubPerStage) * kBK, mt * TOK);
         if (nsub > 1)
           tma_load_2d(smem_x + s * Cfg::kXStageBytes + Cfg::kXPanelBytes, &tmap_x, bar, (kb0 + it * kSubPerStage + 1) * kBK, mt * TOK);
@@ -741,6 +749,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
     }
     if (threadIdx.x == 0) QB_TRACE(3, 2, 3);
     named_bar_sync(1, kEpilogueWarps * 32);
+    pdl_wait_prior_grid();   // C may alias a buffer the previous kernel still reads/writes
     // coalesced 16-byte stores: 16 threads cover one 256-byte token row of the tile
     const int tid = threadIdx.x;             // 0..255
     const int chunk = tid & 15;
