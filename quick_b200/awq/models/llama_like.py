@@ -1,0 +1,201 @@
+"""Minimal Llama-like decoder whose every decoder-layer linear is a WQLinear_QUICK — SURVEY §8(f1).
+
+Only what is needed to report tokens/s the way the reference's examples/benchmark.py does
+(prefill + token-by-token decode with a KV cache, benchmark.py:38-67): embedding, RMSNorm, fused QKV
+(q‖k‖v concatenated in the QUICK layout — the generalised QUICK_cat, so GQA works), RoPE, a static KV
+cache, torch SDPA attention, SwiGLU MLP with gate‖up fused into one GEMM, fp16 lm_head (the reference
+leaves lm_head unquantised, base.py:396-405).  Reference structure mirrored: modules/fused/model.py:63-109,
+block.py:39-74, attn.py:100-245, cache.py:3-58.  Weights are random-init (no checkpoints / network here).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..modules.linear.quick import WQLinear_QUICK
+
+
+@dataclass
+class LlamaLikeConfig:
+    hidden_size: int = 4096
+    intermediate_size: int = 11008
+    num_layers: int = 32
+    num_heads: int = 32
+    num_kv_heads: int = 32
+    vocab_size: int = 32000
+    max_seq_len: int = 256
+    group_size: int = 128
+    rms_eps: float = 1e-5
+    rope_theta: float = 10000.0
+
+    @property
+    def head_dim(self):
+        return self.hidden_size // self.num_heads
+
+
+PRESETS = {
+    "llama-2-7b": LlamaLikeConfig(4096, 11008, 32, 32, 32),
+    "mistral-7b": LlamaLikeConfig(4096, 14336, 32, 32, 8),
+    "llama-2-70b": LlamaLikeConfig(8192, 28672, 80, 64, 8),
+    "tiny": LlamaLikeConfig(512, 1024, 2, 8, 4, vocab_size=1024, max_seq_len=64),
+}
+
+
+def random_quick_linear(in_f: int, out_f: int, G: int, dev, gen: torch.Generator, linear_impl: str = "quick_b200"):
+    """Random-init packed weights straight in the QUICK layout (any nibble pattern is a valid weight; zeros and
+    scales are written with the duplication the format requires, quick.py:129-130,141-150)."""
+    m = WQLinear_QUICK(4, G, in_f, out_f, False, dev)
+    m.qweight = torch.randint(-2 ** 31, 2 ** 31 - 1, m.qweight.shape, dtype=torch.int32, device=dev, generator=gen)
+    z4 = torch.randint(0, 2 ** 16, m.qzeros.shape, dtype=torch.int32, device=dev, generator=gen)
+    m.qzeros = z4 | (z4 << 16)
+    s = (torch.rand((in_f // G, out_f), device=dev, generator=gen) * 0.004 + 0.001).half()
+    m.scales = s.repeat_interleave(2, dim=1).contiguous()
+    m.linear_impl = linear_impl
+    return m
+
+
+class RMSNorm(nn.Module):
+    def __init__(self, dim, eps, dev):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim, dtype=torch.float16, device=dev), requires_grad=False)
+        self.eps = eps
+
+    def forward(self, x):
+        v = x.float()
+        return (v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + self.eps)).half() * self.weight
+
+
+def _linear(m: WQLinear_QUICK, x, ref_mod=None):
+    """Route through the B200 kernel, or (baseline runs only) through the unmodified reference kernel."""
+    if ref_mod is None:
+        return m(x)
+    split = m.k_split_1 if m.out_features > m.in_features else m.k_split_2      # quick.py:161-164
+    out = ref_mod.gemm_forward_cuda_quick(x.reshape(-1, x.shape[-1]), m.qweight, m.scales, m.qzeros, split)
+    return out.reshape(x.shape[:-1] + (m.out_features,))
+
+
+class Block(nn.Module):
+    def __init__(self, cfg: LlamaLikeConfig, dev, gen, batch: int):
+        super().__init__()
+        self.cfg = cfg
+        hd, nh, nkv = cfg.head_dim, cfg.num_heads, cfg.num_kv_heads
+        self.norm_1 = RMSNorm(cfg.hidden_size, cfg.rms_eps, dev)
+        self.norm_2 = RMSNorm(cfg.hidden_size, cfg.rms_eps, dev)
+        self.qkv_proj = random_quick_linear(cfg.hidden_size, (nh + 2 * nkv) * hd, cfg.group_size, dev, gen)
+        self.o_proj = random_quick_linear(cfg.hidden_size, cfg.hidden_size, cfg.group_size, dev, gen)
+        self.gate_up_proj = random_quick_linear(cfg.hidden_size, 2 * cfg.intermediate_size, cfg.group_size, dev, gen)
+        self.down_proj = random_quick_linear(cfg.intermediate_size, cfg.hidden_size, cfg.group_size, dev, gen)
+        self.register_buffer("cache_k", torch.zeros(batch, nkv, cfg.max_seq_len, hd, dtype=torch.float16, device=dev), persistent=False)
+        self.register_buffer("cache_v", torch.zeros(batch, nkv, cfg.max_seq_len, hd, dtype=torch.float16, device=dev), persistent=False)
+
+    def forward(self, x, cos, sin, pos_idx, attn_mask, ref_mod=None):
+        cfg = self.cfg
+        B, T, _ = x.shape
+        hd, nh, nkv = cfg.head_dim, cfg.num_heads, cfg.num_kv_heads
+        qkv = _linear(self.qkv_proj, self.norm_1(x), ref_mod)
+        q, k, v = qkv.split([nh * hd, nkv * hd, nkv * hd], dim=-1)
+        q = q.view(B, T, nh, hd).transpose(1, 2)
+        k = k.view(B, T, nkv, hd).transpose(1, 2)
+        v = v.view(B, T, nkv, hd).transpose(1, 2)
+        q, k = _rope(q, cos, sin), _rope(k, cos, sin)
+        self.cache_k.index_copy_(2, pos_idx, k)
+        self.cache_v.index_copy_(2, pos_idx, v)
+        o = F.scaled_dot_product_attention(q, self.cache_k, self.cache_v, attn_mask=attn_mask, enable_gqa=(nkv != nh))
+        x = x + _linear(self.o_proj, o.transpose(1, 2).reshape(B, T, nh * hd), ref_mod)
+        gu = _linear(self.gate_up_proj, self.norm_2(x), ref_mod)
+        g, u = gu.split(cfg.intermediate_size, dim=-1)
+        return x + _linear(self.down_proj, F.silu(g) * u, ref_mod)
+
+
+def _rope(t, cos, sin):
+    t1, t2 = t[..., : t.shape[-1] // 2], t[..., t.shape[-1] // 2:]
+    return (t * cos + torch.cat((-t2, t1), dim=-1) * sin).to(t.dtype)
+
+
+class LlamaLikeQuickModel(nn.Module):
+    def __init__(self, cfg: LlamaLikeConfig, batch: int, dev="cuda", seed: int = 0):
+        super().__init__()
+        self.cfg, self.batch = cfg, batch
+        gen = torch.Generator(device=dev); gen.manual_seed(seed)
+        self.embed = nn.Embedding(cfg.vocab_size, cfg.hidden_size, device=dev, dtype=torch.float16)
+        self.blocks = nn.ModuleList([Block(cfg, dev, gen, batch) for _ in range(cfg.num_layers)])
+        self.norm = RMSNorm(cfg.hidden_size, cfg.rms_eps, dev)
+        self.lm_head = nn.Linear(cfg.hidden_size, cfg.vocab_size, bias=False, device=dev, dtype=torch.float16)
+        inv = 1.0 / (cfg.rope_theta ** (torch.arange(0, cfg.head_dim, 2, device=dev).float() / cfg.head_dim))
+        ang = torch.outer(torch.arange(cfg.max_seq_len, device=dev).float(), inv)
+        ang = torch.cat((ang, ang), dim=-1)
+        self.register_buffer("rope_cos", ang.cos().half(), persistent=False)
+        self.register_buffer("rope_sin", ang.sin().half(), persistent=False)
+        self.ref_mod = None   # set to the oracle/_ref module to time the reference kernel inside the same runner
+
+    @torch.no_grad()
+    def forward(self, input_ids: torch.Tensor, pos_idx: torch.Tensor):
+        """input_ids (B, T); pos_idx (T,) int64 device tensor of the cache positions being written."""
+        cfg = self.cfg
+        x = self.embed(input_ids)
+        cos = self.rope_cos.index_select(0, pos_idx)[None, None]
+        sin = self.rope_sin.index_select(0, pos_idx)[None, None]
+        # causal mask over the static cache: key j visible to query at position p iff j <= p
+        keys = torch.arange(cfg.max_seq_len, device=x.device)
+        attn_mask = keys[None, :] <= pos_idx[:, None]
+        for blk in self.blocks:
+            x = blk(x, cos, sin, pos_idx, attn_mask, self.ref_mod)
+        return self.lm_head(self.norm(x[:, -1:, :]))
+
+    def weight_bytes(self):
+        n = 0
+        for blk in self.blocks:
+            for m in (blk.qkv_proj, blk.o_proj, blk.gate_up_proj, blk.down_proj):
+                n += m.in_features * m.out_features // 2 + (m.in_features // m.group_size) * m.out_features * 4
+        return n + self.lm_head.weight.numel() * 2
+
+
+@torch.no_grad()
+def benchmark_generation(model: LlamaLikeQuickModel, n_context: int, n_generate: int, use_graph: bool = True):
+    """Reference methodology (examples/benchmark.py:38-67,127-129): prefill tokens/s = ctx*batch / prefill
+    seconds, decode tokens/s = batch / median(decode step seconds); CUDA events."""
+    dev = model.embed.weight.device
+    B = model.batch
+    ids = torch.randint(0, model.cfg.vocab_size, (B, n_context), device=dev)
+    pos = torch.arange(n_context, device=dev)
+    for _ in range(2):
+        model(ids, pos)       # warm-up (also builds the B200 weight copies)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); logits = model(ids, pos); e1.record(); torch.cuda.synchronize()
+    prefill_s = e0.elapsed_time(e1) * 1e-3
+
+    tok = logits.argmax(-1).view(B, 1)
+    step_pos = torch.tensor([n_context], device=dev)
+    static_tok, static_pos = tok.clone(), step_pos.clone()
+    graph = None
+    if use_graph and model.ref_mod is None:   # the reference kernel launches on the legacy stream: not capturable
+        for _ in range(2):
+            model(static_tok, static_pos)
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                static_out = model(static_tok, static_pos)
+        torch.cuda.synchronize()
+    times = []
+    for i in range(n_generate):
+        static_pos.fill_(n_context + i)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        if graph is not None:
+            graph.replay(); out = static_out
+        else:
+            out = model(static_tok, static_pos)
+        b.record(); torch.cuda.synchronize()
+        times.append(a.elapsed_time(b) * 1e-3)
+        static_tok.copy_(out.argmax(-1).view(B, 1))
+    times.sort()
+    med = times[len(times) // 2]
+    return {"batch": B, "prefill_len": n_context, "decode_len": n_generate, "prefill_tokens_per_s": n_context * B / prefill_s,
+            "decode_tokens_per_s": B / med, "decode_ms_per_step": med * 1e3, "cuda_graph": graph is not None}

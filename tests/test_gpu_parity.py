@@ -290,3 +290,36 @@ def test_repeated_launches_are_deterministic_and_never_hang(ops):
             if it % 500 == 499:
                 torch.cuda.synchronize()
                 assert torch.equal(out, first[it % 6]), (M, tok, split, it)
+
+
+def test_llama_like_runner_matches_dense_fp16_model(ops):
+    """the minimal runner (all linears through the tcgen05 kernel, CUDA-graph-free here) against
+    the same network with every WQLinear_QUICK replaced by its dequantised fp16 weight and torch.matmul."""
+    from quick_b200.awq.models.llama_like import PRESETS, LlamaLikeQuickModel
+    import copy
+    cfg = copy.deepcopy(PRESETS["tiny"])
+    model = LlamaLikeQuickModel(cfg, batch=2)
+    ids = torch.randint(0, cfg.vocab_size, (2, 24), device="cuda")
+    pos = torch.arange(24, device="cuda")
+    logits = model(ids, pos)
+    # decode one more token on top of the cache
+    nxt = model(logits.argmax(-1).view(2, 1), torch.tensor([24], device="cuda"))
+
+    dense = {}
+    for blk in model.blocks:
+        for m in (blk.qkv_proj, blk.o_proj, blk.gate_up_proj, blk.down_proj):
+            wq, sz, K, N, G = ops.prepack(m.qweight, m.qzeros, m.scales)
+            dense[id(m)] = ops.dequantize(wq, sz, K, N, G)
+    import quick_b200.awq.models.llama_like as ll
+    orig = ll._linear
+    ll._linear = lambda m, x, ref_mod=None: (x.reshape(-1, x.shape[-1]).float() @ dense[id(m)].float()).half().reshape(x.shape[:-1] + (m.out_features,))
+    try:
+        for blk in model.blocks:
+            blk.cache_k.zero_(); blk.cache_v.zero_()
+        ref_logits = model(ids, pos)
+        ref_nxt = model(ref_logits.argmax(-1).view(2, 1), torch.tensor([24], device="cuda"))
+    finally:
+        ll._linear = orig
+    for a, b in ((logits, ref_logits), (nxt, ref_nxt)):
+        rms = b.float().pow(2).mean().sqrt().item()
+        assert (a.float() - b.float()).abs().max().item() <= 3e-2 * rms + 1e-3, "runner logits drifted from the dense model"

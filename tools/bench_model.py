@@ -1,0 +1,35 @@
+"""tokens/s of a random-init Llama-like AWQ-QUICK model (BASELINE configs[2..3]; reference methodology of
+examples/benchmark.py: prefill = decode = 128).  --impl reference runs the same runner with every linear
+routed to the unmodified reference kernel (oracle/_ref)."""
+import argparse, json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from quick_b200.awq.models.llama_like import PRESETS, LlamaLikeQuickModel, benchmark_generation
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--model", default="llama-2-7b", choices=list(PRESETS))
+ap.add_argument("--batch", type=int, nargs="+", default=[1, 8, 32, 64])
+ap.add_argument("--ctx", type=int, default=128)
+ap.add_argument("--gen", type=int, default=128)
+ap.add_argument("--layers", type=int, default=0, help="override layer count (0 = preset)")
+ap.add_argument("--impl", default="quick_b200", choices=["quick_b200", "reference"])
+ap.add_argument("--out", default="")
+args = ap.parse_args()
+cfg = PRESETS[args.model]
+if args.layers:
+    cfg.num_layers = args.layers
+cfg.max_seq_len = args.ctx + args.gen
+rows = []
+for bs in args.batch:
+    model = LlamaLikeQuickModel(cfg, bs)
+    if args.impl == "reference":
+        from oracle.build_ref import load_ref
+        model.ref_mod = load_ref(); assert model.ref_mod is not None
+    r = benchmark_generation(model, args.ctx, args.gen)
+    r.update({"model": args.model, "impl": args.impl, "layers": cfg.num_layers, "weight_GB": round(model.weight_bytes() / 1e9, 2),
+              "mem_GB": round(torch.cuda.max_memory_allocated() / 1e9, 2)})
+    rows.append(r); print(json.dumps(r), flush=True)
+    del model; torch.cuda.empty_cache()
+if args.out:
+    json.dump(rows, open(args.out, "w"), indent=1)
