@@ -58,37 +58,56 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 // Optional host-mapped buffer (qb200_debug_set_trace): a timed-out wait records who was waiting on what
 // before trapping, so a protocol bug is diagnosable after the context is gone.
 __device__ unsigned long long* g_qb_timeout_report = nullptr;
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0, int iter = -1) {
-  uint32_t done = 0;
-  long long t0 = 0;
-  bool timed = false;
-  while (true) {
-    asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (!timed) { t0 = clock64(); timed = true; }
-    else if (clock64() - t0 > QB200_WAIT_TIMEOUT_CYCLES) {
-      unsigned long long* rep = g_qb_timeout_report;
-      if (rep != nullptr && (threadIdx.x & 31) == 0) {
-        // first block to time out claims the report; each of its warps fills its own row, then lingers so
-        // the other warps of the block (stuck on the same lost event) can report before the trap
-        const unsigned long long me = 1ull + ((static_cast<unsigned long long>(blockIdx.x) << 20) | (blockIdx.y << 10) | blockIdx.z);
-        const unsigned long long prev = atomicCAS(rep, 0ull, me);
-        if (prev == 0ull || prev == me) {
-          unsigned long long st;
-          asm volatile("ld.shared.u64 %0, [%1];" : "=l"(st) : "r"(bar) : "memory");
-          unsigned long long* row = rep + 8 + (threadIdx.x >> 5) * 8;
-          row[0] = tag; row[1] = iter; row[2] = bar; row[3] = parity; row[4] = st; row[5] = 1;
-          __threadfence_system();
-        }
-        const long long t1 = clock64();
-        while (clock64() - t1 < QB200_WAIT_TIMEOUT_CYCLES / 4) { }
-      }
-      __trap();
+// Polls in a tight PTX loop (try_wait itself suspends the warp in hardware for a bounded time, so idle warps
+// do not steal issue slots); the clock is only read on the slow path, once per 4096 polls.
+__device__ __forceinline__ uint32_t mbar_poll(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .u32 cnt;\n"
+      "mov.u32 cnt, 0;\n"
+      "QB_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "@p bra QB_WAIT_DONE;\n"
+      "add.u32 cnt, cnt, 1;\n"
+      "setp.lt.u32 p, cnt, 4096;\n"
+      "@p bra QB_WAIT_LOOP;\n"
+      "mov.u32 %0, 0;\n"
+      "bra QB_WAIT_EXIT;\n"
+      "QB_WAIT_DONE:\n"
+      "mov.u32 %0, 1;\n"
+      "QB_WAIT_EXIT:\n"
+      "}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
+__device__ __noinline__ void mbar_timeout_report(uint32_t bar, uint32_t parity, int tag, int iter) {
+  unsigned long long* rep = g_qb_timeout_report;
+  if (rep != nullptr && (threadIdx.x & 31) == 0) {
+    // first block to time out claims the report; each of its warps fills its own row, then lingers so
+    // the other warps of the block (stuck on the same lost event) can report before the trap
+    const unsigned long long me = 1ull + ((static_cast<unsigned long long>(blockIdx.x) << 20) | (blockIdx.y << 10) | blockIdx.z);
+    const unsigned long long prev = atomicCAS(rep, 0ull, me);
+    if (prev == 0ull || prev == me) {
+      unsigned long long st;
+      asm volatile("ld.shared.u64 %0, [%1];" : "=l"(st) : "r"(bar) : "memory");
+      unsigned long long* row = rep + 8 + (threadIdx.x >> 5) * 8;
+      row[0] = tag; row[1] = iter; row[2] = bar; row[3] = parity; row[4] = st; row[5] = 1;
+      __threadfence_system();
     }
+    const long long t1 = clock64();
+    while (clock64() - t1 < QB200_WAIT_TIMEOUT_CYCLES / 4) { }
+  }
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag = 0, int iter = -1) {
+  if (mbar_poll(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_poll(bar, parity)) {
+    if (clock64() - t0 > QB200_WAIT_TIMEOUT_CYCLES) mbar_timeout_report(bar, parity, tag, iter);
   }
 }
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
