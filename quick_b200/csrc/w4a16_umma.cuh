@@ -34,7 +34,7 @@ constexpr int kEpilogueWarps = 8;    // warps 0..7 run the epilogue
 // issuers on warps 0/1 every already-complete mbarrier wait cost ~300 cycles).
 // NWG dequant warpgroups (4 warps each, warp % 4 = TMEM lane quadrant) take pipeline stages round-robin.
 template <int TOK>
-constexpr int default_nwg() { return TOK <= 64 ? 4 : 2; }
+constexpr int default_nwg() { return TOK <= 64 ? 3 : 2; }   // measured best of (2,6) (3,3) (3,6) (4,4) (5,5) (6,6)
 
 // ------------------------------------------------------------------------------------------------
 // PTX helpers
@@ -302,7 +302,7 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
 constexpr int kSubPerStage = 2;                          // k64 blocks per stage
 constexpr int kWStageBytesV3 = kSubPerStage * kWStageBytes;   // 8192
 template <int TOK>
-constexpr int default_depth() { return TOK <= 128 ? 4 : 3; }
+constexpr int default_depth() { return TOK <= 64 ? 6 : TOK == 128 ? 4 : 3; }
 
 template <int TOK, int D = default_depth<TOK>(), int NWG = default_nwg<TOK>()>
 struct TileCfg {
