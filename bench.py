@@ -34,6 +34,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# keep stdout to the one JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG >= VERSION
+os.environ["NCCL_DEBUG"] = os.environ.get("QB200_NCCL_DEBUG", "NONE")
 
 import torch
 
@@ -282,7 +284,7 @@ def run_mine(args):
         barrier(world)
         dt = max_over_ranks(time.perf_counter() - t0, world)
         e2e = {"value": round(sum(flops(M) for M in MS) * nh * reps * world / dt / 1e12, 3), "unit": "TOPS",
-               "h2d_bytes_per_step": sum(2 * M * K for M in MS) * nh, "d2h_bytes_per_step": sum(2 * M * N for M in MS) * nh,
+               "h2d_bytes_per_step": sum(2 * M * K for M in MS) * nh * world, "d2h_bytes_per_step": sum(2 * M * N for M in MS) * nh * world,
                "api": "qb200_linear_forward_host (C-ABI, pinned host x -> device GEMM -> pinned host y, synchronous)",
                "gemms_per_step": len(MS) * nh, "note": "weights are module state resident in HBM, as in WQLinear_QUICK"}
         for h in handles:
