@@ -106,9 +106,12 @@ void qb200_linear_destroy(qb200_linear* h);
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches claim). */
 unsigned long long qb200_launch_count(void);
 
-/* Debug only: device buffer of >= 4*256*4 int64 that CTA (0,0,0) of every later GEMM launch fills with
+/* Debug only: device buffer of >= 6*256*4 int64 that CTA (0,0,0) of every later GEMM launch fills with
  * clock64() stamps per warp role and k-stage (NULL disables; disabled by default). */
 void qb200_debug_set_trace(void* device_buffer);
+/* Debug only: selects the alternative tile configurations (ring depths / warpgroup counts) compiled into
+ * QB200_VARIANTS builds for A/B measurements; 0 = default.  No effect in the shipped library. */
+void qb200_debug_set_variant(int variant);
 
 #ifdef __cplusplus
 }

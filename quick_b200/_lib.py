@@ -16,7 +16,7 @@ SYMBOLS = [
     "qb200_relayout_from_quick", "qb200_pack_quick", "qb200_dequantize", "qb200_gemm_w4a16",
     "qb200_gemm_w4a16_cfg", "qb200_gemm_plan", "qb200_gemm_forward_quick", "qb200_gemm_w4a16_simt",
     "qb200_linear_create", "qb200_linear_forward_host", "qb200_linear_forward", "qb200_linear_destroy",
-    "qb200_launch_count", "qb200_debug_set_trace",
+    "qb200_launch_count", "qb200_debug_set_trace", "qb200_debug_set_variant",
 ]
 
 QB200_OK, QB200_EINVAL, QB200_ECUDA, QB200_ENOSPC = 0, -1, -2, -3
@@ -61,6 +61,8 @@ def load() -> C.CDLL:
     lib.qb200_launch_count.restype = C.c_ulonglong
     lib.qb200_debug_set_trace.argtypes = [vp]
     lib.qb200_debug_set_trace.restype = None
+    lib.qb200_debug_set_variant.argtypes = [i32]
+    lib.qb200_debug_set_variant.restype = None
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("qb200_version",):

@@ -32,18 +32,31 @@ def _newer(target: str, sources: list[str]) -> bool:
     return all(os.path.getmtime(s) <= t for s in sources)
 
 
-def build_lib(force: bool = False, verbose: bool = False) -> str:
+def build_lib(force: bool = False, verbose: bool = False, defines: tuple[str, ...] = (), out: str | None = None) -> str:
+    """defines/out: development builds only (e.g. ("QB200_TRACE", "QB200_VARIANTS") -> libquick_b200_dev.so,
+    selected with the QB200_LIB environment variable); the product library is built without defines."""
     srcs = [os.path.join(CSRC, "quick_b200.cu"), os.path.join(CSRC, "w4a16_umma.cuh"),
             os.path.join(ROOT, "include", "quick_b200.h")]
-    if not force and _newer(LIB, srcs):
-        return LIB
+    target = out or LIB
+    if not force and _newer(target, srcs):
+        return target
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, srcs[0]]
+    cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", target, srcs[0]]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)
-    return LIB
+    return target
+
+
+DEV_LIB = os.path.join(PKG, "libquick_b200_dev.so")       # + alternative tile variants (timing A/B)
+TRACE_LIB = os.path.join(PKG, "libquick_b200_trace.so")   # + in-kernel clock64 trace (tools/trace.py)
+
+
+def build_dev_libs(force: bool = False):
+    """Development builds used by tools/ through QB200_LIB (never loaded by the product path)."""
+    return (build_lib(force=force, defines=("QB200_VARIANTS",), out=DEV_LIB),
+            build_lib(force=force, defines=("QB200_TRACE", "QB200_VARIANTS"), out=TRACE_LIB))
 
 
 def build_ext(force: bool = False, verbose: bool = False) -> str:
@@ -77,3 +90,5 @@ def build_all(force: bool = False, verbose: bool = False):
 
 if __name__ == "__main__":
     print(build_all(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--dev" in sys.argv:
+        print(build_dev_libs(force="--force" in sys.argv))

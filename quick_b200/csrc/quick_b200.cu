@@ -253,10 +253,13 @@ bool use_pdl() {   // QB200_NO_PDL=1 disables programmatic dependent launch (A/B
   return v == 1;
 }
 
-template <int TOK, int SPLIT>
+std::atomic<int> g_variant{0};         // tile-configuration variant (qb200_debug_set_variant): 0 = default
+std::atomic<int> g_skip_pdl_once{0};   // set by the layout kernels: the GEMM that follows must not prefetch their output early
+
+template <int TOK, int SPLIT, int VAR>
 int launch_umma(const CUtensorMap& map, const qb200::GemmArgs& args, int m_tiles, cudaStream_t stream) {
-  using Cfg = qb200::TileCfg<TOK>;
-  auto kfn = qb200::w4a16_umma_kernel<TOK, SPLIT>;
+  using Cfg = qb200::TileCfg<TOK, VAR>;
+  auto kfn = qb200::w4a16_umma_kernel<TOK, SPLIT, VAR>;
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
     QB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes(SPLIT)));
@@ -272,26 +275,37 @@ int launch_umma(const CUtensorMap& map, const qb200::GemmArgs& args, int m_tiles
   attr[0].val.clusterDim.x = 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = SPLIT;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap our prologue with the previous kernel's tail
+  // PDL: this GEMM's CTAs start (barrier init, TMEM allocation, weight TMA, first dequant) while the previous
+  // kernel of the stream is still running; the weights must therefore not be an output of that kernel.
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = use_pdl() ? 2 : 1;
+  const bool pdl = use_pdl() && g_skip_pdl_once.exchange(0, std::memory_order_relaxed) == 0;
+  cfg.numAttrs = pdl ? 2 : 1;
   QB_CUDA(cudaLaunchKernelEx(&cfg, kfn, map, args));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return QB200_OK;
 }
 
-template <int TOK>
+template <int TOK, int VAR>
 int dispatch_split(int split, const CUtensorMap& map, const qb200::GemmArgs& args, int m_tiles, cudaStream_t st) {
   switch (split) {
-    case 1: return launch_umma<TOK, 1>(map, args, m_tiles, st);
-    case 2: return launch_umma<TOK, 2>(map, args, m_tiles, st);
-    case 4: return launch_umma<TOK, 4>(map, args, m_tiles, st);
+    case 1: return launch_umma<TOK, 1, VAR>(map, args, m_tiles, st);
+    case 2: return launch_umma<TOK, 2, VAR>(map, args, m_tiles, st);
+    case 4: return launch_umma<TOK, 4, VAR>(map, args, m_tiles, st);
     case 8:
-      if constexpr (TOK <= 32) return launch_umma<TOK, 8>(map, args, m_tiles, st);
+      if constexpr (TOK <= 32) return launch_umma<TOK, 8, VAR>(map, args, m_tiles, st);
       break;
   }
   return fail(QB200_EINVAL, "unsupported split %d for tok %d", split, TOK);
+}
+
+template <int TOK>
+int dispatch_variant(int split, const CUtensorMap& map, const qb200::GemmArgs& args, int m_tiles, cudaStream_t st) {
+#ifdef QB200_VARIANTS
+  if (g_variant.load(std::memory_order_relaxed) == 1) return dispatch_split<TOK, 1>(split, map, args, m_tiles, st);
+#endif
+  return dispatch_split<TOK, 0>(split, map, args, m_tiles, st);
 }
 
 int check_device() {
@@ -330,6 +344,7 @@ extern "C" {
 const char* qb200_version(void) { return "quick_b200 0.1 (sm_100a tcgen05/TMEM/TMA W4A16)"; }
 const char* qb200_last_error(void) { return g_last_error.c_str(); }
 unsigned long long qb200_launch_count(void) { return g_launches.load(); }
+void qb200_debug_set_variant(int variant) { g_variant.store(variant); }
 void qb200_debug_set_trace(void* device_buffer) {
   g_trace = reinterpret_cast<long long*>(device_buffer);
   // the same buffer (host-mapped if it should survive a trap) receives the timed-out-wait report
@@ -361,6 +376,7 @@ int qb200_relayout_from_quick(const int32_t* qweight, const int32_t* qzeros, con
   relayout_sz_kernel<<<static_cast<unsigned>((nsz + 255) / 256), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const uint32_t*>(qzeros), reinterpret_cast<const __half*>(scales), sz, K / G, N);
   g_launches.fetch_add(2, std::memory_order_relaxed);
+  g_skip_pdl_once.store(1, std::memory_order_relaxed);   // wq/sz are being written: the next GEMM launches fully serialised
   QB_CUDA(cudaGetLastError());
   return QB200_OK;
 }
@@ -434,11 +450,11 @@ int qb200_gemm_w4a16_cfg(const void* A, const uint32_t* wq, const uint32_t* sz, 
   args.trace = g_trace;
   cudaStream_t st = as_stream(stream);
   switch (tok) {
-    case 16: return dispatch_split<16>(split, map, args, m_tiles, st);
-    case 32: return dispatch_split<32>(split, map, args, m_tiles, st);
-    case 64: return dispatch_split<64>(split, map, args, m_tiles, st);
-    case 128: return dispatch_split<128>(split, map, args, m_tiles, st);
-    case 256: return dispatch_split<256>(split, map, args, m_tiles, st);
+    case 16: return dispatch_variant<16>(split, map, args, m_tiles, st);
+    case 32: return dispatch_variant<32>(split, map, args, m_tiles, st);
+    case 64: return dispatch_variant<64>(split, map, args, m_tiles, st);
+    case 128: return dispatch_variant<128>(split, map, args, m_tiles, st);
+    case 256: return dispatch_variant<256>(split, map, args, m_tiles, st);
   }
   return fail(QB200_EINVAL, "unsupported token tile %d", tok);
 }

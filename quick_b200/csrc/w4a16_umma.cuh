@@ -12,11 +12,14 @@
 //       - the ACTIVATIONS are the B operand in shared memory (K-major, 128B swizzle) loaded by TMA
 //   * packed weights in the "B200 layout" (see include/quick_b200.h): one thread = one TMEM lane =
 //     one output channel, its 16-byte shared-memory read = 32 consecutive k = 16 TMEM columns
-//   * warp roles: warps 0..7 = dequant, warp 8 = TMA producer, warp 9 = MMA issuer (+TMEM alloc)
-//     (two warpgroups alternating k64 stages) and epilogue
+//   * warp roles: 4*NWG dequant warps (warpgroups take 128-k stages round-robin; the first two also run the
+//     epilogue), one TMA producer warp, one MMA issuer warp (+ TMEM owner)
+//   * three decoupled rings: W stages (shared memory, filled before griddepcontrol.wait), X stages (shared
+//     memory), A slots (tensor memory)
 //   * split-K lives inside a thread-block cluster (1,1,SPLIT): partial tiles are exchanged through
-//     distributed shared memory, each CTA reduces and stores TOK/SPLIT token columns; no HBM temp,
-//     no second kernel (reference: (split_k,M,N) temp + at::sum, gemm_cuda_quick.cu:1468,1515)
+//     distributed shared memory (st.async register fragments for small tiles, TMA bulk copies for large
+//     ones), each CTA reduces and stores TOK/SPLIT token columns; no HBM temp, no second kernel
+//     (reference: (split_k,M,N) temp + at::sum, gemm_cuda_quick.cu:1468,1515)
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -29,12 +32,8 @@ constexpr int kChan = 128;          // channels per tile = UMMA M
 constexpr int kBK = 64;             // k per pipeline stage
 constexpr int kWStageBytes = kChan * kBK / 2;   // 4096
 constexpr int kEpilogueWarps = 8;    // warps 0..7 run the epilogue
-// Warp roles.  The single-thread issuers get the HIGHEST warp ids: the SM's warp arbiter favours
-// higher warp ids, and a starved TMA/MMA issuer stalls the whole pipeline (measured: with the
-// issuers on warps 0/1 every already-complete mbarrier wait cost ~300 cycles).
-// NWG dequant warpgroups (4 warps each, warp % 4 = TMEM lane quadrant) take pipeline stages round-robin.
-template <int TOK>
-constexpr int default_nwg() { return TOK <= 64 ? 3 : 2; }   // measured best of (2,6) (3,3) (3,6) (4,4) (5,5) (6,6)
+// The single-thread issuers get the HIGHEST warp ids: the SM's warp arbiter favours higher warp ids, and a
+// starved TMA/MMA issuer stalls the whole pipeline.
 
 // ------------------------------------------------------------------------------------------------
 // PTX helpers
@@ -295,43 +294,83 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
   return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
 }
 
-// Pipeline stage = 128 k (two k64 blocks): W nibbles 8 KB, X tile 2 x [TOK][128 B] swizzled panels, TMEM A
-// slot 64 columns.  The shared-memory stages and the TMEM A slots form ONE ring of depth D, so a single
-// "consumed" barrier per slot (4 dequant-warp arrivals + 1 tcgen05.commit) releases both.  Depths are
-// chosen so that TOK <= 64 tiles fit 2 CTAs / SM (TMEM <= 256 columns, smem <= ~110 KB).
-constexpr int kSubPerStage = 2;                          // k64 blocks per stage
-constexpr int kWStageBytesV3 = kSubPerStage * kWStageBytes;   // 8192
-template <int TOK>
-constexpr int default_depth() { return TOK <= 64 ? 6 : TOK == 128 ? 4 : 3; }
+// ------------------------------------------------------------------------------------------------
+// Pipeline geometry.  A pipeline stage is 128 k (two k64 blocks): W nibbles 8 KB, X tile 2 x [TOK][128 B]
+// swizzled panels, TMEM A slot 64 columns.  Two rings:
+//   W ring (DS stages, shared memory)   — hides HBM latency; filled BEFORE griddepcontrol.wait, i.e. while the
+//                                         previous kernel of the stream is still running (weights are constants)
+//   operand ring (D2 slots)             — slot = X stage in shared memory (hides the L2 latency of the
+//                                         activations, which come from the previous kernel) + A slot in tensor
+//                                         memory (dequant -> MMA hand-off; the first D2 stages are dequantised
+//                                         before the activations arrive)
+// Per operand slot ONE "ready" barrier (4 dequant-warp arrivals + the producer's expect_tx arrival + the X
+// bytes) and ONE "free" barrier (a single tcgen05.commit): the MMA issuer — the serial spine of the kernel —
+// does one wait and one commit per stage.
+// Small tiles (TOK <= 64) are sized so that two CTAs are co-resident on an SM (<= 72 registers x 448 threads,
+// <= 256 TMEM columns, <= 113 KB shared memory): under programmatic dependent launch the next GEMM's CTAs sit
+// next to the running ones with their weights already in shared memory and TMEM.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSubPerStage = 2;                              // k64 blocks per stage
+constexpr int kWStage = kSubPerStage * kWStageBytes;         // 8192
+constexpr int kASlotCols = 32 * kSubPerStage;                // 64 TMEM columns = 128 k of fp16 pairs
 
-template <int TOK, int D = default_depth<TOK>(), int NWG = default_nwg<TOK>()>
+template <int NWG_, int DS_, int D2_>
+struct Rings {
+  static constexpr int NWG = NWG_, DS = DS_, D2 = D2_;
+};
+// VAR 0 = default, VAR 1 = alternative kept for A/B measurements (tools/tune.py, qb200_debug_set_variant)
+template <int TOK, int VAR> struct Variant;
+template <> struct Variant<16, 0> : Rings<3, 6, 3> {};
+template <> struct Variant<16, 1> : Rings<2, 8, 3> {};
+template <> struct Variant<32, 0> : Rings<3, 6, 3> {};
+template <> struct Variant<32, 1> : Rings<2, 8, 3> {};
+template <> struct Variant<64, 0> : Rings<3, 6, 3> {};
+template <> struct Variant<64, 1> : Rings<2, 6, 3> {};
+template <> struct Variant<128, 0> : Rings<2, 4, 4> {};
+template <> struct Variant<128, 1> : Rings<2, 4, 2> {};
+template <> struct Variant<256, 0> : Rings<2, 4, 3> {};
+template <> struct Variant<256, 1> : Rings<2, 4, 2> {};
+
+template <int TOK, int VAR = 0>
 struct TileCfg {
-  static constexpr int kDepth = D;
-  static constexpr int kNumWG = NWG;
-  static constexpr int kProducerWarp = 4 * NWG;
-  static constexpr int kMmaWarp = 4 * NWG + 1;
-  static constexpr int kNumThreads = (4 * NWG + 2) * 32;
-  // when D is a multiple of NWG a slot is always consumed by the same warpgroup, so its warps see every
-  // phase of "their" full barriers in order; otherwise each warp must also observe the skipped stages
-  static constexpr bool kInOrderWaits = (D % NWG) != 0;
+  using R = Variant<TOK, VAR>;
+  static constexpr int kNumWG = R::NWG, kDS = R::DS, kD2 = R::D2;
+  // A W slot is always served by the same warpgroup (DS % NWG == 0), so its warps observe every phase of
+  // "their" TMA barriers in order (mbarrier parity waits are only valid one phase ahead, and TMA completions
+  // arrive out of order).  The "free" barriers complete in MMA order, so D2 >= NWG suffices for them.
+  static_assert(kDS % kNumWG == 0 && kD2 >= kNumWG, "ring depths vs warpgroup count");
+  static_assert(kDS >= kD2, "the W ring is at least as deep as the operand ring");
+  static constexpr int kProducerWarp = 4 * kNumWG;
+  static constexpr int kMmaWarp = 4 * kNumWG + 1;
+  static constexpr int kNumThreads = (4 * kNumWG + 2) * 32;
   static constexpr int kXPanelBytes = TOK * 128;                      // one k64 panel
   static constexpr int kXStageBytes = kSubPerStage * kXPanelBytes;
-  static constexpr int kStageBytes = kXStageBytes + kWStageBytesV3;
   static constexpr int kACol0 = TOK < 32 ? 32 : TOK;
-  static constexpr int kASlotCols = 32 * kSubPerStage;
-  static constexpr int kColsNeeded = kACol0 + kASlotCols * D;
+  static constexpr int kColsNeeded = kACol0 + kASlotCols * kD2;
   static constexpr int kTmemCols = kColsNeeded <= 32 ? 32 : kColsNeeded <= 64 ? 64 : kColsNeeded <= 128 ? 128
                                    : kColsNeeded <= 256 ? 256 : 512;
   static_assert(kColsNeeded <= 512, "TMEM budget");
-  static constexpr int kBarBytes = (3 * D + 2) * 8 + 16;
-  static constexpr int kPipeBytes = D * kStageBytes;
-  // split-K receive buffer: (SPLIT-1) fp16 partial slices of 128 x (TOK/SPLIT); dedicated (not aliasing the
-  // pipeline stages) for TOK <= 128 so that senders need no "owner finished its main loop" barrier
-  static constexpr bool kDedicatedRecv = TOK <= 128;
-  __host__ __device__ static constexpr int recv_bytes(int split) { return split > 1 ? (split - 1) * kChan * (TOK / split) * 2 : 0; }
+  static constexpr int kNumBars = kDS + 2 * kD2 + 2;
+  static constexpr int kBarBytes = kNumBars * 8 + 16;
+  static constexpr int kPipeBytes = kD2 * kXStageBytes + kDS * kWStage;
+  // split-K exchange: TOK <= 64 sends register fragments with st.async straight into the owner's receive
+  // buffer; larger tiles stage packed fp16 slices and move them with one TMA bulk DSMEM copy per owner.
+  static constexpr bool kAsyncExchange = TOK <= 64;
+  // dedicated receive buffer (not aliasing the pipeline stages): senders need no "owner finished its main
+  // loop" barrier
+  static constexpr bool kDedicatedRecv = TOK <= 64 || (TOK == 128 && kD2 >= 3);
+  __host__ __device__ static constexpr int slice(int split) { return TOK / split; }
+  // bytes per exchanged element: fp32 when a thread owns <= 4 columns of a slice, packed fp16 otherwise
+  __host__ __device__ static constexpr int elem_bytes(int split) { return (kAsyncExchange && slice(split) / 2 <= 4) ? 4 : 2; }
+  __host__ __device__ static constexpr int recv_bytes(int split) {
+    return split > 1 ? (split - 1) * kChan * slice(split) * elem_bytes(split) : 0;
+  }
   __host__ __device__ static constexpr int smem_bytes(int split) {
     return kPipeBytes + kBarBytes + (kDedicatedRecv ? recv_bytes(split) + 16 : 0) + 1024;   // + 1024-B alignment slack
   }
+  // two CTAs per SM: 233472 B per SM, 1 KB reserved per CTA
+  static constexpr bool kCoResident = kTmemCols <= 256 && 2 * (smem_bytes(4) + 1024) <= 233472;
+  static constexpr int kMinBlocks = kCoResident ? 2 : 1;
 };
 
 struct GemmArgs {
@@ -353,9 +392,9 @@ struct GemmArgs {
 #define QB_TRACE(slot, it, k) do { } while (0)
 #endif
 
-// Programmatic dependent launch (PDL): let the next kernel in the stream start its prologue (barrier init,
-// TMEM allocation, weight TMA) while this one is still running, and wait for the previous kernel only where
-// its results (the activations) are first consumed.  No-ops when launched without the PDL attribute.
+// Programmatic dependent launch (PDL): the next kernel in the stream starts while this one is running; it
+// waits for this kernel only where its results (the activations) are first consumed.  No-ops when launched
+// without the PDL attribute.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
@@ -370,26 +409,36 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __device__ __forceinline__ void sts_u16(uint32_t addr, unsigned short v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t a) {
-  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
-}
 // shared::cta -> (remote) shared::cluster bulk copy by the TMA engine, completing on the destination CTA's mbarrier
 __device__ __forceinline__ void bulk_s2dsmem(uint32_t remote_dst, uint32_t local_src, uint32_t bytes, uint32_t remote_bar) {
   asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(remote_dst),
                "r"(local_src), "r"(bytes), "r"(remote_bar)
                : "memory");
 }
+// register -> (remote) shared::cluster store that completes bytes on the destination CTA's mbarrier (SASS: STAS)
+template <int NW>
+__device__ __forceinline__ void st_async(uint32_t remote_dst, const uint32_t* v, uint32_t remote_bar) {
+  if constexpr (NW == 1) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_dst), "r"(v[0]),
+                 "r"(remote_bar)
+                 : "memory");
+  } else if constexpr (NW == 2) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(remote_dst),
+                 "r"(v[0]), "r"(v[1]), "r"(remote_bar)
+                 : "memory");
+  } else {
+    static_assert(NW == 4, "st_async: 1, 2 or 4 words");
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(remote_dst),
+                 "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(remote_bar)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed;" ::: "memory"); }
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t a) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
@@ -418,51 +467,59 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+  return v;
+}
 
 // ------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------
-template <int TOK, int SPLIT, int D = default_depth<TOK>(), int NWG = default_nwg<TOK>()>
-__global__ void __launch_bounds__(TileCfg<TOK, D, NWG>::kNumThreads, 1)
+template <int TOK, int SPLIT, int VAR = 0>
+__global__ void __launch_bounds__(TileCfg<TOK, VAR>::kNumThreads, TileCfg<TOK, VAR>::kMinBlocks)
 w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs args) {
-  using Cfg = TileCfg<TOK, D, NWG>;
+  using Cfg = TileCfg<TOK, VAR>;
+  constexpr int NWG = Cfg::kNumWG, DS = Cfg::kDS, D2 = Cfg::kD2;
   constexpr int kProducerWarp = Cfg::kProducerWarp;
   constexpr int kMmaWarp = Cfg::kMmaWarp;
   constexpr int SLICE = TOK / SPLIT;          // token columns owned by one cluster rank
-  constexpr int CH = SLICE / 2;               // columns per (owner, warpgroup)
+  constexpr int CH = SLICE / 2;               // columns per (owner, epilogue warpgroup)
   static_assert(CH >= 1, "TOK / SPLIT must be >= 2");
+  constexpr bool kAsync = Cfg::kAsyncExchange;
+  constexpr bool kF32X = kAsync && CH <= 4;   // exchange fp32 fragments (else packed fp16)
+  constexpr bool kDirectStore = kAsync && CH <= 4;   // C rows written straight from registers
   constexpr int PIECE = CH < 16 ? CH : 16;    // columns per tcgen05.ld
-  constexpr int UNIT = CH < 8 ? CH : 8;       // columns per exchanged vector (UNIT halves = 2*UNIT bytes per lane)
-  // Epilogue staging.
-  //   recv : partial slices from the other SPLIT-1 ranks as packed fp16, laid out [src][unit][channel][UNIT]
-  //          so that the 32 lanes of a warp (consecutive channels) write one contiguous run — DSMEM, like
-  //          global memory, wants coalesced warps.  Dedicated region for TOK <= 128, else aliases the
-  //          (dead) pipeline stages behind a cluster barrier.
-  //   out  : this CTA's [SLICE tokens][128 channels] fp16 tile (aliases the dead pipeline stages), stored
-  //          with 16-byte coalesced writes.
+  constexpr int UNIT = CH < 8 ? CH : 8;       // columns per exchanged vector
+  constexpr int ES = Cfg::elem_bytes(SPLIT);
+  static_assert(ES == (kF32X ? 4 : 2), "exchange element size");
+  // Epilogue staging (shared memory).
+  //   recv : partial slices from the other SPLIT-1 ranks.
+  //            st.async path : [src][channel][SLICE] elements (fp32 or fp16), dedicated region
+  //            bulk path     : packed fp16 [src][unit][channel][UNIT] (32 lanes of a warp write one contiguous
+  //                            run); dedicated for TOK = 128, else aliases the (dead) pipeline stages behind a
+  //                            cluster barrier
+  //   stage: (bulk path) the partial slices this CTA sends, same layout, LOCAL shared memory (dead pipeline stages)
+  //   out  : this CTA's [SLICE tokens][128 channels] fp16 tile (dead pipeline stages), stored with 16-byte writes
   constexpr int kRecvBytes = Cfg::recv_bytes(SPLIT);
   constexpr int kOutBytes = SLICE * kChan * 2;
   static_assert(kRecvBytes % 16 == 0, "recv alignment");
-  //   stage: the partial slices this CTA sends, same layout, in LOCAL shared memory (aliases the dead pipeline
-  //          stages); one TMA bulk copy per owner moves a slice into the owner's recv slot and completes on the
-  //          owner's mbarrier (cp.async.bulk.shared::cluster.shared::cta) — far faster than per-thread
-  //          st.shared::cluster, and no release/acquire round trip per owner.
-  static_assert((Cfg::kDedicatedRecv ? 0 : kRecvBytes) + kRecvBytes + kOutBytes <= Cfg::kPipeBytes,
-                "epilogue staging must fit the (dead) pipeline stages: X stages then W stages are contiguous");
+  static_assert((kAsync ? 0 : (Cfg::kDedicatedRecv ? 0 : kRecvBytes) + kRecvBytes) + kOutBytes <= Cfg::kPipeBytes,
+                "epilogue staging must fit the (dead) pipeline stages");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t smem_x = smem_base;                                   // D x 2 x [TOK rows][128 B] swizzled
-  const uint32_t smem_w = smem_base + D * Cfg::kXStageBytes;           // D x 2 x [2][128][16 B]
-  const uint32_t bar_full = smem_w + D * kWStageBytesV3;               // TMA landed (W + X)
-  const uint32_t bar_tfull = bar_full + 8 * D;                         // A operand written to TMEM slot
-  const uint32_t bar_cons = bar_tfull + 8 * D;                         // slot consumed: 4 dequant warps + MMA commit
-  const uint32_t bar_accum = bar_cons + 8 * D;                         // all MMAs of the tile done
+  const uint32_t smem_x = smem_base;                                   // D2 x 2 x [TOK rows][128 B] swizzled
+  const uint32_t smem_w = smem_base + D2 * Cfg::kXStageBytes;          // DS x 2 x [2][128][16 B]
+  const uint32_t bar_wfull = smem_w + DS * kWStage;                    // W stage landed (TMA bytes)
+  const uint32_t bar_ready = bar_wfull + 8 * DS;                       // operand slot ready: A in TMEM (4 warps) + X landed
+  const uint32_t bar_free = bar_ready + 8 * D2;                        // operand slot read by its MMAs (one tcgen05.commit)
+  const uint32_t bar_accum = bar_free + 8 * D2;                        // all MMAs of the tile done
   const uint32_t bar_recv = bar_accum + 8;                             // split-K partials from the other ranks landed
   const uint32_t tmem_ptr_smem = bar_recv + 8;
   const uint32_t smem_recv = Cfg::kDedicatedRecv ? ((tmem_ptr_smem + 16 + 15) & ~15u) : smem_x;
-  const uint32_t smem_stage = Cfg::kDedicatedRecv ? smem_x : smem_x + kRecvBytes;
-  const uint32_t smem_out = smem_stage + kRecvBytes;
+  const uint32_t smem_stage = Cfg::kDedicatedRecv ? smem_x : smem_x + kRecvBytes;   // bulk path only
+  const uint32_t smem_out = kAsync ? smem_x : smem_stage + kRecvBytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -473,75 +530,89 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
   const int kb0 = rank * args.kb_per_split;
   const int nkb = min(args.kb_per_split, KB - kb0);            // k64 blocks of this CTA
   const int nst = (nkb + kSubPerStage - 1) / kSubPerStage;     // pipeline stages (last may hold one block)
+  const uint32_t* wsrc = args.wq + (static_cast<size_t>(nt) * KB + kb0) * (kWStageBytes / 4);
+  auto issue_w = [&](int it) {   // one elected producer lane
+    const int s = it % DS;
+    const int nsub = min(kSubPerStage, nkb - it * kSubPerStage);
+    const uint32_t bar = bar_wfull + 8 * s;
+    mbar_arrive_expect_tx(bar, nsub * kWStageBytes);
+    bulk_g2s(smem_w + s * kWStage, wsrc + static_cast<size_t>(it) * (kWStage / 4), nsub * kWStageBytes, bar);
+  };
 
+  // ---------------- setup: three warps work in parallel, everybody meets once ----------------
   pdl_launch_dependents();
   if (threadIdx.x == 0) QB_TRACE(3, 0, 0);
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < D; ++i) {
-      mbar_init(bar_full + 8 * i, 1);
-      mbar_init(bar_tfull + 8 * i, 4);
-      mbar_init(bar_cons + 8 * i, 5);
+  if (warp == kProducerWarp) {
+    // The whole W ring is requested right here — before the TMEM allocation, before griddepcontrol.wait — so
+    // under PDL the HBM stream of this GEMM overlaps the previous kernel.
+    if (elect_one()) {
+      for (int i = 0; i < DS; ++i) mbar_init(bar_wfull + 8 * i, 1);
+      fence_barrier_init();
+      fence_proxy_async();
+      const int npre = min(nst, DS);
+      for (int it = 0; it < npre; ++it) issue_w(it);
+      QB_TRACE(0, 0, 2);
+    }
+    __syncwarp();
+  } else if (warp == kMmaWarp) {
+    tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);   // blocks while a co-resident CTA of the previous kernel holds the columns
+  } else if (threadIdx.x == 0) {
+    for (int i = 0; i < D2; ++i) {
+      mbar_init(bar_ready + 8 * i, 5);   // 4 dequant warps + the producer's expect_tx arrival
+      mbar_init(bar_free + 8 * i, 1);
     }
     mbar_init(bar_accum, 1);
-    if constexpr (SPLIT > 1) mbar_init(bar_recv, 1);   // one expect_tx arrive; the senders' bulk copies complete the bytes
+    mbar_init(bar_recv, 1);   // one expect_tx arrive by the owner; the senders' copies complete the bytes
     fence_barrier_init();
     fence_proxy_async();
     prefetch_tmap(&tmap_x);
   }
-  if (warp == kMmaWarp) tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem) : "memory");
+  const uint32_t tmem_base = lds_u32(tmem_ptr_smem);
+  if constexpr (SPLIT > 1) cluster_arrive_relaxed();   // matched by a wait just before the first remote access
   if (threadIdx.x == 0) QB_TRACE(3, 0, 1);
-  if constexpr (SPLIT > 1) cluster_arrive();   // matched by a wait just before the first remote access
 
   if (warp == kProducerWarp) {
     // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
-    const uint32_t* wsrc = args.wq + (static_cast<size_t>(nt) * KB + kb0) * (kWStageBytes / 4);
-    int s = 0;
-    uint32_t ph = 0;
-    for (int it = 0; it < nst; ++it) {
-      if (it >= D) mbar_wait(bar_cons + 8 * s, ph ^ 1, 1, it);   // the first D slots are free by construction
+    // One in-order loop over the X stages: X(j) reuses the operand slot of stage j-D2, and the W stage issued
+    // with it, W(j+DS-D2), reuses the W slot of the same stage j-D2 — whose nibbles were read into registers
+    // before its MMAs could even start.  So the single "MMAs of stage j-D2 complete" barrier releases both.
+    pdl_wait_prior_grid();   // the activations come from the previous kernel
+    int x = 0;
+    uint32_t xph = 0;
+    for (int j = 0; j < nst; ++j) {
+      if (j >= D2) mbar_wait(bar_free + 8 * x, xph ^ 1, 1, j);
       if (elect_one()) {
-        QB_TRACE(0, it, 0);
-        const int nsub = min(kSubPerStage, nkb - it * kSubPerStage);
-        const uint32_t bar = bar_full + 8 * s;
-        mbar_arrive_expect_tx(bar, nsub * (kWStageBytes + Cfg::kXPanelBytes));
-        bulk_g2s(smem_w + s * kWStageBytesV3, wsrc + static_cast<size_t>(it) * (kWStageBytesV3 / 4), nsub * kWStageBytes, bar);
-        if (it == 0) pdl_wait_prior_grid();   // weights are constants; the activations come from the previous kernel
-        tma_load_2d(smem_x + s * Cfg::kXStageBytes, &tmap_x, bar, (kb0 + it * kSubPerStage) * kBK, mt * TOK);
+        QB_TRACE(0, j, 0);
+        const int nsub = min(kSubPerStage, nkb - j * kSubPerStage);
+        const uint32_t bar = bar_ready + 8 * x;
+        mbar_arrive_expect_tx(bar, nsub * Cfg::kXPanelBytes);
+        tma_load_2d(smem_x + x * Cfg::kXStageBytes, &tmap_x, bar, (kb0 + j * kSubPerStage) * kBK, mt * TOK);
         if (nsub > 1)
-          tma_load_2d(smem_x + s * Cfg::kXStageBytes + Cfg::kXPanelBytes, &tmap_x, bar, (kb0 + it * kSubPerStage + 1) * kBK, mt * TOK);
-        QB_TRACE(0, it, 1);
+          tma_load_2d(smem_x + x * Cfg::kXStageBytes + Cfg::kXPanelBytes, &tmap_x, bar, (kb0 + j * kSubPerStage + 1) * kBK, mt * TOK);
+        const int jw = j + (DS - D2);
+        if (j >= D2 && jw < nst) issue_w(jw);
+        QB_TRACE(0, j, 1);
       }
       __syncwarp();
-      if (++s == D) { s = 0; ph ^= 1; }
-    }
-    // Tail: observe the final "consumed" phase of every slot that was used.  The tcgen05.commit arrives are
-    // asynchronous; if the CTA exited before they landed they would hit the barrier words of the NEXT CTA
-    // scheduled on this SM (same shared-memory layout) and corrupt its phase accounting (seen as rare hangs
-    // under back-to-back launches).
-    for (int i = 0; i < min(D, nst); ++i) {
-      const int it = nst - 1 - i;
-      mbar_wait(bar_cons + 8 * (it % D), (it / D) & 1, 6, it);
+      if (++x == D2) { x = 0; xph ^= 1; }
     }
   } else if (warp == kMmaWarp) {
-    // ===================== MMA issuer =====================
-    // Waits only on "A operand in TMEM": the dequant warps observed the TMA barrier of the same slot before
-    // writing it, so the X tile of the slot is complete (and ordered) by then.
+    // ===================== MMA issuer: one wait, 8 MMAs, one commit per stage =====================
     constexpr uint32_t idesc = make_idesc_f16(TOK);
-    int s = 0;
-    uint32_t ph = 0;
+    int t = 0;
+    uint32_t tph = 0;
     for (int it = 0; it < nst; ++it) {
-      mbar_wait(bar_tfull + 8 * s, ph, 2, it);
+      if (lane == 0) QB_TRACE(5, it, 0);
+      mbar_wait(bar_ready + 8 * t, tph, 2, it);
       tc_fence_after();
       if (elect_one()) {
         QB_TRACE(1, it, 0);
         const int nsub = min(kSubPerStage, nkb - it * kSubPerStage);
-        const uint64_t bdesc = make_smem_desc_sw128(smem_x + s * Cfg::kXStageBytes);
-        const uint32_t a_tmem = tmem_base + Cfg::kACol0 + s * Cfg::kASlotCols;
+        const uint64_t bdesc = make_smem_desc_sw128(smem_x + t * Cfg::kXStageBytes);
+        const uint32_t a_tmem = tmem_base + Cfg::kACol0 + t * kASlotCols;
 #pragma unroll
         for (int j = 0; j < kBK / 16; ++j) {
           // +32 B (= 2 in 16-B units) of start address per k16 step inside the 128-B swizzle row
@@ -553,12 +624,19 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
           for (int j = 0; j < kBK / 16; ++j) umma_f16_ts(tmem_base, a_tmem + 32 + j * 8, bdesc1 + 2 * j, idesc, 1u);
         }
         QB_TRACE(1, it, 1);
-        umma_commit(bar_cons + 8 * s);     // smem slot + TMEM slot free once these MMAs have completed
+        umma_commit(bar_free + 8 * t);     // X stage, W stage and TMEM A slot free once these MMAs have completed
         if (it == nst - 1) umma_commit(bar_accum);
         QB_TRACE(1, it, 2);
       }
       __syncwarp();
-      if (++s == D) { s = 0; ph ^= 1; }
+      if (++t == D2) { t = 0; tph ^= 1; }
+    }
+    // Tail: observe the final phase of every barrier that receives tcgen05.commit arrivals.  They are
+    // asynchronous; if the CTA exited before they landed they would hit the barrier words of the NEXT CTA
+    // scheduled on this SM (same shared-memory layout) and corrupt its phase accounting.
+    for (int i = 0; i < min(D2, nst); ++i) {
+      const int it = nst - 1 - i;
+      mbar_wait(bar_free + 8 * (it % D2), (it / D2) & 1, 6, it);
     }
   } else {
     // ===================== dequant warps: smem nibbles -> registers -> TMEM A operand =====================
@@ -582,25 +660,13 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
       }
     };
     if (wg < nst) load_sz();
-    int s = wg % D;
-    uint32_t ph = 0;
+    int s = wg % DS, t = wg % D2;
+    uint32_t sph = 0;
     for (int it = wg; it < nst; it += NWG) {
       const int nsub = min(kSubPerStage, nkb - it * kSubPerStage);
-      // mbarrier parity waits are only valid one phase ahead.  The other warpgroup consumes stage it-1, and
-      // TMA completions arrive out of order, so this warp must first observe stage it-1's barrier itself:
-      // otherwise, with slot reuse distance D odd, it could test slot s for stage `it` while the slot is
-      // still in the phase of stage it-D and the parity test would alias and pass (seen as rare hangs).
-      if constexpr (Cfg::kInOrderWaits) {
-        static_assert(!Cfg::kInOrderWaits || NWG == 2, "in-order observation is implemented for two warpgroups");
-        if (it > 0) {
-          const int sp = s == 0 ? D - 1 : s - 1;
-          const uint32_t php = s == 0 ? ph ^ 1 : ph;
-          mbar_wait(bar_full + 8 * sp, php, 7, it - 1);
-        }
-      }
-      mbar_wait(bar_full + 8 * s, ph, 3, it);
+      mbar_wait(bar_wfull + 8 * s, sph, 3, it);
       if (lane == 0 && quad == 2) QB_TRACE(2, it, 0);
-      const uint32_t wbase = smem_w + s * kWStageBytesV3 + ch * 16;
+      const uint32_t wbase = smem_w + s * kWStage + ch * 16;
       uint4 w[4];
       w[0] = lds128(wbase);
       w[1] = lds128(wbase + 2048);
@@ -608,8 +674,6 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
         w[2] = lds128(wbase + 4096);
         w[3] = lds128(wbase + 6144);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_cons + 8 * s);     // W nibbles are in registers
       GroupConsts gc[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) gc[q] = make_group_consts(szw[q]);
@@ -617,11 +681,14 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
       rem += 2 * kSubPerStage * NWG;
       while (rem >= g32) { rem -= g32; ++grp; }
       if (it + NWG < nst) load_sz();
-      // TMEM slot s is free once the MMAs of stage it - D have completed (the previous phase of bar_cons);
-      // the producer already observed that phase before refilling the slot, this wait is the acquire.
-      mbar_wait(bar_cons + 8 * s, ph ^ 1, 4, it);
-      tc_fence_after();
-      const uint32_t a_tmem = tmem_base + lane_addr + Cfg::kACol0 + s * Cfg::kASlotCols;
+      if (lane == 0 && quad == 2) QB_TRACE(4, it, 0);
+      // operand slot t is free once the MMAs of stage it - D2 have completed
+      if (it >= D2) {
+        mbar_wait(bar_free + 8 * t, ((it / D2) & 1) ^ 1, 4, it);
+        tc_fence_after();
+      }
+      if (lane == 0 && quad == 2) QB_TRACE(4, it, 1);
+      const uint32_t a_tmem = tmem_base + lane_addr + Cfg::kACol0 + t * kASlotCols;
 #pragma unroll
       for (int sub = 0; sub < kSubPerStage; ++sub) {
         if (sub < nsub) {
@@ -636,16 +703,19 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
           dequant_word(w[2 * sub + 1].w, gc[2 * sub + 1], r + 28);
           tmem_st16(a_tmem + sub * 32, r);
           tmem_st16(a_tmem + sub * 32 + 16, r + 16);
+          if (sub == 0 && lane == 0 && quad == 2) QB_TRACE(4, it, 2);
         }
       }
       if (lane == 0 && quad == 2) QB_TRACE(2, it, 1);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tfull + 8 * s);
+      if (lane == 0 && quad == 2) QB_TRACE(4, it, 3);
+      if (lane == 0) mbar_arrive(bar_ready + 8 * t);
       if (lane == 0 && quad == 2) QB_TRACE(2, it, 2);
       s += NWG;
-      while (s >= D) { s -= D; ph ^= 1; }
+      if (s >= DS) { s -= DS; sph ^= 1; }
+      t = (t + NWG) % D2;
     }
   }
 
@@ -653,138 +723,227 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
   const int quad = warp & 3;
   const int wg = warp >> 2;
   const int ch = quad * 32 + lane;
-  const bool is_dq = warp < kEpilogueWarps;   // the first two warpgroups run the epilogue
+  const bool is_epi = warp < kEpilogueWarps;   // the first two dequant warpgroups run the epilogue
   const uint32_t d_tmem = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
   const int n0 = nt * kChan;
-  const float bias_v = (args.bias != nullptr && is_dq) ? __half2float(args.bias[n0 + ch]) : 0.f;
+  const int valid = min(TOK, args.M - mt * TOK);    // token columns of this tile that exist (the rest are zero rows)
+  const bool i_own = rank * SLICE < valid;          // this rank's slice holds at least one real row
+  const float bias_v = (args.bias != nullptr && is_epi) ? __half2float(args.bias[n0 + ch]) : 0.f;
+  const int m_base = mt * TOK + rank * SLICE;
 
-  if (is_dq) {
+  if (is_epi) {
     mbar_wait(bar_accum, 0, 5, nst);   // every TMA write landed and every MMA read of this CTA's smem is complete
     tc_fence_after();
     if (threadIdx.x == 0) QB_TRACE(3, 0, 2);
   }
-  if constexpr (SPLIT > 1) {
-    // Exchange partial tiles through distributed shared memory: rank o owns token columns
-    // [o*SLICE, (o+1)*SLICE) and receives the other ranks' partials for them as packed fp16; its own partial
-    // stays in TMEM as fp32.  Point-to-point: each sending warp arrives (release.cluster) on the owner's
-    // bar_recv after its stores; no cluster-wide barrier on the critical path for TOK <= 128.
-    cluster_wait();              // every CTA of the cluster has initialised its barriers
-    if constexpr (!Cfg::kDedicatedRecv) {
-      cluster_arrive();
-      cluster_wait();            // every CTA is past its main loop: the aliased pipeline stages are dead
-    }
-    if (threadIdx.x == 0) QB_TRACE(3, 2, 0);
-    constexpr uint32_t kSliceBytes = kChan * SLICE * 2;
-    if (threadIdx.x == 0) mbar_arrive_expect_tx(bar_recv, (SPLIT - 1) * kSliceBytes);
-    if (is_dq) {
+
+  if constexpr (kAsync) {
+    // ---------- small tiles: register fragments go straight to the owner with st.async ----------
+    if constexpr (SPLIT > 1) {
+      // rank o owns token columns [o*SLICE, (o+1)*SLICE); owners whose slice has no real row neither receive
+      // nor store.  The own partial stays fp32 in TMEM.
+      cluster_wait();              // every CTA of the cluster has initialised its barriers
+      if (threadIdx.x == 0) QB_TRACE(3, 2, 0);
+      if (threadIdx.x == 0 && i_own) mbar_arrive_expect_tx(bar_recv, static_cast<uint32_t>(kRecvBytes));
+      if (is_epi) {
 #pragma unroll 1
-      for (int oo = 1; oo < SPLIT; ++oo) {
-        const int o = (rank + oo) % SPLIT;
-        const uint32_t dst = smem_stage + static_cast<uint32_t>((oo - 1) * kSliceBytes);
+        for (int oo = 1; oo < SPLIT; ++oo) {
+          const int o = (rank + oo) % SPLIT;
+          if (o * SLICE >= valid) continue;
+          const int src_slot = rank < o ? rank : rank - 1;    // my slot among the owner's SPLIT-1 sources
+          const uint32_t dst = mapa_shared(
+              smem_recv + static_cast<uint32_t>((src_slot * kChan + ch) * (SLICE * ES) + wg * CH * ES), static_cast<uint32_t>(o));
+          const uint32_t rbar = mapa_shared(bar_recv, static_cast<uint32_t>(o));
+          if constexpr (kF32X) {
+            uint32_t v[CH];
+            tmem_ld<CH>(d_tmem + o * SLICE + wg * CH, v);
+            tmem_wait_ld();
+            st_async<CH>(dst, v, rbar);
+          } else {
 #pragma unroll 1
-        for (int p = 0; p < CH / PIECE; ++p) {
-          uint32_t v[PIECE];
-          tmem_ld<PIECE>(d_tmem + o * SLICE + wg * CH + p * PIECE, v);
-          tmem_wait_ld();
+            for (int p = 0; p < CH / 8; ++p) {
+              uint32_t v[8], h[4];
+              tmem_ld<8>(d_tmem + o * SLICE + wg * CH + p * 8, v);
+              tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < PIECE; i += UNIT) {
-            const int unit = (wg * CH + p * PIECE + i) / UNIT;       // unit index inside the slice
-            const uint32_t addr = dst + static_cast<uint32_t>((unit * kChan + ch) * (UNIT * 2));
-            if constexpr (UNIT == 8) {
+              for (int i = 0; i < 4; ++i) h[i] = pack_half2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+              st_async<4>(dst + p * 16, h, rbar);
+            }
+          }
+        }
+        if (threadIdx.x == 0) QB_TRACE(3, 2, 1);
+        if (i_own) mbar_wait_cluster(bar_recv, 0);   // all partial slices for my columns have landed
+        if (threadIdx.x == 0) QB_TRACE(3, 2, 2);
+      }
+    }
+    if (is_epi && i_own) {
+      pdl_wait_prior_grid();   // C may alias a buffer the previous kernel still reads/writes
+#pragma unroll 1
+      for (int p = 0; p < CH / PIECE; ++p) {
+        const int j0 = wg * CH + p * PIECE;
+        uint32_t v[PIECE];
+        tmem_ld<PIECE>(d_tmem + rank * SLICE + j0, v);
+        tmem_wait_ld();
+        float acc[PIECE];
+#pragma unroll
+        for (int i = 0; i < PIECE; ++i) acc[i] = __uint_as_float(v[i]) + bias_v;
+        if constexpr (SPLIT > 1) {
+#pragma unroll
+          for (int r = 0; r < SPLIT - 1; ++r) {
+            const uint32_t addr = smem_recv + static_cast<uint32_t>((r * kChan + ch) * (SLICE * ES) + j0 * ES);
+            if constexpr (kF32X) {
+              static_assert(!kF32X || PIECE == CH, "fp32 exchange: one piece per thread");
+              if constexpr (CH == 4) {
+                const uint4 q = lds128(addr);
+                acc[0] += __uint_as_float(q.x); acc[1] += __uint_as_float(q.y);
+                acc[2] += __uint_as_float(q.z); acc[3] += __uint_as_float(q.w);
+              } else if constexpr (CH == 2) {
+                const uint2 q = lds64(addr);
+                acc[0] += __uint_as_float(q.x); acc[1] += __uint_as_float(q.y);
+              } else {
+                acc[0] += __uint_as_float(lds_u32(addr));
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < PIECE; i += 8) {
+                const uint4 q = lds128(addr + i * 2);
+                const float2 a = unpack_half2(q.x), b = unpack_half2(q.y), c = unpack_half2(q.z), d = unpack_half2(q.w);
+                acc[i] += a.x; acc[i + 1] += a.y; acc[i + 2] += b.x; acc[i + 3] += b.y;
+                acc[i + 4] += c.x; acc[i + 5] += c.y; acc[i + 6] += d.x; acc[i + 7] += d.y;
+              }
+            }
+          }
+        }
+        if constexpr (kDirectStore) {
+          // 32 lanes = 32 consecutive channels of one token row: 64-byte runs, no staging round trip
+#pragma unroll
+          for (int i = 0; i < PIECE; ++i) {
+            const int m = m_base + j0 + i;
+            if (m < args.M) args.C[static_cast<size_t>(m) * args.N + n0 + ch] = __float2half_rn(acc[i]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < PIECE; ++i)
+            sts_u16(smem_out + static_cast<uint32_t>(((j0 + i) * kChan + ch) * 2), __half_as_ushort(__float2half_rn(acc[i])));
+        }
+      }
+      if constexpr (!kDirectStore) {
+        named_bar_sync(1, kEpilogueWarps * 32);
+        const int tid = threadIdx.x;             // 0..255
+        const int chunk = tid & 15;
+#pragma unroll 1
+        for (int row = tid >> 4; row < SLICE; row += (kEpilogueWarps * 32) / 16) {
+          const int m = m_base + row;
+          if (m < args.M) {
+            const uint4 v = lds128(smem_out + static_cast<uint32_t>(row * kChan * 2 + chunk * 16));
+            *reinterpret_cast<uint4*>(args.C + static_cast<size_t>(m) * args.N + n0 + chunk * 8) = v;
+          }
+        }
+      }
+      if (threadIdx.x == 0) QB_TRACE(3, 0, 3);
+    }
+    // No exit barrier on this path: an owner leaves only after all its inbound bytes have landed (bar_recv),
+    // and nobody writes into a CTA that owns nothing; outbound st.async data is in flight from registers.
+  } else {
+    // ---------- large tiles: packed fp16 slices staged locally, one TMA bulk DSMEM copy per owner ----------
+    if constexpr (SPLIT > 1) {
+      cluster_wait();              // every CTA of the cluster has initialised its barriers
+      if constexpr (!Cfg::kDedicatedRecv) {
+        cluster_arrive();
+        cluster_wait();            // every CTA is past its main loop: the aliased pipeline stages are dead
+      }
+      if (threadIdx.x == 0) QB_TRACE(3, 2, 0);
+      constexpr uint32_t kSliceBytes = kChan * SLICE * 2;
+      if (threadIdx.x == 0) mbar_arrive_expect_tx(bar_recv, (SPLIT - 1) * kSliceBytes);
+      if (is_epi) {
+#pragma unroll 1
+        for (int oo = 1; oo < SPLIT; ++oo) {
+          const int o = (rank + oo) % SPLIT;
+          const uint32_t dst = smem_stage + static_cast<uint32_t>((oo - 1) * kSliceBytes);
+#pragma unroll 1
+          for (int p = 0; p < CH / PIECE; ++p) {
+            uint32_t v[PIECE];
+            tmem_ld<PIECE>(d_tmem + o * SLICE + wg * CH + p * PIECE, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < PIECE; i += UNIT) {
+              static_assert(kAsync || UNIT == 8, "bulk path exchanges 8-column units");
+              const int unit = (wg * CH + p * PIECE + i) / UNIT;       // unit index inside the slice
+              const uint32_t addr = dst + static_cast<uint32_t>((unit * kChan + ch) * (UNIT * 2));
               sts_v4(addr, pack_half2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
                      pack_half2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])),
                      pack_half2(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])),
                      pack_half2(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
-            } else if constexpr (UNIT == 4) {
-              sts_u32(addr, pack_half2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-              sts_u32(addr + 4, pack_half2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
-            } else if constexpr (UNIT == 2) {
-              sts_u32(addr, pack_half2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-            } else {
-              sts_u16(addr, __half_as_ushort(__float2half_rn(__uint_as_float(v[i]))));
             }
           }
         }
+        fence_proxy_async();                                  // generic-proxy smem writes -> visible to the TMA engine
+        named_bar_sync(1, kEpilogueWarps * 32);
+        if (threadIdx.x < SPLIT - 1) {                        // one thread per owner issues that owner's slice
+          const int oo = threadIdx.x + 1;
+          const int o = (rank + oo) % SPLIT;
+          const int src_slot = rank < o ? rank : rank - 1;    // my slot among the owner's SPLIT-1 sources
+          bulk_s2dsmem(mapa_shared(smem_recv + static_cast<uint32_t>(src_slot * kSliceBytes), static_cast<uint32_t>(o)),
+                       smem_stage + static_cast<uint32_t>((oo - 1) * kSliceBytes), kSliceBytes,
+                       mapa_shared(bar_recv, static_cast<uint32_t>(o)));
+        }
+        if (threadIdx.x == 0) QB_TRACE(3, 2, 1);
+        mbar_wait_cluster(bar_recv, 0);   // all partial slices for my columns have landed
+        if (threadIdx.x == 0) QB_TRACE(3, 2, 2);
       }
-      fence_proxy_async();                                  // generic-proxy smem writes -> visible to the TMA engine
-      named_bar_sync(1, kEpilogueWarps * 32);
-      if (threadIdx.x < SPLIT - 1) {                        // one thread per owner issues that owner's slice
-        const int oo = threadIdx.x + 1;
-        const int o = (rank + oo) % SPLIT;
-        const int src_slot = rank < o ? rank : rank - 1;    // my slot among the owner's SPLIT-1 sources
-        bulk_s2dsmem(mapa_shared(smem_recv + static_cast<uint32_t>(src_slot * kSliceBytes), static_cast<uint32_t>(o)),
-                     smem_stage + static_cast<uint32_t>((oo - 1) * kSliceBytes), kSliceBytes,
-                     mapa_shared(bar_recv, static_cast<uint32_t>(o)));
-      }
-      if (threadIdx.x == 0) QB_TRACE(3, 2, 1);
-      mbar_wait_cluster(bar_recv, 0);   // all partial slices for my columns have landed
-      if (threadIdx.x == 0) QB_TRACE(3, 2, 2);
+      // Every bulk copy is some CTA's inbound slice: once every CTA of the cluster has seen its bar_recv
+      // complete, no TMA engine is still reading anybody's staging buffer.  Arrive now, wait just before exit,
+      // so no CTA frees its shared memory under an in-flight copy.
+      cluster_arrive_relaxed();
     }
-    // Every bulk copy is some CTA's inbound slice: once every CTA of the cluster has seen its bar_recv
-    // complete, no TMA engine is still reading anybody's staging buffer.  Arrive now, wait just before exit,
-    // so no CTA frees its shared memory under an in-flight copy.
-    cluster_arrive();
-  }
-  if (is_dq) {
-    // this thread's CH columns of the owned slice (+ the other ranks' partials) -> fp16 -> staging tile [token][channel]
+    if (is_epi) {
+      // this thread's CH columns of the owned slice (+ the other ranks' partials) -> fp16 -> staging tile [token][channel]
 #pragma unroll 1
-    for (int p = 0; p < CH / PIECE; ++p) {
-      const int j0 = wg * CH + p * PIECE;
-      uint32_t v[PIECE];
-      tmem_ld<PIECE>(d_tmem + rank * SLICE + j0, v);
-      tmem_wait_ld();
-      float acc[PIECE];
+      for (int p = 0; p < CH / PIECE; ++p) {
+        const int j0 = wg * CH + p * PIECE;
+        uint32_t v[PIECE];
+        tmem_ld<PIECE>(d_tmem + rank * SLICE + j0, v);
+        tmem_wait_ld();
+        float acc[PIECE];
 #pragma unroll
-      for (int i = 0; i < PIECE; ++i) acc[i] = __uint_as_float(v[i]) + bias_v;
-      if constexpr (SPLIT > 1) {
+        for (int i = 0; i < PIECE; ++i) acc[i] = __uint_as_float(v[i]) + bias_v;
+        if constexpr (SPLIT > 1) {
 #pragma unroll
-        for (int r = 0; r < SPLIT - 1; ++r) {
+          for (int r = 0; r < SPLIT - 1; ++r) {
 #pragma unroll
-          for (int i = 0; i < PIECE; i += UNIT) {
-            const int unit = (j0 + i) / UNIT;
-            const uint32_t addr = smem_recv + static_cast<uint32_t>(r * (kChan * SLICE * 2) + (unit * kChan + ch) * (UNIT * 2));
-            if constexpr (UNIT == 8) {
+            for (int i = 0; i < PIECE; i += UNIT) {
+              const int unit = (j0 + i) / UNIT;
+              const uint32_t addr = smem_recv + static_cast<uint32_t>(r * (kChan * SLICE * 2) + (unit * kChan + ch) * (UNIT * 2));
               const uint4 q = lds128(addr);
               const float2 a = unpack_half2(q.x), b = unpack_half2(q.y), c = unpack_half2(q.z), d = unpack_half2(q.w);
               acc[i] += a.x; acc[i + 1] += a.y; acc[i + 2] += b.x; acc[i + 3] += b.y;
               acc[i + 4] += c.x; acc[i + 5] += c.y; acc[i + 6] += d.x; acc[i + 7] += d.y;
-            } else if constexpr (UNIT == 4) {
-              const float2 a = unpack_half2(lds_u32(addr)), b = unpack_half2(lds_u32(addr + 4));
-              acc[i] += a.x; acc[i + 1] += a.y; acc[i + 2] += b.x; acc[i + 3] += b.y;
-            } else if constexpr (UNIT == 2) {
-              const float2 a = unpack_half2(lds_u32(addr));
-              acc[i] += a.x; acc[i + 1] += a.y;
-            } else {
-              unsigned short hv;
-              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(addr) : "memory");
-              acc[i] += __half2float(__ushort_as_half(hv));
             }
           }
         }
-      }
 #pragma unroll
-      for (int i = 0; i < PIECE; ++i)
-        sts_u16(smem_out + static_cast<uint32_t>(((j0 + i) * kChan + ch) * 2), __half_as_ushort(__float2half_rn(acc[i])));
-    }
-    if (threadIdx.x == 0) QB_TRACE(3, 2, 3);
-    named_bar_sync(1, kEpilogueWarps * 32);
-    pdl_wait_prior_grid();   // C may alias a buffer the previous kernel still reads/writes
-    // coalesced 16-byte stores: 16 threads cover one 256-byte token row of the tile
-    const int tid = threadIdx.x;             // 0..255
-    const int chunk = tid & 15;
-    const int m_base = mt * TOK + rank * SLICE;
-#pragma unroll 1
-    for (int row = tid >> 4; row < SLICE; row += (kEpilogueWarps * 32) / 16) {
-      const int m = m_base + row;
-      if (m < args.M) {
-        const uint4 v = lds128(smem_out + static_cast<uint32_t>(row * kChan * 2 + chunk * 16));
-        *reinterpret_cast<uint4*>(args.C + static_cast<size_t>(m) * args.N + n0 + chunk * 8) = v;
+        for (int i = 0; i < PIECE; ++i)
+          sts_u16(smem_out + static_cast<uint32_t>(((j0 + i) * kChan + ch) * 2), __half_as_ushort(__float2half_rn(acc[i])));
       }
+      if (threadIdx.x == 0) QB_TRACE(3, 2, 3);
+      named_bar_sync(1, kEpilogueWarps * 32);
+      pdl_wait_prior_grid();   // C may alias a buffer the previous kernel still reads/writes
+      // coalesced 16-byte stores: 16 threads cover one 256-byte token row of the tile
+      const int tid = threadIdx.x;             // 0..255
+      const int chunk = tid & 15;
+#pragma unroll 1
+      for (int row = tid >> 4; row < SLICE; row += (kEpilogueWarps * 32) / 16) {
+        const int m = m_base + row;
+        if (m < args.M) {
+          const uint4 v = lds128(smem_out + static_cast<uint32_t>(row * kChan * 2 + chunk * 16));
+          *reinterpret_cast<uint4*>(args.C + static_cast<size_t>(m) * args.N + n0 + chunk * 8) = v;
+        }
+      }
+      if (threadIdx.x == 0) QB_TRACE(3, 0, 3);
     }
-    if (threadIdx.x == 0) QB_TRACE(3, 0, 3);
+    if constexpr (SPLIT > 1) cluster_wait();
   }
 
-  if constexpr (SPLIT > 1) cluster_wait();
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, Cfg::kTmemCols);

@@ -8,9 +8,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 
-from quick_b200 import ops
+from quick_b200 import _lib, ops
 
 dev = "cuda"
+VARIANTS = [int(v) for v in os.environ.get("VARS", "0").split(",")]   # needs QB200_LIB=libquick_b200_dev.so for 1
+SPLITS = [int(v) for v in os.environ.get("SPLITS", "1,2,4,8").split(",")]
 K = int(os.environ.get("K", 4096)); N = int(os.environ.get("N", 4096)); G = 128
 NSETS = 40
 Ms = [int(m) for m in os.environ.get("MS", "1,8,16,32,64,128,256,512,1024,2048").split(",")]
@@ -57,15 +59,16 @@ for M in Ms:
     toks = [t for t in (16, 32, 64, 128, 256) if t >= min(M, 256) or t == 256]
     toks = [t for t in toks if t <= max(16, 4 * M)] if M <= 64 else [t for t in (64, 128, 256) if t <= max(64, M)]
     auto = ops.plan(M, K, N, G)
-    for tok in toks:
-        for split in (1, 2, 4, 8):
+    for var, tok in [(v, t) for v in VARIANTS for t in toks]:
+        _lib.load().qb200_debug_set_variant(var)
+        for split in SPLITS:
             if split == 8 and tok > 32: continue
             try:
                 cold = time_graph(lambda i: ops.gemm(x, sets[i % NSETS][0], sets[i % NSETS][1], N, G, tok=tok, split=split, out=out), NSETS)
                 hot = time_graph(lambda i: ops.gemm(x, sets[0][0], sets[0][1], N, G, tok=tok, split=split, out=out), NSETS)
             except Exception as e:
                 print("ERR", M, tok, split, str(e)[:200], flush=True); continue
-            rec = {"M": M, "tok": tok, "split": split, "cold_us": cold * 1e6, "hot_us": hot * 1e6,
+            rec = {"M": M, "var": var, "tok": tok, "split": split, "cold_us": cold * 1e6, "hot_us": hot * 1e6,
                    "cold_TOPS": flop / cold / 1e12, "cold_GBs": alg_bytes / cold / 1e9, "auto": [tok, split] == list(auto[:2])}
             res.append(rec)
             print(json.dumps({k: (round(v, 2) if isinstance(v, float) else v) for k, v in rec.items()}), flush=True)
