@@ -388,8 +388,22 @@ struct GemmArgs {
     if (args.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)         \
       args.trace[((slot) * 256 + (it)) * 4 + (k)] = clock64();                                 \
   } while (0)
+// Cross-launch timeline (tools/timeline.py): CTA (0,0,0) of every launch takes a sequence number and stamps
+// %globaltimer at its start / after griddepcontrol.wait / accumulator complete / exit.
+#define QB_TL_BASE (6 * 256 * 4)
+__device__ __forceinline__ long long qb_globaltimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define QB_TL(k)                                                                                        \
+  do {                                                                                                  \
+    if (args.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)                  \
+      args.trace[QB_TL_BASE + 8 + (qb_tl_seq & 255) * 4 + (k)] = qb_globaltimer();                       \
+  } while (0)
 #else
 #define QB_TRACE(slot, it, k) do { } while (0)
+#define QB_TL(k) do { } while (0)
 #endif
 
 // Programmatic dependent launch (PDL): the next kernel in the stream starts while this one is running; it
@@ -541,6 +555,14 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
 
   // ---------------- setup: three warps work in parallel, everybody meets once ----------------
   pdl_launch_dependents();
+#ifdef QB200_TRACE
+  __shared__ int qb_tl_seq_s;
+  if (threadIdx.x == 0 && args.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    qb_tl_seq_s = static_cast<int>(atomicAdd(reinterpret_cast<unsigned long long*>(args.trace + QB_TL_BASE), 1ull));
+    const int qb_tl_seq = qb_tl_seq_s;
+    QB_TL(0);
+  }
+#endif
   if (threadIdx.x == 0) QB_TRACE(3, 0, 0);
   if (warp == kProducerWarp) {
     // The whole W ring is requested right here — before the TMEM allocation, before griddepcontrol.wait — so
@@ -571,6 +593,9 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = lds_u32(tmem_ptr_smem);
+#ifdef QB200_TRACE
+  const int qb_tl_seq = qb_tl_seq_s;
+#endif
   if constexpr (SPLIT > 1) cluster_arrive_relaxed();   // matched by a wait just before the first remote access
   if (threadIdx.x == 0) QB_TRACE(3, 0, 1);
 
@@ -580,6 +605,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
     // with it, W(j+DS-D2), reuses the W slot of the same stage j-D2 — whose nibbles were read into registers
     // before its MMAs could even start.  So the single "MMAs of stage j-D2 complete" barrier releases both.
     pdl_wait_prior_grid();   // the activations come from the previous kernel
+    if (lane == 0) QB_TL(1);
     int x = 0;
     uint32_t xph = 0;
     for (int j = 0; j < nst; ++j) {
@@ -713,6 +739,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
       if (lane == 0 && quad == 2) QB_TRACE(4, it, 3);
       if (lane == 0) mbar_arrive(bar_ready + 8 * t);
       if (lane == 0 && quad == 2) QB_TRACE(2, it, 2);
+      if (lane == 0 && quad != 2) QB_TRACE(5, it, 1 + (quad == 3 ? 2 : quad));   // hand-off of the other quadrants
       s += NWG;
       if (s >= DS) { s -= DS; sph ^= 1; }
       t = (t + NWG) % D2;
@@ -735,6 +762,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
     mbar_wait(bar_accum, 0, 5, nst);   // every TMA write landed and every MMA read of this CTA's smem is complete
     tc_fence_after();
     if (threadIdx.x == 0) QB_TRACE(3, 0, 2);
+    if (threadIdx.x == 0) QB_TL(2);
   }
 
   if constexpr (kAsync) {
@@ -948,6 +976,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, Cfg::kTmemCols);
   if (threadIdx.x == kMmaWarp * 32) QB_TRACE(3, 1, 0);
+  if (threadIdx.x == kMmaWarp * 32) QB_TL(3);
 }
 
 }  // namespace qb200

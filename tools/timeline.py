@@ -1,0 +1,46 @@
+"""Cross-launch timeline (QB200_TRACE build): 40 back-to-back GEMMs replayed from a CUDA graph; CTA (0,0,0) of
+every launch stamps %globaltimer at start / after griddepcontrol.wait / accumulator complete / exit."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from quick_b200 import ops, _lib
+M, K, N = map(int, sys.argv[1:4]); G = 128
+tok = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+split = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+NL = 40
+dev = "cuda"
+lib = _lib.load()
+sets = []
+for i in range(NL):
+    wq = torch.randint(-2**31, 2**31 - 1, (K * N // 8,), device=dev, dtype=torch.int32)
+    sz = torch.full((K // G * N,), 0x64082000, device=dev, dtype=torch.int32)
+    sets.append((wq, sz))
+x = torch.randn(M, K, device=dev).half()
+out = torch.empty(M, N, device=dev, dtype=torch.float16)
+TL = 6 * 256 * 4
+tr = torch.zeros(TL + 8 + 256 * 4, dtype=torch.int64, device=dev)
+def run():
+    for i in range(NL): ops.gemm(x, sets[i][0], sets[i][1], N, G, tok=tok or None, split=split or None, out=out)
+run(); torch.cuda.synchronize()
+lib.qb200_debug_set_trace(tr.data_ptr())
+st = torch.cuda.Stream(); g = torch.cuda.CUDAGraph()
+with torch.cuda.stream(st):
+    with torch.cuda.graph(g, stream=st):
+        run()
+lib.qb200_debug_set_trace(None)
+for _ in range(3): g.replay()
+torch.cuda.synchronize()
+tr.zero_(); torch.cuda.synchronize()
+a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+a.record(); g.replay(); b.record(); torch.cuda.synchronize()
+t = tr.cpu()
+n = int(t[TL]); rows = t[TL + 8: TL + 8 + 4 * n].view(n, 4)
+t0 = int(rows[0, 0])
+print(f"M={M} K={K} N={N} plan={ops.plan(M, K, N, G)} forced=({tok},{split}) launches={n} graph_us_per_gemm={a.elapsed_time(b) * 1e3 / NL:.2f}")
+print("seq | start  post_wait  accum  exit   (ns, rel. to first start) | start-to-start  exit-to-next-postwait")
+for i in range(n):
+    r = [int(v) - t0 if int(v) else None for v in rows[i]]
+    d = (int(rows[i, 0]) - int(rows[i - 1, 0])) if i else 0
+    e = (int(rows[i, 1]) - int(rows[i - 1, 3])) if i and int(rows[i, 1]) and int(rows[i - 1, 3]) else None
+    if i < 12 or i >= n - 3: print(i, "|", *r, "|", d, e)

@@ -13,11 +13,11 @@ sz = torch.full((K // G * N,), 0x64082000, device=dev, dtype=torch.int32)
 x = torch.randn(M, K, device=dev).half()
 for _ in range(3): ops.gemm(x, wq, sz, N, G, tok=tok, split=split)
 torch.cuda.synchronize()
-tr = torch.zeros(6 * 256 * 4, dtype=torch.int64, device=dev)
+tr = torch.zeros(6 * 256 * 4 + 8 + 256 * 4, dtype=torch.int64, device=dev)
 lib = _lib.load(); lib.qb200_debug_set_trace(tr.data_ptr())
 ops.gemm(x, wq, sz, N, G, tok=tok, split=split); torch.cuda.synchronize()
 lib.qb200_debug_set_trace(None)
-t = tr.cpu().view(6, 256, 4)
+t = tr.cpu()[:6 * 256 * 4].view(6, 256, 4)
 t0 = int(t[3, 0, 0])
 rel = lambda v: int(v) - t0 if int(v) else None
 nkb = (K // 64 // split + 1) // 2
@@ -26,4 +26,4 @@ print("setup_done", rel(t[3, 0, 1]), "accum_seen", rel(t[3, 0, 2]), "cluster_bar
 print("it | prod: x_slot_free issued | mma: loop_top tfull_seen ready mmas_issued committed | deq: w_landed lds+consts tmem_free st_half st_issued st_done handed_off")
 for it in range(min(nkb, 40)):
     print(it, "|", rel(t[0, it, 0]), rel(t[0, it, 1]), "|", rel(t[5, it, 0]), rel(t[5, it, 1]), rel(t[1, it, 0]), rel(t[1, it, 1]), rel(t[1, it, 2]), "|",
-          rel(t[2, it, 0]), rel(t[4, it, 0]), rel(t[4, it, 1]), rel(t[4, it, 2]), rel(t[2, it, 1]), rel(t[4, it, 3]), rel(t[2, it, 2]))
+          rel(t[2, it, 0]), rel(t[4, it, 0]), rel(t[4, it, 1]), rel(t[4, it, 2]), rel(t[2, it, 1]), rel(t[4, it, 3]), rel(t[2, it, 2]), "| handoff q0 q1 q3:", rel(t[5, it, 1]), rel(t[5, it, 2]), rel(t[5, it, 3]))
