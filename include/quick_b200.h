@@ -75,8 +75,21 @@ int qb200_gemm_w4a16(const void* A_fp16, const uint32_t* wq, const uint32_t* sz,
 int qb200_gemm_w4a16_cfg(const void* A_fp16, const uint32_t* wq, const uint32_t* sz, const void* bias_fp16_or_null,
                          void* C_fp16, int M, int K, int N, int G, int tok, int split, void* stream);
 
+/* Same with launch flags; tok = 0 / split = 0 let the planner choose.
+ * QB200_GEMM_INDEPENDENT: the caller guarantees that A, C and the weights of this launch are neither written
+ * nor (for C) read by any earlier kernel of the stream that may still be running — e.g. sibling projections
+ * of the same activations, or a batch of unrelated GEMMs.  The launch then overlaps its predecessor completely
+ * under programmatic dependent launch instead of waiting for it before the first activation load; stream order
+ * of COMPLETION is preserved (a later ordinary launch still sees all results).  The reference has no such
+ * mode: its launches serialise on the legacy default stream (gemm_cuda_quick.cu:1491-1513). */
+#define QB200_GEMM_INDEPENDENT 1u
+int qb200_gemm_w4a16_ex(const void* A_fp16, const uint32_t* wq, const uint32_t* sz, const void* bias_fp16_or_null,
+                        void* C_fp16, int M, int K, int N, int G, int tok, int split, unsigned flags, void* stream);
+
 /* Reports the configuration qb200_gemm_w4a16 would pick. */
 int qb200_gemm_plan(int M, int K, int N, int G, int split_k_hint, int* tok, int* split, int* ctas);
+/* Same for a given set of launch flags (the independent plan never splits K). */
+int qb200_gemm_plan_ex(int M, int K, int N, int G, int split_k_hint, unsigned flags, int* tok, int* split, int* ctas);
 
 /* Stateless drop-in for gemm_forward_cuda_quick on QUICK-layout operands: relayout into the caller's
  * workspace (>= qb200_wq_bytes + qb200_sz_bytes, 256-B aligned) then GEMM.  The torch binding
@@ -99,6 +112,11 @@ int qb200_linear_create(qb200_linear** out, const int32_t* qweight_host, const i
                         int K, int N, int G, int max_m, int device);
 /* y[M][N] = x[M][K] · W (+ bias): copies x from host, runs the kernel, copies y back, synchronises. */
 int qb200_linear_forward_host(qb200_linear* h, const void* x_fp16_host, void* y_fp16_host, int M);
+/* Asynchronous form: enqueues H2D(x) -> GEMM -> D2H(y) on the handle's private stream and returns; x_host and
+ * y_host must be pinned and stay valid until qb200_linear_synchronize(h).  Calls on different handles overlap
+ * (PCIe in both directions and the GEMMs run concurrently); calls on one handle run in order. */
+int qb200_linear_forward_host_async(qb200_linear* h, const void* x_fp16_host, void* y_fp16_host, int M);
+int qb200_linear_synchronize(qb200_linear* h);
 /* Device-pointer forward on the handle's weights (async on `stream`). */
 int qb200_linear_forward(qb200_linear* h, const void* x_fp16_dev, void* y_fp16_dev, int M, void* stream);
 void qb200_linear_destroy(qb200_linear* h);

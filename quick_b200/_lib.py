@@ -14,8 +14,9 @@ LIB_PATH = os.environ.get("QB200_LIB") or os.path.join(_PKG, "libquick_b200.so")
 SYMBOLS = [
     "qb200_version", "qb200_last_error", "qb200_wq_bytes", "qb200_sz_bytes", "qb200_check_shape",
     "qb200_relayout_from_quick", "qb200_pack_quick", "qb200_dequantize", "qb200_gemm_w4a16",
-    "qb200_gemm_w4a16_cfg", "qb200_gemm_plan", "qb200_gemm_forward_quick", "qb200_gemm_w4a16_simt",
-    "qb200_linear_create", "qb200_linear_forward_host", "qb200_linear_forward", "qb200_linear_destroy",
+    "qb200_gemm_w4a16_cfg", "qb200_gemm_w4a16_ex", "qb200_gemm_plan", "qb200_gemm_plan_ex", "qb200_gemm_forward_quick", "qb200_gemm_w4a16_simt",
+    "qb200_linear_create", "qb200_linear_forward_host", "qb200_linear_forward_host_async", "qb200_linear_synchronize",
+    "qb200_linear_forward", "qb200_linear_destroy",
     "qb200_launch_count", "qb200_debug_set_trace", "qb200_debug_set_variant",
 ]
 
@@ -50,11 +51,15 @@ def load() -> C.CDLL:
     lib.qb200_dequantize.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     lib.qb200_gemm_w4a16.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.qb200_gemm_w4a16_cfg.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    lib.qb200_gemm_w4a16_ex.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, C.c_uint, vp]
     lib.qb200_gemm_plan.argtypes = [i32, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    lib.qb200_gemm_plan_ex.argtypes = [i32, i32, i32, i32, i32, C.c_uint, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.qb200_gemm_forward_quick.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, sz, vp]
     lib.qb200_gemm_w4a16_simt.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.qb200_linear_create.argtypes = [C.POINTER(vp), vp, vp, vp, vp, i32, i32, i32, i32, i32]
     lib.qb200_linear_forward_host.argtypes = [vp, vp, vp, i32]
+    lib.qb200_linear_forward_host_async.argtypes = [vp, vp, vp, i32]
+    lib.qb200_linear_synchronize.argtypes = [vp]
     lib.qb200_linear_forward.argtypes = [vp, vp, vp, i32, vp]
     lib.qb200_linear_destroy.argtypes = [vp]
     lib.qb200_linear_destroy.restype = None

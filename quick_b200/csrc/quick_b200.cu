@@ -320,9 +320,21 @@ int check_device() {
   return QB200_OK;
 }
 
-void plan(int M, int K, int N, int split_hint, int* tok_out, int* split_out) {
+// Two plans (measured on B200, tools/tune.py, K = N = 4096):
+//   ordered (default)  — the GEMM must finish as early as possible on its own: smallest tile that still covers M
+//                        without duplicating too much dequant work, then grow the split-K cluster until the grid
+//                        fills the 148 SMs.
+//   independent        — QB200_GEMM_INDEPENDENT launches overlap each other, so throughput wins: no split-K
+//                        (no exchange, one CTA per 128-channel tile streams the whole K) and the largest token
+//                        tile, which leaves the other SMs to the neighbouring GEMMs.
+void plan(int M, int K, int N, int split_hint, unsigned flags, int* tok_out, int* split_out) {
   (void)split_hint;   // the reference's split_k_iters is accepted but only a hint
-  const int tok = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
+  if (flags & QB200_GEMM_INDEPENDENT) {
+    *tok_out = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
+    *split_out = 1;
+    return;
+  }
+  const int tok = M <= 8 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 256 ? 128 : 256;
   const int tiles = (N / 128) * ((M + tok - 1) / tok);
   const int KB = K / 64;
   const int sms = device_sm_count();
@@ -408,10 +420,14 @@ int qb200_dequantize(const uint32_t* wq, const uint32_t* sz, int K, int N, int G
 }
 
 int qb200_gemm_plan(int M, int K, int N, int G, int split_k_hint, int* tok, int* split, int* ctas) {
+  return qb200_gemm_plan_ex(M, K, N, G, split_k_hint, 0u, tok, split, ctas);
+}
+
+int qb200_gemm_plan_ex(int M, int K, int N, int G, int split_k_hint, unsigned flags, int* tok, int* split, int* ctas) {
   int rc = qb200_check_shape(M, K, N, G);
   if (rc) return rc;
   int t, s;
-  plan(M, K, N, split_k_hint, &t, &s);
+  plan(M, K, N, split_k_hint, flags, &t, &s);
   if (tok) *tok = t;
   if (split) *split = s;
   if (ctas) *ctas = (N / 128) * ((M + t - 1) / t) * s;
@@ -420,11 +436,23 @@ int qb200_gemm_plan(int M, int K, int N, int G, int split_k_hint, int* tok, int*
 
 int qb200_gemm_w4a16_cfg(const void* A, const uint32_t* wq, const uint32_t* sz, const void* bias, void* C, int M, int K,
                          int N, int G, int tok, int split, void* stream) {
+  return qb200_gemm_w4a16_ex(A, wq, sz, bias, C, M, K, N, G, tok, split, 0u, stream);
+}
+
+int qb200_gemm_w4a16_ex(const void* A, const uint32_t* wq, const uint32_t* sz, const void* bias, void* C, int M, int K,
+                        int N, int G, int tok, int split, unsigned flags, void* stream) {
   int rc = qb200_check_shape(M, K, N, G);
   if (rc) return rc;
   if (M == 0) return QB200_OK;
   rc = check_device();
   if (rc) return rc;
+  if (flags & ~QB200_GEMM_INDEPENDENT) return fail(QB200_EINVAL, "unknown flags 0x%x", flags);
+  if (tok == 0 || split == 0) {
+    int t, s;
+    plan(M, K, N, 0, flags, &t, &s);
+    if (tok == 0) tok = t;
+    if (split == 0) split = s;
+  }
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(wq) & 15))
     return fail(QB200_EINVAL, "A and wq must be 16-byte aligned");
   const int KB = K / 64;
@@ -447,6 +475,7 @@ int qb200_gemm_w4a16_cfg(const void* A, const uint32_t* wq, const uint32_t* sz, 
   args.N = N;
   args.G = G;
   args.kb_per_split = kbps;
+  args.flags = flags;
   args.trace = g_trace;
   cudaStream_t st = as_stream(stream);
   switch (tok) {
@@ -464,7 +493,7 @@ int qb200_gemm_w4a16(const void* A, const uint32_t* wq, const uint32_t* sz, cons
   int rc = qb200_check_shape(M, K, N, G);
   if (rc) return rc;
   int tok, split;
-  plan(M, K, N, split_k_hint, &tok, &split);
+  plan(M, K, N, split_k_hint, 0u, &tok, &split);
   return qb200_gemm_w4a16_cfg(A, wq, sz, bias, C, M, K, N, G, tok, split, stream);
 }
 
@@ -559,6 +588,25 @@ int qb200_linear_forward_host(qb200_linear* h, const void* x_host, void* y_host,
   int rc = qb200_gemm_w4a16(h->x, h->wq, h->sz, h->bias, h->y, M, h->K, h->N, h->G, 0, h->stream);
   if (rc) return rc;
   QB_CUDA(cudaMemcpyAsync(y_host, h->y, static_cast<size_t>(M) * h->N * 2, cudaMemcpyDeviceToHost, h->stream));
+  QB_CUDA(cudaStreamSynchronize(h->stream));
+  return QB200_OK;
+}
+
+int qb200_linear_forward_host_async(qb200_linear* h, const void* x_host, void* y_host, int M) {
+  if (!h) return fail(QB200_EINVAL, "null handle");
+  if (M > h->max_m) return fail(QB200_EINVAL, "M=%d exceeds the handle's max_m=%d", M, h->max_m);
+  if (M == 0) return QB200_OK;
+  // Everything is ordered on the handle's own stream, so the staging buffers are reused safely by the next
+  // call on the same handle, while calls on OTHER handles (other streams) overlap their copies with this GEMM.
+  QB_CUDA(cudaMemcpyAsync(h->x, x_host, static_cast<size_t>(M) * h->K * 2, cudaMemcpyHostToDevice, h->stream));
+  int rc = qb200_gemm_w4a16(h->x, h->wq, h->sz, h->bias, h->y, M, h->K, h->N, h->G, 0, h->stream);
+  if (rc) return rc;
+  QB_CUDA(cudaMemcpyAsync(y_host, h->y, static_cast<size_t>(M) * h->N * 2, cudaMemcpyDeviceToHost, h->stream));
+  return QB200_OK;
+}
+
+int qb200_linear_synchronize(qb200_linear* h) {
+  if (!h) return fail(QB200_EINVAL, "null handle");
   QB_CUDA(cudaStreamSynchronize(h->stream));
   return QB200_OK;
 }

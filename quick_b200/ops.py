@@ -79,8 +79,10 @@ def dequantize(wq: torch.Tensor, sz: torch.Tensor, K: int, N: int, G: int) -> to
 
 
 def gemm(x: torch.Tensor, wq: torch.Tensor, sz: torch.Tensor, N: int, G: int, bias: torch.Tensor | None = None,
-         tok: int | None = None, split: int | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
-    """y[M,N] = x[M,K] · W (+bias) through the tcgen05 kernel. tok/split force a tile config."""
+         tok: int | None = None, split: int | None = None, out: torch.Tensor | None = None,
+         independent: bool = False) -> torch.Tensor:
+    """y[M,N] = x[M,K] · W (+bias) through the tcgen05 kernel. tok/split force a tile config;
+    independent=True passes QB200_GEMM_INDEPENDENT (see include/quick_b200.h)."""
     _require_cuda(x, wq, sz, bias)
     lib = _lib.load()
     assert x.dim() == 2 and x.dtype == torch.float16
@@ -89,13 +91,11 @@ def gemm(x: torch.Tensor, wq: torch.Tensor, sz: torch.Tensor, N: int, G: int, bi
     if out is None:
         out = torch.empty((M, N), dtype=torch.float16, device=x.device)
     with torch.cuda.device(x.device):
-        if tok is None and split is None:
+        if tok is None and split is None and not independent:
             rc = lib.qb200_gemm_w4a16(_ptr(x), _ptr(wq), _ptr(sz), _ptr(bias), _ptr(out), M, K, N, G, 0, _stream_ptr())
         else:
-            p_tok, p_split, p_ctas = C.c_int(), C.c_int(), C.c_int()
-            _lib.check(lib.qb200_gemm_plan(M, K, N, G, 0, C.byref(p_tok), C.byref(p_split), C.byref(p_ctas)))
-            rc = lib.qb200_gemm_w4a16_cfg(_ptr(x), _ptr(wq), _ptr(sz), _ptr(bias), _ptr(out), M, K, N, G,
-                                          tok or p_tok.value, split or p_split.value, _stream_ptr())
+            rc = lib.qb200_gemm_w4a16_ex(_ptr(x), _ptr(wq), _ptr(sz), _ptr(bias), _ptr(out), M, K, N, G,
+                                         tok or 0, split or 0, 1 if independent else 0, _stream_ptr())
     _lib.check(rc)
     return out
 
@@ -112,10 +112,10 @@ def gemm_simt(x: torch.Tensor, wq: torch.Tensor, sz: torch.Tensor, N: int, G: in
     return out
 
 
-def plan(M: int, K: int, N: int, G: int, split_hint: int = 0):
+def plan(M: int, K: int, N: int, G: int, split_hint: int = 0, independent: bool = False):
     lib = _lib.load()
     tok, split, ctas = C.c_int(), C.c_int(), C.c_int()
-    _lib.check(lib.qb200_gemm_plan(M, K, N, G, split_hint, C.byref(tok), C.byref(split), C.byref(ctas)))
+    _lib.check(lib.qb200_gemm_plan_ex(M, K, N, G, split_hint, 1 if independent else 0, C.byref(tok), C.byref(split), C.byref(ctas)))
     return tok.value, split.value, ctas.value
 
 
@@ -160,6 +160,17 @@ class HostLinear:
             y_host = torch.empty((M, self.N), dtype=torch.float16, pin_memory=True)
         _lib.check(self._lib.qb200_linear_forward_host(self._h, _ptr(x_host), _ptr(y_host), M))
         return y_host
+
+    def forward_host_async(self, x_host: torch.Tensor, y_host: torch.Tensor) -> torch.Tensor:
+        """Enqueue H2D -> GEMM -> D2H on the handle's stream; both buffers must be pinned and stay alive
+        until synchronize()."""
+        assert not x_host.is_cuda and x_host.dtype == torch.float16 and x_host.is_contiguous()
+        assert x_host.is_pinned() and y_host.is_pinned(), "asynchronous host calls need pinned buffers"
+        _lib.check(self._lib.qb200_linear_forward_host_async(self._h, _ptr(x_host), _ptr(y_host), x_host.shape[0]))
+        return y_host
+
+    def synchronize(self):
+        _lib.check(self._lib.qb200_linear_synchronize(self._h))
 
     def close(self):
         if getattr(self, "_h", None):

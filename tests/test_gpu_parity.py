@@ -223,6 +223,64 @@ def test_host_buffer_handle_end_to_end(ops):
     h.close()
 
 
+def test_host_buffer_handle_async_calls_overlap_and_match(ops):
+    """qb200_linear_forward_host_async on several handles (= several streams), one synchronize per handle:
+    every result must equal the synchronous call's."""
+    K, N, G = 512, 768, 128
+    cases = [make_gpu_case(ops, K, N, G, seed=100 + i) for i in range(3)]
+    hs = [ops.HostLinear(c[3], c[4], c[5], max_m=128) for c in cases]
+    xs = {M: torch.from_numpy(qo.make_activations(M, K, seed=M)).pin_memory() for M in (1, 17, 128)}
+    ys = {(M, i): torch.empty(M, N, dtype=torch.float16).pin_memory() for M in xs for i in range(3)}
+    for M, x in xs.items():
+        for i, h in enumerate(hs):
+            h.forward_host_async(x, ys[(M, i)])
+    for h in hs:
+        h.synchronize()
+    for M, x in xs.items():
+        for i, h in enumerate(hs):
+            assert torch.equal(ys[(M, i)], h.forward_host(x)), (M, i)
+            assert_close(ys[(M, i)].cuda(), x.cuda().double() @ cases[i][6].double(), f"async host handle M={M} #{i}")
+    with pytest.raises(AssertionError):
+        hs[0].forward_host_async(torch.zeros(1, K, dtype=torch.float16), ys[(1, 0)])   # unpinned x
+    for h in hs:
+        h.close()
+
+
+def test_independent_launches_overlap_but_complete_in_stream_order(ops):
+    """QB200_GEMM_INDEPENDENT: consecutive GEMMs (distinct weights and outputs) overlap under programmatic
+    dependent launch.  Results must be bit-identical to ordered launches of the same configuration, and an
+    ordinary kernel enqueued afterwards must see every result (completion stays transitive)."""
+    K = N = 4096
+    G = 128
+    sets = []
+    for i in range(8):
+        g = torch.Generator(device="cuda"); g.manual_seed(50 + i)
+        wq = torch.randint(-2 ** 31, 2 ** 31 - 1, (K * N // 8,), device="cuda", dtype=torch.int32, generator=g)
+        s = (torch.rand(K // G * N, device="cuda", generator=g) * 0.01 + 0.002).half().view(torch.int16).to(torch.int32) & 0xFFFF
+        z = torch.randint(0, 16, (K // G * N,), device="cuda", generator=g, dtype=torch.int32)
+        sets.append((wq, (s | ((0x6400 + z) << 16)).to(torch.int32)))
+    for M in (1, 16, 64, 128, 256, 300):
+        x = torch.randn(M, K, device="cuda").half()
+        tok, split, _ = ops.plan(M, K, N, G, independent=True)
+        assert split == 1
+        want = [ops.gemm(x, w, z_, N, G, tok=tok, split=split) for (w, z_) in sets]
+        torch.cuda.synchronize()
+        outs = [torch.zeros(M, N, device="cuda", dtype=torch.float16) for _ in sets]
+        for rep in range(20):
+            for o in outs:
+                o.zero_()
+            for (w, z_), o in zip(sets, outs):
+                ops.gemm(x, w, z_, N, G, out=o, independent=True)
+            total = torch.stack(outs).float().sum(0)        # ordinary kernel right behind the last GEMM
+            torch.cuda.synchronize()
+            for o, w_ in zip(outs, want):
+                assert torch.equal(o, w_), (M, rep)
+            assert torch.equal(total, torch.stack(want).float().sum(0)), (M, rep)
+        # and against the oracle definition for one of them
+        W16 = ops.dequantize(sets[0][0], sets[0][1], K, N, G)
+        assert_close(outs[0], x.double() @ W16.double(), f"independent M={M}")
+
+
 def test_full_size_properties(ops):
     """At BASELINE's full sizes: size-independent properties instead of a CPU oracle —
     linearity in A, row independence (ragged M == prefix of padded M), and agreement of every

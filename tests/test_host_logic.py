@@ -104,7 +104,12 @@ def test_gemm_plan_fills_the_machine(built):
     for M in (1, 8, 16, 64, 128, 256, 512, 4096):
         tok, split, ctas = ops.plan(M, 4096, 4096, 128)
         assert tok in (16, 32, 64, 128, 256) and split in (1, 2, 4, 8) and ctas >= 32
-        assert tok >= min(M, 256)
+        assert ctas == (4096 // 128) * -(-M // tok) * split
+        if M <= 512:
+            assert 100 <= ctas <= 148 + 148 // 4, "one ordered GEMM should fill the 148 SMs"
+        # independent launches overlap each other: never split K, largest token tile
+        itok, isplit, ictas = ops.plan(M, 4096, 4096, 128, independent=True)
+        assert isplit == 1 and itok >= min(M, 256) and ictas == (4096 // 128) * -(-M // itok)
 
 
 def test_quick_kernels_module_surface(built):

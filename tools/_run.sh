@@ -1,6 +1,11 @@
 mkdir -p gpurun_out
-export QB200_LIB=$PWD/quick_b200/libquick_b200_trace.so
-for cfg in "1 4096 4096" "1 4096 4096 16 8" "16 4096 4096 32 4" "256 4096 4096" "256 4096 4096 128 2" "512 4096 4096"; do timeout 120 python tools/timeline.py $cfg; done > gpurun_out/timeline_v4.log 2>&1
-QB200_NO_PDL=1 timeout 120 python tools/timeline.py 1 4096 4096 >> gpurun_out/timeline_v4.log 2>&1
-for cfg in "16 4 1 4096 4096 0" "64 1 256 4096 4096 0" "128 1 512 4096 4096 0"; do timeout 120 python tools/trace.py $cfg; done > gpurun_out/trace_v4b.log 2>&1
-cat gpurun_out/timeline_v4.log
+( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu.log
+( time timeout 400 python bench.py --steps 20 --warmup 3 ) > gpurun_out/bench_v5.json 2> gpurun_out/bench_v5.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_v5.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_v5.json').read().strip().splitlines()[0])
+print(d['value'], d['e2e'], d['roofline'])
+for r in d['sweep']: print(r)
+print(d['independent']['value'])
+for r in d['independent']['sweep']: print(r)
+PY

@@ -50,7 +50,7 @@ for var in variants:
         if bias is not None:
             ref = ref + bias.float()
         out = ops.gemm(A, wq, sz, N, G, bias=bias, tok=tok or None, split=split or None)
-        out2 = ops.gemm(A, wq, sz, N, G, bias=bias, tok=tok or None, split=split or None)
+        out2 = ops.gemm(A, wq, sz, N, G, bias=bias, tok=tok or None, split=split or None, independent=True)
         torch.cuda.synchronize()
         rms = ref.pow(2).mean().sqrt().item()
         ok = bool(torch.allclose(out.float(), ref, rtol=1e-2, atol=1e-2 * rms)) and bool(torch.equal(out, out2))

@@ -9,6 +9,7 @@ M, K, N = map(int, sys.argv[1:4]); G = 128
 tok = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 split = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 NL = 40
+INDEP = os.environ.get("INDEP", "0") == "1"
 dev = "cuda"
 lib = _lib.load()
 sets = []
@@ -17,11 +18,11 @@ for i in range(NL):
     sz = torch.full((K // G * N,), 0x64082000, device=dev, dtype=torch.int32)
     sets.append((wq, sz))
 x = torch.randn(M, K, device=dev).half()
-out = torch.empty(M, N, device=dev, dtype=torch.float16)
+outs = [torch.empty(M, N, device=dev, dtype=torch.float16) for _ in range(NL)]
 TL = 6 * 256 * 4
 tr = torch.zeros(TL + 8 + 256 * 4, dtype=torch.int64, device=dev)
 def run():
-    for i in range(NL): ops.gemm(x, sets[i][0], sets[i][1], N, G, tok=tok or None, split=split or None, out=out)
+    for i in range(NL): ops.gemm(x, sets[i][0], sets[i][1], N, G, tok=tok or None, split=split or None, out=outs[i], independent=INDEP)
 run(); torch.cuda.synchronize()
 lib.qb200_debug_set_trace(tr.data_ptr())
 st = torch.cuda.Stream(); g = torch.cuda.CUDAGraph()
@@ -37,7 +38,7 @@ a.record(); g.replay(); b.record(); torch.cuda.synchronize()
 t = tr.cpu()
 n = int(t[TL]); rows = t[TL + 8: TL + 8 + 4 * n].view(n, 4)
 t0 = int(rows[0, 0])
-print(f"M={M} K={K} N={N} plan={ops.plan(M, K, N, G)} forced=({tok},{split}) launches={n} graph_us_per_gemm={a.elapsed_time(b) * 1e3 / NL:.2f}")
+print(f"indep={INDEP} M={M} K={K} N={N} plan={ops.plan(M, K, N, G)} forced=({tok},{split}) launches={n} graph_us_per_gemm={a.elapsed_time(b) * 1e3 / NL:.2f}")
 print("seq | start  post_wait  accum  exit   (ns, rel. to first start) | start-to-start  exit-to-next-postwait")
 for i in range(n):
     r = [int(v) - t0 if int(v) else None for v in rows[i]]

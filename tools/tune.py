@@ -15,6 +15,7 @@ VARIANTS = [int(v) for v in os.environ.get("VARS", "0").split(",")]   # needs QB
 SPLITS = [int(v) for v in os.environ.get("SPLITS", "1,2,4,8").split(",")]
 K = int(os.environ.get("K", 4096)); N = int(os.environ.get("N", 4096)); G = 128
 NSETS = 40
+INDEP = os.environ.get("INDEP", "0") == "1"   # QB200_GEMM_INDEPENDENT launches (distinct output buffer per weight set)
 Ms = [int(m) for m in os.environ.get("MS", "1,8,16,32,64,128,256,512,1024,2048").split(",")]
 
 
@@ -53,7 +54,7 @@ def time_graph(fn_i, n_launch, reps=20):
 res = []
 for M in Ms:
     x = torch.randn(M, K, device=dev).half()
-    out = torch.empty(M, N, device=dev, dtype=torch.float16)
+    outs = [torch.empty(M, N, device=dev, dtype=torch.float16) for _ in range(NSETS)]
     flop = 2.0 * M * K * N
     alg_bytes = K * N / 2 + (K // G) * N * 2.5 + M * K * 2 + M * N * 2
     toks = [t for t in (16, 32, 64, 128, 256) if t >= min(M, 256) or t == 256]
@@ -64,12 +65,12 @@ for M in Ms:
         for split in SPLITS:
             if split == 8 and tok > 32: continue
             try:
-                cold = time_graph(lambda i: ops.gemm(x, sets[i % NSETS][0], sets[i % NSETS][1], N, G, tok=tok, split=split, out=out), NSETS)
-                hot = time_graph(lambda i: ops.gemm(x, sets[0][0], sets[0][1], N, G, tok=tok, split=split, out=out), NSETS)
+                cold = time_graph(lambda i: ops.gemm(x, sets[i % NSETS][0], sets[i % NSETS][1], N, G, tok=tok, split=split, out=outs[i % NSETS], independent=INDEP), NSETS)
+                hot = time_graph(lambda i: ops.gemm(x, sets[0][0], sets[0][1], N, G, tok=tok, split=split, out=outs[i % NSETS], independent=INDEP), NSETS)
             except Exception as e:
                 print("ERR", M, tok, split, str(e)[:200], flush=True); continue
             rec = {"M": M, "var": var, "tok": tok, "split": split, "cold_us": cold * 1e6, "hot_us": hot * 1e6,
-                   "cold_TOPS": flop / cold / 1e12, "cold_GBs": alg_bytes / cold / 1e9, "auto": [tok, split] == list(auto[:2])}
+                   "cold_TOPS": flop / cold / 1e12, "cold_GBs": alg_bytes / cold / 1e9, "indep": INDEP, "auto": [tok, split] == list(auto[:2])}
             res.append(rec)
             print(json.dumps({k: (round(v, 2) if isinstance(v, float) else v) for k, v in rec.items()}), flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
