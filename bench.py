@@ -275,8 +275,8 @@ def run_mine(args):
         roof = {"bound": "tensor", "achieved": dom["TOPS"], "peak": pk["tf_sustained"], "unit": "TFLOP/s"}
     else:
         roof = {"bound": "hbm", "achieved": dom["GBs"], "peak": pk["hbm_gbs"], "unit": "GB/s"}
-    # DRAM bytes per launch of the same kernel from `ncu --set full` (profiles/r1_ncu_full_M*.json): no re-reads
-    ncu_traffic = {1: 8952320, 256: 11044864, 512: 13141248}
+    # DRAM bytes per launch of the same kernel from `ncu --set full` (profiles/r1b_ncu_full.json): no re-reads
+    ncu_traffic = {1: 8948480, 256: 11040512, 512: 13138432}
     roof.update({"frac": round(roof["achieved"] / roof["peak"], 4), "traffic": ncu_traffic.get(dom["M"]), "kernel": "w4a16_umma_kernel",
                  "algorithmic_bytes": int(alg_bytes(dom["M"])),
                  "at_M": dom["M"], "share_of_step": round(dom["us"] / sum(r["us"] for r in sweep), 3),

@@ -476,6 +476,7 @@ int qb200_gemm_w4a16_ex(const void* A, const uint32_t* wq, const uint32_t* sz, c
   args.G = G;
   args.kb_per_split = kbps;
   args.flags = flags;
+  args.launch_id = static_cast<unsigned>(g_launches.load(std::memory_order_relaxed));
   args.trace = g_trace;
   cudaStream_t st = as_stream(stream);
   switch (tok) {

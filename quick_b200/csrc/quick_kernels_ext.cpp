@@ -139,8 +139,10 @@ std::vector<torch::Tensor> prepack_quick(torch::Tensor kernel, torch::Tensor sca
 }
 
 // GEMM on already-converted weights, bias fused into the epilogue.
+// independent = true passes QB200_GEMM_INDEPENDENT (include/quick_b200.h): the caller guarantees that the operands
+// are not produced by a kernel that may still be running (e.g. sibling projections of one activation tensor).
 torch::Tensor gemm_forward_b200(torch::Tensor in_feats, torch::Tensor wq, torch::Tensor sz,
-                                c10::optional<torch::Tensor> bias, int64_t N, int64_t G) {
+                                c10::optional<torch::Tensor> bias, int64_t N, int64_t G, bool independent) {
   TORCH_CHECK(in_feats.dim() == 2 && in_feats.is_cuda(), "in_feats must be a 2-D CUDA tensor (there is no CPU path)");
   const at::cuda::OptionalCUDAGuard device_guard(device_of(in_feats));
   torch::Tensor x = in_feats.contiguous();
@@ -157,16 +159,19 @@ torch::Tensor gemm_forward_b200(torch::Tensor in_feats, torch::Tensor wq, torch:
   }
   torch::Tensor out = torch::empty({M, N}, x.options());
   auto stream = at::cuda::getCurrentCUDAStream();
-  check(qb200_gemm_w4a16(x.data_ptr<at::Half>(), reinterpret_cast<const uint32_t*>(wq.data_ptr<int>()),
-                         reinterpret_cast<const uint32_t*>(sz.data_ptr<int>()), bias_ptr, out.data_ptr<at::Half>(), M, K,
-                         static_cast<int>(N), static_cast<int>(G), 0, stream.stream()));
+  check(qb200_gemm_w4a16_ex(x.data_ptr<at::Half>(), reinterpret_cast<const uint32_t*>(wq.data_ptr<int>()),
+                            reinterpret_cast<const uint32_t*>(sz.data_ptr<int>()), bias_ptr, out.data_ptr<at::Half>(), M, K,
+                            static_cast<int>(N), static_cast<int>(G), /*tok*/ 0, /*split*/ 0,
+                            independent ? QB200_GEMM_INDEPENDENT : 0u, stream.stream()));
   return out;
 }
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_forward_cuda_quick", &gemm_forward_cuda_quick, "QUICK AWQ GEMM kernel.");
   m.def("prepack_quick", &prepack_quick, "QUICK layout -> B200 layout (wq, sz)");
-  m.def("gemm_forward_b200", &gemm_forward_b200, "W4A16 GEMM on B200-layout weights (bias fused)");
+  m.def("gemm_forward_b200", &gemm_forward_b200, "W4A16 GEMM on B200-layout weights (bias fused)", pybind11::arg("in_feats"),
+        pybind11::arg("wq"), pybind11::arg("sz"), pybind11::arg("bias"), pybind11::arg("N"), pybind11::arg("G"),
+        pybind11::arg("independent") = false);
   m.def("cache_stats", [] {
     std::lock_guard<std::mutex> lock(g_mu);
     return std::vector<int64_t>{static_cast<int64_t>(g_cache.size()), static_cast<int64_t>(g_hits), static_cast<int64_t>(g_misses)};

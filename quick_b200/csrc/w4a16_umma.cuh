@@ -383,8 +383,12 @@ struct GemmArgs {
   int M, K, N, G;
   int kb_per_split;   // k64 blocks per cluster rank
   unsigned flags;     // QB200_GEMM_* (include/quick_b200.h)
+  unsigned launch_id; // host-side launch counter (QB200_TRACE builds: row of the cross-launch timeline)
   long long* trace;   // debug (QB200_TRACE builds only): clock64 stamps of CTA (0,0,0)
 };
+#ifndef QB_TQ
+#define QB_TQ 2   // TMEM lane quadrant whose dequant warps are traced in detail
+#endif
 #ifdef QB200_TRACE
 #define QB_TRACE(slot, it, k)                                                                  \
   do {                                                                                         \
@@ -404,9 +408,21 @@ __device__ __forceinline__ long long qb_globaltimer() {
     if (args.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)                  \
       args.trace[QB_TL_BASE + 8 + (qb_tl_seq & 255) * 4 + (k)] = qb_globaltimer();                       \
   } while (0)
+// every CTA of the launch: min/max over the grid of (0) CTA start, (1) griddepcontrol.wait returned, (2) CTA exit
+#define QB_TLALL_BASE (QB_TL_BASE + 8 + 256 * 4)
+#define QB_TLALL(k)                                                                                     \
+  do {                                                                                                  \
+    if (args.trace != nullptr) {                                                                        \
+      const unsigned long long t_ = static_cast<unsigned long long>(qb_globaltimer());                  \
+      unsigned long long* row_ = reinterpret_cast<unsigned long long*>(args.trace) + QB_TLALL_BASE + (args.launch_id & 255) * 8; \
+      atomicMin(row_ + 2 * (k), t_);                                                                    \
+      atomicMax(row_ + 2 * (k) + 1, t_);                                                                \
+    }                                                                                                   \
+  } while (0)
 #else
 #define QB_TRACE(slot, it, k) do { } while (0)
 #define QB_TL(k) do { } while (0)
+#define QB_TLALL(k) do { } while (0)
 #endif
 
 // Programmatic dependent launch (PDL): the next kernel in the stream starts while this one is running; it
@@ -572,11 +588,21 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
   }
 #endif
   if (threadIdx.x == 0) QB_TRACE(3, 0, 0);
+  if (threadIdx.x == 32) QB_TLALL(0);
   if (warp == kProducerWarp) {
-    // The whole W ring is requested right here — before the TMEM allocation, before griddepcontrol.wait — so
-    // under PDL the HBM stream of this GEMM overlaps the previous kernel.
+    // One elected producer lane owns the whole setup: tensor-map prefetch first (the descriptor fetch is a cold
+    // miss whose latency should overlap everything else), all barriers, then the whole W ring — requested before
+    // the TMEM allocation and before griddepcontrol.wait, so under PDL the HBM stream of this GEMM overlaps the
+    // previous kernel.
     if (elect_one()) {
+      prefetch_tmap(&tmap_x);
       for (int i = 0; i < DS; ++i) mbar_init(bar_wfull + 8 * i, 1);
+      for (int i = 0; i < D2; ++i) {
+        mbar_init(bar_ready + 8 * i, 5);   // 4 dequant warps + the producer's expect_tx arrival
+        mbar_init(bar_free + 8 * i, 1);
+      }
+      mbar_init(bar_accum, 1);
+      mbar_init(bar_recv, 1);   // one expect_tx arrive by the owner; the senders' copies complete the bytes
       fence_barrier_init();
       fence_proxy_async();
       const int npre = min(nst, DS);
@@ -586,16 +612,6 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
     __syncwarp();
   } else if (warp == kMmaWarp) {
     tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);   // blocks while a co-resident CTA of the previous kernel holds the columns
-  } else if (threadIdx.x == 0) {
-    for (int i = 0; i < D2; ++i) {
-      mbar_init(bar_ready + 8 * i, 5);   // 4 dequant warps + the producer's expect_tx arrival
-      mbar_init(bar_free + 8 * i, 1);
-    }
-    mbar_init(bar_accum, 1);
-    mbar_init(bar_recv, 1);   // one expect_tx arrive by the owner; the senders' copies complete the bytes
-    fence_barrier_init();
-    fence_proxy_async();
-    prefetch_tmap(&tmap_x);
   }
   tc_fence_before();
   __syncthreads();
@@ -614,6 +630,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
     // before its MMAs could even start.  So the single "MMAs of stage j-D2 complete" barrier releases both.
     if (!independent) pdl_wait_prior_grid();   // the activations come from the previous kernel
     if (lane == 0) QB_TL(1);
+    if (lane == 0) QB_TLALL(1);
     int x = 0;
     uint32_t xph = 0;
     for (int j = 0; j < nst; ++j) {
@@ -702,7 +719,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
     for (int it = wg; it < nst; it += NWG) {
       const int nsub = min(kSubPerStage, nkb - it * kSubPerStage);
       mbar_wait(bar_wfull + 8 * s, sph, 3, it);
-      if (lane == 0 && quad == 2) QB_TRACE(2, it, 0);
+      if (lane == 0 && quad == QB_TQ) QB_TRACE(2, it, 0);
       const uint32_t wbase = smem_w + s * kWStage + ch * 16;
       uint4 w[4];
       w[0] = lds128(wbase);
@@ -718,13 +735,13 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
       rem += 2 * kSubPerStage * NWG;
       while (rem >= g32) { rem -= g32; ++grp; }
       if (it + NWG < nst) load_sz();
-      if (lane == 0 && quad == 2) QB_TRACE(4, it, 0);
+      if (lane == 0 && quad == QB_TQ) QB_TRACE(4, it, 0);
       // operand slot t is free once the MMAs of stage it - D2 have completed
       if (it >= D2) {
         mbar_wait(bar_free + 8 * t, ((it / D2) & 1) ^ 1, 4, it);
         tc_fence_after();
       }
-      if (lane == 0 && quad == 2) QB_TRACE(4, it, 1);
+      if (lane == 0 && quad == QB_TQ) QB_TRACE(4, it, 1);
       const uint32_t a_tmem = tmem_base + lane_addr + Cfg::kACol0 + t * kASlotCols;
 #pragma unroll
       for (int sub = 0; sub < kSubPerStage; ++sub) {
@@ -740,17 +757,17 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
           dequant_word(w[2 * sub + 1].w, gc[2 * sub + 1], r + 28);
           tmem_st16(a_tmem + sub * 32, r);
           tmem_st16(a_tmem + sub * 32 + 16, r + 16);
-          if (sub == 0 && lane == 0 && quad == 2) QB_TRACE(4, it, 2);
+          if (sub == 0 && lane == 0 && quad == QB_TQ) QB_TRACE(4, it, 2);
         }
       }
-      if (lane == 0 && quad == 2) QB_TRACE(2, it, 1);
+      if (lane == 0 && quad == QB_TQ) QB_TRACE(2, it, 1);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0 && quad == 2) QB_TRACE(4, it, 3);
+      if (lane == 0 && quad == QB_TQ) QB_TRACE(4, it, 3);
       if (lane == 0) mbar_arrive(bar_ready + 8 * t);
-      if (lane == 0 && quad == 2) QB_TRACE(2, it, 2);
-      if (lane == 0 && quad != 2) QB_TRACE(5, it, 1 + (quad == 3 ? 2 : quad));   // hand-off of the other quadrants
+      if (lane == 0 && quad == QB_TQ) QB_TRACE(2, it, 2);
+      if (lane == 0 && quad != QB_TQ) QB_TRACE(5, it, 1 + (quad < QB_TQ ? quad : quad - 1));   // hand-off of the other quadrants
       s += NWG;
       if (s >= DS) { s -= DS; sph ^= 1; }
       t = (t + NWG) % D2;
@@ -989,6 +1006,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
   if (independent) pdl_wait_prior_grid();
   if (threadIdx.x == kMmaWarp * 32) QB_TRACE(3, 1, 0);
   if (threadIdx.x == kMmaWarp * 32) QB_TL(3);
+  if (threadIdx.x == kMmaWarp * 32) QB_TLALL(2);
 }
 
 }  // namespace qb200

@@ -49,6 +49,8 @@ for var in variants:
         bias = torch.randn(N, device="cuda").half() if (M % 2 == 1) else None
         if bias is not None:
             ref = ref + bias.float()
+        if not tok:
+            tok, split, _ = ops.plan(M, K, N, G)
         out = ops.gemm(A, wq, sz, N, G, bias=bias, tok=tok or None, split=split or None)
         out2 = ops.gemm(A, wq, sz, N, G, bias=bias, tok=tok or None, split=split or None, independent=True)
         torch.cuda.synchronize()

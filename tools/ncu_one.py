@@ -5,6 +5,7 @@ sys.path.insert(0, ROOT)
 import torch
 from quick_b200 import ops
 M = int(sys.argv[1]); K = N = 4096; G = 128
+INDEP = len(sys.argv) > 2 and sys.argv[2] == "indep"   # QB200_GEMM_INDEPENDENT plan (ncu serialises the launches anyway)
 dev = "cuda"
 sets = []
 for i in range(20):   # 20 x 9 MB > L2: cold weights
@@ -15,6 +16,6 @@ for i in range(20):   # 20 x 9 MB > L2: cold weights
     sets.append((wq, (s | ((0x6400 + z) << 16)).to(torch.int32)))
 x = torch.randn(M, K, device=dev).half()
 for i in range(20):
-    ops.gemm(x, sets[i][0], sets[i][1], N, G)
+    ops.gemm(x, sets[i][0], sets[i][1], N, G, independent=INDEP)
 torch.cuda.synchronize()
-print("done", M, ops.plan(M, K, N, G))
+print("done", M, ops.plan(M, K, N, G, independent=INDEP))

@@ -20,7 +20,11 @@ for i in range(NL):
 x = torch.randn(M, K, device=dev).half()
 outs = [torch.empty(M, N, device=dev, dtype=torch.float16) for _ in range(NL)]
 TL = 6 * 256 * 4
-tr = torch.zeros(TL + 8 + 256 * 4, dtype=torch.int64, device=dev)
+TLALL = TL + 8 + 256 * 4
+tr = torch.zeros(TLALL + 256 * 8, dtype=torch.int64, device=dev)
+def reset():
+    tr.zero_()
+    tr[TLALL:].view(256, 8)[:, 0::2] = 2 ** 62     # atomicMin slots
 def run():
     for i in range(NL): ops.gemm(x, sets[i][0], sets[i][1], N, G, tok=tok or None, split=split or None, out=outs[i], independent=INDEP)
 run(); torch.cuda.synchronize()
@@ -32,7 +36,7 @@ with torch.cuda.stream(st):
 lib.qb200_debug_set_trace(None)
 for _ in range(3): g.replay()
 torch.cuda.synchronize()
-tr.zero_(); torch.cuda.synchronize()
+reset(); torch.cuda.synchronize()
 a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
 a.record(); g.replay(); b.record(); torch.cuda.synchronize()
 t = tr.cpu()
@@ -45,3 +49,14 @@ for i in range(n):
     d = (int(rows[i, 0]) - int(rows[i - 1, 0])) if i else 0
     e = (int(rows[i, 1]) - int(rows[i - 1, 3])) if i and int(rows[i, 1]) and int(rows[i - 1, 3]) else None
     if i < 12 or i >= n - 3: print(i, "|", *r, "|", d, e)
+# all-CTA view: rows indexed by the host launch counter (consecutive for the 40 launches of the graph)
+allr = t[TLALL:].view(256, 8)
+used = [i for i in range(256) if int(allr[i, 1]) > 0]
+used.sort(key=lambda i: int(allr[i, 0]))
+print("launch | CTA start min..max | wait-returned min..max | exit min..max  (ns rel.) | grid done -> next wait-returned(min)")
+prev_exit = None
+for j, i in enumerate(used):
+    r = [int(v) - t0 for v in allr[i, :6]]
+    gap = (int(allr[i, 2]) - prev_exit) if prev_exit is not None else None
+    if j < 12 or j >= len(used) - 2: print(j, "|", r[0], r[1], "|", r[2], r[3], "|", r[4], r[5], "|", gap)
+    prev_exit = int(allr[i, 5])

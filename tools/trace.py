@@ -13,7 +13,7 @@ sz = torch.full((K // G * N,), 0x64082000, device=dev, dtype=torch.int32)
 x = torch.randn(M, K, device=dev).half()
 for _ in range(3): ops.gemm(x, wq, sz, N, G, tok=tok, split=split)
 torch.cuda.synchronize()
-tr = torch.zeros(6 * 256 * 4 + 8 + 256 * 4, dtype=torch.int64, device=dev)
+tr = torch.zeros(6 * 256 * 4 + 8 + 256 * 4 + 256 * 8, dtype=torch.int64, device=dev)
 lib = _lib.load(); lib.qb200_debug_set_trace(tr.data_ptr())
 ops.gemm(x, wq, sz, N, G, tok=tok, split=split); torch.cuda.synchronize()
 lib.qb200_debug_set_trace(None)
