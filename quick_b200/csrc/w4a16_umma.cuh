@@ -310,31 +310,33 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int n) {
 // <= 256 TMEM columns, <= 113 KB shared memory): under programmatic dependent launch the next GEMM's CTAs sit
 // next to the running ones with their weights already in shared memory and TMEM.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSubPerStage = 2;                              // k64 blocks per stage
-constexpr int kWStage = kSubPerStage * kWStageBytes;         // 8192
-constexpr int kASlotCols = 32 * kSubPerStage;                // 64 TMEM columns = 128 k of fp16 pairs
-
-template <int NWG_, int DS_, int D2_>
+// SUB = k64 blocks per pipeline stage (2 -> 128 k, 3 -> 192 k, 4 -> 256 k).  The MMA issuer pays a fixed ≈650 cycles
+// per stage (mbarrier wait, commit, loop) whatever the stage holds, so tiles whose tensor work per 128 k is below
+// that (TOK <= 128) want longer stages; the price is shared memory (X stage = SUB x TOK x 128 B) and TMEM
+// (A slot = 32 x SUB columns).
+template <int NWG_, int DS_, int D2_, int SUB_ = 2>
 struct Rings {
-  static constexpr int NWG = NWG_, DS = DS_, D2 = D2_;
+  static constexpr int NWG = NWG_, DS = DS_, D2 = D2_, SUB = SUB_;
 };
 // VAR 0 = default, VAR 1 = alternative kept for A/B measurements (tools/tune.py, qb200_debug_set_variant)
 template <int TOK, int VAR> struct Variant;
 template <> struct Variant<16, 0> : Rings<3, 6, 3> {};
-template <> struct Variant<16, 1> : Rings<3, 6, 6> {};
+template <> struct Variant<16, 1> : Rings<3, 6, 3, 4> {};
 template <> struct Variant<32, 0> : Rings<3, 6, 3> {};
-template <> struct Variant<32, 1> : Rings<3, 6, 6> {};
+template <> struct Variant<32, 1> : Rings<3, 6, 3, 4> {};
 template <> struct Variant<64, 0> : Rings<3, 6, 3> {};
-template <> struct Variant<64, 1> : Rings<4, 8, 4> {};
+template <> struct Variant<64, 1> : Rings<3, 6, 3, 4> {};
 template <> struct Variant<128, 0> : Rings<3, 6, 3> {};
-template <> struct Variant<128, 1> : Rings<2, 4, 2> {};
+template <> struct Variant<128, 1> : Rings<3, 6, 4, 2> {};
 template <> struct Variant<256, 0> : Rings<2, 4, 3> {};
 template <> struct Variant<256, 1> : Rings<2, 4, 2> {};
 
 template <int TOK, int VAR = 0>
 struct TileCfg {
   using R = Variant<TOK, VAR>;
-  static constexpr int kNumWG = R::NWG, kDS = R::DS, kD2 = R::D2;
+  static constexpr int kNumWG = R::NWG, kDS = R::DS, kD2 = R::D2, kSub = R::SUB;
+  static constexpr int kWStage = kSub * kWStageBytes;         // packed nibbles of one stage (SUB x 4 KB)
+  static constexpr int kASlotCols = 32 * kSub;                // TMEM columns of one A slot (fp16 pairs)
   // A W slot is always served by the same warpgroup (DS % NWG == 0), so its warps observe every phase of
   // "their" TMA barriers in order (mbarrier parity waits are only valid one phase ahead, and TMA completions
   // arrive out of order).  The "free" barriers complete in MMA order, so D2 >= NWG suffices for them.
@@ -344,7 +346,7 @@ struct TileCfg {
   static constexpr int kMmaWarp = 4 * kNumWG + 1;
   static constexpr int kNumThreads = (4 * kNumWG + 2) * 32;
   static constexpr int kXPanelBytes = TOK * 128;                      // one k64 panel
-  static constexpr int kXStageBytes = kSubPerStage * kXPanelBytes;
+  static constexpr int kXStageBytes = kSub * kXPanelBytes;
   static constexpr int kACol0 = TOK < 32 ? 32 : TOK;
   static constexpr int kColsNeeded = kACol0 + kASlotCols * kD2;
   static constexpr int kTmemCols = kColsNeeded <= 32 ? 32 : kColsNeeded <= 64 ? 64 : kColsNeeded <= 128 ? 128
@@ -358,7 +360,7 @@ struct TileCfg {
   static constexpr bool kAsyncExchange = TOK <= 64;
   // dedicated receive buffer (not aliasing the pipeline stages): senders need no "owner finished its main
   // loop" barrier
-  static constexpr bool kDedicatedRecv = TOK <= 64 || (TOK == 128 && kD2 >= 3);
+  static constexpr bool kDedicatedRecv = TOK <= 64 || (TOK == 128 && kD2 >= 3 && kPipeBytes <= 184 * 1024);
   __host__ __device__ static constexpr int slice(int split) { return TOK / split; }
   // bytes per exchanged element: fp32 when a thread owns <= 4 columns of a slice, packed fp16 otherwise
   __host__ __device__ static constexpr int elem_bytes(int split) { return (kAsyncExchange && slice(split) / 2 <= 4) ? 4 : 2; }
@@ -369,6 +371,7 @@ struct TileCfg {
     return kPipeBytes + kBarBytes + (kDedicatedRecv ? recv_bytes(split) + 16 : 0) + 1024;   // + 1024-B alignment slack
   }
   // two CTAs per SM: 233472 B per SM, 1 KB reserved per CTA
+  static_assert(smem_bytes(4) <= 232448, "shared-memory budget (227 KB per CTA)");
   static constexpr bool kCoResident = kTmemCols <= 256 && 2 * (smem_bytes(4) + 1024) <= 233472;
   static constexpr int kMinBlocks = kCoResident ? 2 : 1;
 };
@@ -514,6 +517,7 @@ __global__ void __launch_bounds__(TileCfg<TOK, VAR>::kNumThreads, TileCfg<TOK, V
 w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs args) {
   using Cfg = TileCfg<TOK, VAR>;
   constexpr int NWG = Cfg::kNumWG, DS = Cfg::kDS, D2 = Cfg::kD2;
+  constexpr int kSubPerStage = Cfg::kSub, kWStage = Cfg::kWStage, kASlotCols = Cfg::kASlotCols;
   constexpr int kProducerWarp = Cfg::kProducerWarp;
   constexpr int kMmaWarp = Cfg::kMmaWarp;
   constexpr int SLICE = TOK / SPLIT;          // token columns owned by one cluster rank
@@ -640,9 +644,10 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
         const int nsub = min(kSubPerStage, nkb - j * kSubPerStage);
         const uint32_t bar = bar_ready + 8 * x;
         mbar_arrive_expect_tx(bar, nsub * Cfg::kXPanelBytes);
-        tma_load_2d(smem_x + x * Cfg::kXStageBytes, &tmap_x, bar, (kb0 + j * kSubPerStage) * kBK, mt * TOK);
-        if (nsub > 1)
-          tma_load_2d(smem_x + x * Cfg::kXStageBytes + Cfg::kXPanelBytes, &tmap_x, bar, (kb0 + j * kSubPerStage + 1) * kBK, mt * TOK);
+#pragma unroll
+        for (int p = 0; p < kSubPerStage; ++p)
+          if (p < nsub)
+            tma_load_2d(smem_x + x * Cfg::kXStageBytes + p * Cfg::kXPanelBytes, &tmap_x, bar, (kb0 + j * kSubPerStage + p) * kBK, mt * TOK);
         const int jw = j + (DS - D2);
         if (j >= D2 && jw < nst) issue_w(jw);
         QB_TRACE(0, j, 1);
@@ -665,14 +670,15 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
         const uint64_t bdesc = make_smem_desc_sw128(smem_x + t * Cfg::kXStageBytes);
         const uint32_t a_tmem = tmem_base + Cfg::kACol0 + t * kASlotCols;
 #pragma unroll
-        for (int j = 0; j < kBK / 16; ++j) {
-          // +32 B (= 2 in 16-B units) of start address per k16 step inside the 128-B swizzle row
-          umma_f16_ts(tmem_base, a_tmem + j * 8, bdesc + 2 * j, idesc, (it | j) != 0 ? 1u : 0u);
-        }
-        if (nsub > 1) {
-          const uint64_t bdesc1 = bdesc + (Cfg::kXPanelBytes >> 4);
+        for (int p = 0; p < kSubPerStage; ++p) {
+          if (p < nsub) {
+            const uint64_t bdesc_p = bdesc + static_cast<uint64_t>(p * (Cfg::kXPanelBytes >> 4));
 #pragma unroll
-          for (int j = 0; j < kBK / 16; ++j) umma_f16_ts(tmem_base, a_tmem + 32 + j * 8, bdesc1 + 2 * j, idesc, 1u);
+            for (int j = 0; j < kBK / 16; ++j) {
+              // +32 B (= 2 in 16-B units) of start address per k16 step inside the 128-B swizzle row
+              umma_f16_ts(tmem_base, a_tmem + p * 32 + j * 8, bdesc_p + 2 * j, idesc, (it | p | j) != 0 ? 1u : 0u);
+            }
+          }
         }
         QB_TRACE(1, it, 1);
         umma_commit(bar_free + 8 * t);     // X stage, W stage and TMEM A slot free once these MMAs have completed
@@ -704,11 +710,11 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
     // group index of each of the 4 k32 blocks of the next stage, advanced incrementally (no divisions in the loop)
     int kq = (kb0 + wg * kSubPerStage) * 2;
     int grp = kq / g32, rem = kq % g32;
-    uint32_t szw[4];
+    uint32_t szw[2 * kSubPerStage];
     auto load_sz = [&]() {
       int g = grp, r = rem;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < 2 * kSubPerStage; ++q) {
         szw[q] = __ldg(szp + static_cast<size_t>(min(g, NG - 1)) * kChan);
         if (++r >= g32) { r = 0; ++g; }
       }
@@ -721,16 +727,17 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
       mbar_wait(bar_wfull + 8 * s, sph, 3, it);
       if (lane == 0 && quad == QB_TQ) QB_TRACE(2, it, 0);
       const uint32_t wbase = smem_w + s * kWStage + ch * 16;
-      uint4 w[4];
-      w[0] = lds128(wbase);
-      w[1] = lds128(wbase + 2048);
-      if (nsub > 1) {
-        w[2] = lds128(wbase + 4096);
-        w[3] = lds128(wbase + 6144);
-      }
-      GroupConsts gc[4];
+      uint4 w[2 * kSubPerStage];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) gc[q] = make_group_consts(szw[q]);
+      for (int p = 0; p < kSubPerStage; ++p) {
+        if (p < nsub) {
+          w[2 * p] = lds128(wbase + p * 4096);
+          w[2 * p + 1] = lds128(wbase + p * 4096 + 2048);
+        }
+      }
+      GroupConsts gc[2 * kSubPerStage];
+#pragma unroll
+      for (int q = 0; q < 2 * kSubPerStage; ++q) gc[q] = make_group_consts(szw[q]);
       // advance NWG stages (4 k32 blocks each) and prefetch the next scale/zero words
       rem += 2 * kSubPerStage * NWG;
       while (rem >= g32) { rem -= g32; ++grp; }

@@ -1,18 +1,5 @@
 mkdir -p gpurun_out
-( time timeout 900 python -m pytest tests -m gpu -x -q -rs ) > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/pytest_gpu.log
-( time timeout 400 python bench.py --impl reference --steps 10 --warmup 3 ) > gpurun_out/bench_ref_final.json 2> gpurun_out/bench_ref_final.err; echo "bench ref rc=$?"
-( time timeout 400 python bench.py --steps 20 --warmup 3 ) > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_final.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:umma -c 900 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1; echo "ncu list rc=$?"
-for m in 1 256 512; do timeout 300 ncu --set full --clock-control none --import-source on -k regex:umma -s 10 -c 2 -f -o gpurun_out/full_M$m python tools/ncu_one.py $m > gpurun_out/ncu_full_M$m.log 2>&1; echo "ncu full M=$m rc=$?"; done
-for m in 1 256; do timeout 300 ncu --set full --clock-control none --import-source on -k regex:umma -s 10 -c 2 -f -o gpurun_out/full_indep_M$m python tools/ncu_one.py $m indep > gpurun_out/ncu_full_indep_M$m.log 2>&1; echo "ncu full indep M=$m rc=$?"; done
-timeout 600 python tools/bench_model.py --model llama-2-7b --out gpurun_out/model_llama2_7b.json > gpurun_out/model_llama2_7b.log 2>&1; echo "model rc=$?"; tail -4 gpurun_out/model_llama2_7b.log | cut -c1-300
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/bench_final.json').read().strip().splitlines()[0])
-print(d['value'], d['e2e']['value'], d['roofline'], d['clocks'])
-for r in d['sweep']: print(r)
-print(d['independent']['value'])
-for r in d['independent']['sweep']: print(r)
-r=json.loads(open('gpurun_out/bench_ref_final.json').read().strip().splitlines()[0])
-print('REF', r['value'], r['e2e'], [ (x['M'], x['us']) for x in r.get('sweep', [])])
-PY
+export QB200_LIB=$PWD/quick_b200/libquick_b200_dev.so
+VARS=0,1 timeout 300 python tools/check_fast.py > gpurun_out/check13.log 2>&1; rc=$?; echo "check rc=$rc"; tail -1 gpurun_out/check13.log; grep '"ok": false' gpurun_out/check13.log | head -5; grep -i "error\|Traceback" gpurun_out/check13.log | head -5
+[ $rc -ne 0 ] && exit 1
+MS=1,16,64,128,256,512 VARS=0,1 SPLITS=1,2,4 OUT=tune_v13.json timeout 400 python tools/tune.py > gpurun_out/tune_v13.log 2>&1; echo "tune rc=$?"
