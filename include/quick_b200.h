@@ -61,6 +61,16 @@ int qb200_relayout_from_quick(const int32_t* qweight, const int32_t* qzeros, con
 int qb200_pack_quick(const uint8_t* q, const uint8_t* z, const void* s_fp16, int K, int N, int G,
                      int32_t* qweight, int32_t* qzeros, void* scales_fp16, void* stream);
 
+/* AWQ "GEMM" checkpoint layout (what public AWQ checkpoints ship: qweight int32 [K][N/8], qzeros int32 [K/G][N/8],
+ * nibble i of a word = column 8c + {0,2,4,6,1,3,5,7}[i]; scales fp16 [K/G][N]) -> QUICK-layout tensors, bit-exact.
+ * The reference has no such converter: its GEMM packer is quick/awq/modules/linear/gemm.py:108-143 and the inverse
+ * nibble order is in quick/awq/utils/packing_utils.py:4-39; QUICK models had to be re-quantized from fp16. */
+int qb200_awq_gemm_to_quick(const int32_t* gemm_qweight, const int32_t* gemm_qzeros, const void* gemm_scales_fp16,
+                            int K, int N, int G, int32_t* qweight, int32_t* qzeros, void* scales_fp16, void* stream);
+/* Same source format straight into the B200 layout the kernel streams (skips the QUICK intermediate). */
+int qb200_relayout_from_awq_gemm(const int32_t* gemm_qweight, const int32_t* gemm_qzeros, const void* gemm_scales_fp16,
+                                 int K, int N, int G, uint32_t* wq, uint32_t* sz, void* stream);
+
 /* B200 layout -> W16[K][N] fp16 = fp16((q - z)) * s, one rounding (gemm_cuda_quick.cu:52-60). */
 int qb200_dequantize(const uint32_t* wq, const uint32_t* sz, int K, int N, int G, void* w16_fp16, void* stream);
 

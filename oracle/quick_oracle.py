@@ -307,6 +307,35 @@ def shard_columns(qweight, qzeros, scales, rank: int, world: int):
 # Synthetic inputs
 # ---------------------------------------------------------------------------
 
+AWQ_ORDER = (0, 2, 4, 6, 1, 3, 5, 7)
+
+
+def unpack_awq_gemm(qweight: np.ndarray, qzeros: np.ndarray):
+    """AWQ "GEMM" layout -> logical (q [K,N], z [K/G,N]) uint8.  Restates the reference's
+    unpack_awq (quick/awq/utils/packing_utils.py:8-25: nibble i of word c -> unpacked column 8c+i),
+    reverse_awq_order (:28-39: column 8c+j of the result = unpacked column 8c+AWQ_REVERSE_ORDER[j]) and
+    the 4-bit mask (:84-85); equivalently nibble i holds logical column 8c + AWQ_ORDER[i], the packer's
+    order_map (quick/awq/modules/linear/gemm.py:117-123)."""
+    def unpack(t):
+        w = t.astype(np.int64) & 0xFFFFFFFF
+        out = np.empty(t.shape + (8,), dtype=np.uint8)
+        for i in range(8):
+            out[..., AWQ_ORDER[i]] = (w >> (4 * i)) & 0xF
+        return out.reshape(t.shape[0], -1)
+    return unpack(qweight), unpack(qzeros)
+
+
+def pack_awq_gemm(q: np.ndarray, z: np.ndarray):
+    """Logical -> AWQ "GEMM" layout (reference packer loops, gemm.py:108-143, in closed form)."""
+    def pack(t):
+        t8 = (t.astype(np.int64) & 0xF).reshape(t.shape[0], -1, 8)
+        w = np.zeros(t8.shape[:2], dtype=np.int64)
+        for i in range(8):
+            w |= t8[:, :, AWQ_ORDER[i]] << (4 * i)
+        return w.astype(np.uint32).view(np.int32)
+    return pack(q), pack(z)
+
+
 def make_case(K: int, N: int, G: int, seed: int = 1234):
     rng = np.random.default_rng(seed)
     q = rng.integers(0, 16, size=(K, N), dtype=np.int32)

@@ -13,7 +13,8 @@ LIB_PATH = os.environ.get("QB200_LIB") or os.path.join(_PKG, "libquick_b200.so")
 # every symbol include/quick_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "qb200_version", "qb200_last_error", "qb200_wq_bytes", "qb200_sz_bytes", "qb200_check_shape",
-    "qb200_relayout_from_quick", "qb200_pack_quick", "qb200_dequantize", "qb200_gemm_w4a16",
+    "qb200_relayout_from_quick", "qb200_pack_quick", "qb200_awq_gemm_to_quick", "qb200_relayout_from_awq_gemm",
+    "qb200_dequantize", "qb200_gemm_w4a16",
     "qb200_gemm_w4a16_cfg", "qb200_gemm_w4a16_ex", "qb200_gemm_plan", "qb200_gemm_plan_ex", "qb200_gemm_forward_quick", "qb200_gemm_w4a16_simt",
     "qb200_linear_create", "qb200_linear_forward_host", "qb200_linear_forward_host_async", "qb200_linear_synchronize",
     "qb200_linear_forward", "qb200_linear_destroy",
@@ -48,6 +49,8 @@ def load() -> C.CDLL:
     lib.qb200_check_shape.argtypes = [i32, i32, i32, i32]
     lib.qb200_relayout_from_quick.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp]
     lib.qb200_pack_quick.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.qb200_awq_gemm_to_quick.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.qb200_relayout_from_awq_gemm.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp]
     lib.qb200_dequantize.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     lib.qb200_gemm_w4a16.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.qb200_gemm_w4a16_cfg.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]

@@ -84,6 +84,28 @@ class WQLinear_QUICK(nn.Module):
             awq_linear.bias = linear.bias.clone().half()
         return awq_linear
 
+    @classmethod
+    def from_awq_gemm(cls, qweight, qzeros, scales, bias=None, w_bit=4, group_size=None, k_split_1=2, k_split_2=8):
+        """Build the module from AWQ "GEMM" checkpoint tensors (the layout of WQLinear_GEMM, reference
+        quick/awq/modules/linear/gemm.py:37-58: qweight int32 [K, N/8], qzeros int32 [K/G, N/8], scales fp16 [K/G, N])
+        without re-quantizing: a bit-exact nibble permutation into the QUICK layout (GPU kernel on CUDA tensors,
+        quick_b200.layout on CPU tensors).  The reference can only produce QUICK modules from fp16 weights."""
+        K, N = int(qweight.shape[0]), int(qweight.shape[1]) * 8
+        G = K // int(scales.shape[0])
+        if group_size not in (None, -1, G):
+            raise ValueError(f"group_size={group_size} does not match the tensors (K/G rows of scales -> G={G})")
+        m = cls(w_bit, G, K, N, bias is not None, qweight.device, k_split_1, k_split_2)
+        if qweight.is_cuda:
+            from .... import ops
+            qw, qz, sc = ops.awq_gemm_to_quick(qweight, qzeros, scales)
+        else:
+            from ....layout import awq_gemm_to_quick
+            qw, qz, sc = awq_gemm_to_quick(qweight, qzeros, scales)
+        m.qweight, m.qzeros, m.scales = qw, qz, sc
+        if bias is not None:
+            m.bias = bias.clone().half()
+        return m
+
     def _prepacked(self):
         key = tuple((t.data_ptr(), 0 if t.is_inference() else t._version) for t in (self.qweight, self.qzeros, self.scales))
         if self._b200 is None or self._b200_key != key:

@@ -146,6 +146,86 @@ __global__ void pack_sz_kernel(const uint8_t* __restrict__ z, const __half* __re
   qzeros[idx] = zw | (zw << 16);
 }
 
+// ---- AWQ "GEMM" checkpoint layout (the format public AWQ checkpoints ship in) ----
+// qweight int32 [K][N/8], qzeros int32 [K/G][N/8]: nibble i of word (row, c) is column 8c + ORDER[i],
+// ORDER = {0,2,4,6,1,3,5,7} (reference packer quick/awq/modules/linear/gemm.py:108-143, inverse in
+// quick/awq/utils/packing_utils.py:4-39); scales fp16 [K/G][N].
+__device__ __forceinline__ uint32_t awq_gemm_nibble(const uint32_t* __restrict__ packed, int row, int n, int N) {
+  const int inv = ((n & 1) << 2) | ((n & 7) >> 1);   // position of column (n % 8) inside the word: inverse of ORDER
+  return (__ldg(packed + static_cast<size_t>(row) * (N >> 3) + (n >> 3)) >> (4 * inv)) & 0xFu;
+}
+
+// AWQ-GEMM -> QUICK layout: one thread per QUICK qweight word / per zero word (same closed form as pack_*_kernel).
+__global__ void gemm_to_quick_qweight_kernel(const uint32_t* __restrict__ gq, uint32_t* __restrict__ qweight, int K, int N) {
+  const size_t f = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (f >= static_cast<size_t>(K) * N / 8) return;
+  const int kt = static_cast<int>(f / (4 * static_cast<size_t>(N)));
+  const int r = static_cast<int>(f % (4 * static_cast<size_t>(N)));
+  const int r4 = r / N, c = r % N, bx = c >> 7, w = c & 127;
+  const int lane = 16 * (r4 & 1) + (w >> 3), ty = r4 >> 1, ks = (w & 7) >> 2, chk = w & 3;
+  const int k0 = 32 * kt + 16 * ks + 2 * (lane & 3);
+  const int c0 = 128 * bx + 64 * ty + 16 * chk + (lane >> 2);
+  uint32_t out = 0;
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const int dk = ((p >> 2) & 1) + 8 * (p & 1);
+    const int dc = 8 * ((p >> 1) & 1);
+    out |= awq_gemm_nibble(gq, k0 + dk, c0 + dc, N) << (4 * p);
+  }
+  qweight[f] = out;
+}
+__global__ void gemm_to_quick_sz_kernel(const uint32_t* __restrict__ gz, const __half* __restrict__ gs,
+                                        uint32_t* __restrict__ qzeros, __half* __restrict__ scales, int NG, int N) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<size_t>(NG) * (N / 4)) return;
+  const int g = static_cast<int>(idx / (N / 4));
+  const int xw = static_cast<int>(idx % (N / 4));
+  const int nb = N >> 7;
+  uint32_t zw = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int x = 4 * xw + i;
+    const int ty = x / (N >> 1), lh = (x / (N >> 2)) & 1, bx = (x >> 5) % nb, j4 = (x & 31) >> 3, m = x & 7;
+    const int n = 128 * bx + 64 * ty + 16 * (m >> 1) + 8 * (m & 1) + 4 * lh + j4;
+    zw |= awq_gemm_nibble(gz, g, n, N) << (4 * i);
+    const __half sv = gs[static_cast<size_t>(g) * N + n];
+    scales[static_cast<size_t>(g) * 2 * N + 2 * x] = sv;
+    scales[static_cast<size_t>(g) * 2 * N + 2 * x + 1] = sv;
+  }
+  qzeros[idx] = zw | (zw << 16);
+}
+
+// AWQ-GEMM -> B200 layout directly (what the kernel streams): one thread per B200 word / per (group, channel).
+__global__ void gemm_to_b200_wq_kernel(const uint32_t* __restrict__ gq, uint32_t* __restrict__ wq, int K, int N) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<size_t>(K) * N / 8) return;
+  const int KB = K / 64;
+  const int j = idx & 3, c = (idx >> 2) & 127, h = (idx >> 9) & 1;
+  const size_t blk = idx >> 10;
+  const int kb = static_cast<int>(blk % KB), nt = static_cast<int>(blk / KB);
+  const int n = nt * 128 + c;
+  const int kbase = kb * 64 + h * 32 + j * 8;
+  uint32_t out = 0;
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const int i = (p < 4) ? 2 * p : 2 * (p - 4) + 1;   // nibble order k0,k2,k4,k6,k1,k3,k5,k7
+    out |= awq_gemm_nibble(gq, kbase + i, n, N) << (4 * p);
+  }
+  wq[idx] = out;
+}
+__global__ void gemm_to_b200_sz_kernel(const uint32_t* __restrict__ gz, const __half* __restrict__ gs,
+                                       uint32_t* __restrict__ sz, int NG, int N) {
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<size_t>(NG) * N) return;
+  const int c = idx & 127;
+  const size_t blk = idx >> 7;
+  const int g = static_cast<int>(blk % NG), nt = static_cast<int>(blk / NG);
+  const int n = nt * 128 + c;
+  const uint32_t z = awq_gemm_nibble(gz, g, n, N);
+  const uint32_t sbits = __half_as_ushort(__ldg(gs + static_cast<size_t>(g) * N + n));
+  sz[idx] = sbits | ((0x6400u + z) << 16);
+}
+
 // B200 layout -> W16[K][N]
 __global__ void dequant_kernel(const uint32_t* __restrict__ wq, const uint32_t* __restrict__ sz, __half* __restrict__ W,
                                int K, int N, int G) {
@@ -404,6 +484,38 @@ int qb200_pack_quick(const uint8_t* q, const uint8_t* z, const void* s, int K, i
   pack_sz_kernel<<<static_cast<unsigned>((nz + 255) / 256), 256, 0, as_stream(stream)>>>(
       z, reinterpret_cast<const __half*>(s), reinterpret_cast<uint32_t*>(qzeros), reinterpret_cast<__half*>(scales), K / G, N);
   g_launches.fetch_add(2, std::memory_order_relaxed);
+  QB_CUDA(cudaGetLastError());
+  return QB200_OK;
+}
+
+int qb200_awq_gemm_to_quick(const int32_t* gemm_qweight, const int32_t* gemm_qzeros, const void* gemm_scales, int K, int N,
+                            int G, int32_t* qweight, int32_t* qzeros, void* scales, void* stream) {
+  int rc = qb200_check_shape(1, K, N, G);
+  if (rc) return rc;
+  const size_t words = static_cast<size_t>(K) * N / 8;
+  gemm_to_quick_qweight_kernel<<<static_cast<unsigned>((words + 255) / 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint32_t*>(gemm_qweight), reinterpret_cast<uint32_t*>(qweight), K, N);
+  const size_t nz = static_cast<size_t>(K / G) * (N / 4);
+  gemm_to_quick_sz_kernel<<<static_cast<unsigned>((nz + 255) / 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint32_t*>(gemm_qzeros), reinterpret_cast<const __half*>(gemm_scales),
+      reinterpret_cast<uint32_t*>(qzeros), reinterpret_cast<__half*>(scales), K / G, N);
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  QB_CUDA(cudaGetLastError());
+  return QB200_OK;
+}
+
+int qb200_relayout_from_awq_gemm(const int32_t* gemm_qweight, const int32_t* gemm_qzeros, const void* gemm_scales, int K,
+                                 int N, int G, uint32_t* wq, uint32_t* sz, void* stream) {
+  int rc = qb200_check_shape(1, K, N, G);
+  if (rc) return rc;
+  const size_t words = static_cast<size_t>(K) * N / 8;
+  gemm_to_b200_wq_kernel<<<static_cast<unsigned>((words + 255) / 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint32_t*>(gemm_qweight), wq, K, N);
+  const size_t nsz = static_cast<size_t>(K / G) * N;
+  gemm_to_b200_sz_kernel<<<static_cast<unsigned>((nsz + 255) / 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const uint32_t*>(gemm_qzeros), reinterpret_cast<const __half*>(gemm_scales), sz, K / G, N);
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  g_skip_pdl_once.store(1, std::memory_order_relaxed);   // wq/sz are being written: the next GEMM launches fully serialised
   QB_CUDA(cudaGetLastError());
   return QB200_OK;
 }

@@ -93,6 +93,41 @@ def unpack_quick(qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tens
     return q, z, s
 
 
+AWQ_ORDER = (0, 2, 4, 6, 1, 3, 5, 7)   # nibble i of an AWQ-GEMM word holds column 8c + AWQ_ORDER[i] (gemm.py:117-123)
+
+
+def unpack_awq_gemm(qweight: torch.Tensor, qzeros: torch.Tensor):
+    """AWQ "GEMM" checkpoint tensors (qweight int32 [K, N/8], qzeros int32 [K/G, N/8]) -> logical
+    (q int32 [K, N], z int32 [K/G, N]).  Same result as the reference's unpack_awq + reverse_awq_order + mask
+    (quick/awq/utils/packing_utils.py:8-39, :82-90)."""
+    def unpack(t):
+        w = t.to(torch.int64) & 0xFFFFFFFF
+        out = torch.empty((t.shape[0], t.shape[1], 8), dtype=torch.int32, device=t.device)
+        for i in range(8):
+            out[:, :, AWQ_ORDER[i]] = ((w >> (4 * i)) & 0xF).to(torch.int32)
+        return out.reshape(t.shape[0], -1)
+    return unpack(qweight), unpack(qzeros)
+
+
+def pack_awq_gemm(q: torch.Tensor, z: torch.Tensor):
+    """Logical (q [K, N], z [K/G, N]) -> AWQ-GEMM (qweight int32 [K, N/8], qzeros int32 [K/G, N/8]); the
+    reference packer's loops (quick/awq/modules/linear/gemm.py:108-143) in closed form."""
+    def pack(t):
+        t8 = (t.to(torch.int64) & 0xF).reshape(t.shape[0], -1, 8)
+        w = torch.zeros(t8.shape[:2], dtype=torch.int64, device=t.device)
+        for i in range(8):
+            w |= t8[:, :, AWQ_ORDER[i]] << (4 * i)
+        return _to_i32(w).contiguous()
+    return pack(q), pack(z)
+
+
+def awq_gemm_to_quick(qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor):
+    """AWQ-GEMM checkpoint tensors -> QUICK-layout (qweight, qzeros, scales); works on CPU or CUDA tensors
+    (the GPU kernels are quick_b200.ops.awq_gemm_to_quick / prepack_awq_gemm)."""
+    q, z = unpack_awq_gemm(qweight, qzeros)
+    return pack_quick(q, z, scales.to(torch.float16))
+
+
 def quick_cat(tensors, options: str) -> torch.Tensor:
     """N-concatenation of packed tensors (reference QUICK_cat, fused_utils.py:119-159), also for
     unequal widths (GQA k/v projections), which the reference rejects (fused_utils.py:139-142)."""

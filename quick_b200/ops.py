@@ -68,6 +68,45 @@ def pack_quick(q: torch.Tensor, z: torch.Tensor, s: torch.Tensor, G: int):
     return qweight, qzeros, scales
 
 
+def _awq_gemm_shapes(qweight, qzeros, scales):
+    """AWQ-GEMM tensors: qweight int32 [K, N/8], qzeros int32 [K/G, N/8], scales fp16 [K/G, N]."""
+    K, N = int(qweight.shape[0]), int(qweight.shape[1]) * 8
+    if tuple(scales.shape) != (scales.shape[0], N) or tuple(qzeros.shape) != (scales.shape[0], N // 8):
+        raise ValueError("not AWQ-GEMM shaped tensors: qweight [K, N/8], qzeros [K/G, N/8], scales [K/G, N]")
+    return K, N, K // int(scales.shape[0])
+
+
+def awq_gemm_to_quick(qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor):
+    """AWQ-GEMM checkpoint tensors -> QUICK-layout (qweight, qzeros, scales), bit-exact, on the GPU."""
+    _require_cuda(qweight, qzeros, scales)
+    lib = _lib.load()
+    K, N, G = _awq_gemm_shapes(qweight, qzeros, scales)
+    _lib.check(lib.qb200_check_shape(1, K, N, G))
+    qweight, qzeros, scales = qweight.contiguous(), qzeros.contiguous(), scales.to(torch.float16).contiguous()
+    out_qw = torch.empty((K // 4, N // 2), dtype=torch.int32, device=qweight.device)
+    out_qz = torch.empty((K // G, N // 4), dtype=torch.int32, device=qweight.device)
+    out_sc = torch.empty((K // G, 2 * N), dtype=torch.float16, device=qweight.device)
+    with torch.cuda.device(qweight.device):
+        _lib.check(lib.qb200_awq_gemm_to_quick(_ptr(qweight), _ptr(qzeros), _ptr(scales), K, N, G, _ptr(out_qw), _ptr(out_qz),
+                                               _ptr(out_sc), _stream_ptr()))
+    return out_qw, out_qz, out_sc
+
+
+def prepack_awq_gemm(qweight: torch.Tensor, qzeros: torch.Tensor, scales: torch.Tensor):
+    """AWQ-GEMM checkpoint tensors -> B200 layout.  Returns (wq int32 flat, sz int32 flat, K, N, G)."""
+    _require_cuda(qweight, qzeros, scales)
+    lib = _lib.load()
+    K, N, G = _awq_gemm_shapes(qweight, qzeros, scales)
+    _lib.check(lib.qb200_check_shape(1, K, N, G))
+    qweight, qzeros, scales = qweight.contiguous(), qzeros.contiguous(), scales.to(torch.float16).contiguous()
+    wq = torch.empty(lib.qb200_wq_bytes(K, N) // 4, dtype=torch.int32, device=qweight.device)
+    sz = torch.empty(lib.qb200_sz_bytes(K, N, G) // 4, dtype=torch.int32, device=qweight.device)
+    with torch.cuda.device(qweight.device):
+        _lib.check(lib.qb200_relayout_from_awq_gemm(_ptr(qweight), _ptr(qzeros), _ptr(scales), K, N, G, _ptr(wq), _ptr(sz),
+                                                    _stream_ptr()))
+    return wq, sz, K, N, G
+
+
 def dequantize(wq: torch.Tensor, sz: torch.Tensor, K: int, N: int, G: int) -> torch.Tensor:
     """B200 layout -> W16 [K, N] fp16 (bit-identical to the reference's in-register weights)."""
     _require_cuda(wq, sz)

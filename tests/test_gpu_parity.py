@@ -65,6 +65,30 @@ def test_gpu_packer_and_relayout_bitexact_vs_golden(ops, path):
     assert np.array_equal(W.view(np.uint16), qo.kernel_view_w16(d["qweight"], d["qzeros"], d["scales"], G).view(np.uint16))
 
 
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "awqgemm_*.npz"))), ids=os.path.basename)
+def test_awq_gemm_checkpoint_converters_bitexact_vs_golden(ops, path):
+    """AWQ-GEMM checkpoint tensors -> QUICK layout and -> B200 layout on the GPU, against the
+    integers the reference's own unpacker produced (tests/golden/make_golden_awq_gemm.py), then through the GEMM."""
+    from quick_b200.awq.modules.linear.quick import WQLinear_QUICK
+    d = np.load(path)
+    G = int(d["G"])
+    gq, gz, gs = (torch.from_numpy(d[k]).cuda() for k in ("qweight", "qzeros", "scales"))
+    qw, qz, sc = ops.awq_gemm_to_quick(gq, gz, gs)
+    want = qo.pack_quick(d["q"].astype(np.int32), d["z"].astype(np.int32), d["scales"])
+    assert np.array_equal(qw.cpu().numpy(), want[0]) and np.array_equal(qz.cpu().numpy(), want[1])
+    assert np.array_equal(sc.cpu().numpy().view(np.uint16), want[2].view(np.uint16))
+    wq, sz, K, N, G2 = ops.prepack_awq_gemm(gq, gz, gs)
+    assert G2 == G
+    wq2, sz2, *_ = ops.prepack(qw, qz, sc)
+    assert torch.equal(wq, wq2) and torch.equal(sz, sz2)
+    assert np.array_equal(ops.dequantize(wq, sz, K, N, G).cpu().numpy().view(np.uint16), d["W16"].view(np.uint16))
+    m = WQLinear_QUICK.from_awq_gemm(gq, gz, gs)
+    x = torch.from_numpy(qo.make_activations(33, K, seed=5)).cuda()
+    assert_close(m(x), x.double() @ torch.from_numpy(d["W16"]).cuda().double(), "from_awq_gemm forward")
+    with pytest.raises(ValueError):
+        ops.awq_gemm_to_quick(gq, gz[:, :-1], gs)
+
+
 def test_identity_probe_reads_w16_through_the_tensor_cores(ops):
     """A = rows of the identity: the GEMM output must equal W16 rows exactly (products by 1.0 and
     sums with exact zeros are exact) — the 'bit-exact integer unpack/index' pin through the hot path."""

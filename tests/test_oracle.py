@@ -128,3 +128,41 @@ def test_linearity_property():
     rhs = qo.gemm_exact(A1, W16) + qo.gemm_exact(A2, W16)
     # A1 + A2 is rounded to fp16 once, so compare against that rounding explicitly
     assert np.max(np.abs(lhs - rhs)) <= 2e-2 * np.sqrt(np.mean(rhs ** 2))
+
+
+# ---- AWQ "GEMM" checkpoint layout: golden vectors from the reference's packing_utils.py ----
+AWQ_FILES = sorted(glob.glob(os.path.join(GOLD, "awqgemm_*.npz")))
+
+
+def test_awq_gemm_golden_files_present():
+    assert len(AWQ_FILES) >= 3
+
+
+@pytest.mark.parametrize("path", AWQ_FILES, ids=os.path.basename)
+def test_awq_gemm_unpack_matches_reference_unpacker(path):
+    d = np.load(path)
+    q, z = qo.unpack_awq_gemm(d["qweight"], d["qzeros"])
+    assert np.array_equal(q, d["q"]) and np.array_equal(z, d["z"])
+    # the packer is its inverse on arbitrary 32-bit words (every nibble is used)
+    qw, qz = qo.pack_awq_gemm(q, z)
+    assert np.array_equal(qw, d["qweight"]) and np.array_equal(qz, d["qzeros"])
+    # and the oracle's W16 definition is the reference's CPU dequantize_gemm, bit for bit
+    W16 = qo.dequant_w16(q.astype(np.int32), z.astype(np.int32), d["scales"], int(d["G"]))
+    assert np.array_equal(_bits(W16), _bits(d["W16"]))
+
+
+@pytest.mark.parametrize("path", AWQ_FILES, ids=os.path.basename)
+def test_awq_gemm_to_quick_host_converter(path):
+    """quick_b200.layout.awq_gemm_to_quick (torch, CPU): QUICK tensors that unpack to the reference's integers."""
+    import torch
+    from quick_b200 import layout
+    d = np.load(path)
+    tq, tz, ts = (torch.from_numpy(d[k]) for k in ("qweight", "qzeros", "scales"))
+    q, z = layout.unpack_awq_gemm(tq, tz)
+    assert np.array_equal(q.numpy(), d["q"]) and np.array_equal(z.numpy(), d["z"])
+    pq, pz = layout.pack_awq_gemm(q, z)
+    assert torch.equal(pq, tq) and torch.equal(pz, tz)
+    qw, qz, sc = layout.awq_gemm_to_quick(tq, tz, ts)
+    want = qo.pack_quick(d["q"].astype(np.int32), d["z"].astype(np.int32), d["scales"])
+    assert np.array_equal(qw.numpy(), want[0]) and np.array_equal(qz.numpy(), want[1])
+    assert np.array_equal(_bits(sc.numpy()), _bits(want[2]))
