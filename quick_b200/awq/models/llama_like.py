@@ -69,10 +69,29 @@ class RMSNorm(nn.Module):
         return (v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + self.eps)).half() * self.weight
 
 
+def tp_world() -> int:
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def _gather_columns(local: torch.Tensor) -> torch.Tensor:
+    """Tensor-parallel linears (BASELINE config 5): every rank holds N/R output columns of each
+    weight and computes its (.., N/R) slab with the same kernel; ONE all-gather (NCCL over NVLink) rebuilds the
+    full width.  Same reassembly as quick_b200.parallel.ColumnParallelQuickLinear."""
+    import torch.distributed as dist
+    R = dist.get_world_size()
+    lead, n_local = local.shape[:-1], local.shape[-1]
+    flat = local.reshape(-1, n_local).contiguous()
+    gathered = torch.empty((R * flat.shape[0], n_local), dtype=flat.dtype, device=flat.device)
+    dist.all_gather_into_tensor(gathered, flat)
+    return gathered.view(R, flat.shape[0], n_local).permute(1, 0, 2).reshape(lead + (R * n_local,))
+
+
 def _linear(m: WQLinear_QUICK, x, ref_mod=None):
     """Route through the B200 kernel, or (baseline runs only) through the unmodified reference kernel."""
     if ref_mod is None:
-        return m(x)
+        y = m(x)
+        return _gather_columns(y) if getattr(m, "tp_sharded", False) else y
     split = m.k_split_1 if m.out_features > m.in_features else m.k_split_2      # quick.py:161-164
     out = ref_mod.gemm_forward_cuda_quick(x.reshape(-1, x.shape[-1]), m.qweight, m.scales, m.qzeros, split)
     return out.reshape(x.shape[:-1] + (m.out_features,))
@@ -85,10 +104,21 @@ class Block(nn.Module):
         hd, nh, nkv = cfg.head_dim, cfg.num_heads, cfg.num_kv_heads
         self.norm_1 = RMSNorm(cfg.hidden_size, cfg.rms_eps, dev)
         self.norm_2 = RMSNorm(cfg.hidden_size, cfg.rms_eps, dev)
-        self.qkv_proj = random_quick_linear(cfg.hidden_size, (nh + 2 * nkv) * hd, cfg.group_size, dev, gen)
-        self.o_proj = random_quick_linear(cfg.hidden_size, cfg.hidden_size, cfg.group_size, dev, gen)
-        self.gate_up_proj = random_quick_linear(cfg.hidden_size, 2 * cfg.intermediate_size, cfg.group_size, dev, gen)
-        self.down_proj = random_quick_linear(cfg.intermediate_size, cfg.hidden_size, cfg.group_size, dev, gen)
+        # Under torch.distributed every linear is column-parallel: this rank's module holds N/R output columns
+        # (random-init, so the shard is generated directly instead of slicing a full weight with
+        # layout.shard_columns) and _linear() all-gathers the slabs.  N/R must stay a multiple of 128.
+        R = tp_world()
+
+        def lin(in_f, out_f):
+            assert out_f % (128 * R) == 0, f"N={out_f} does not split into {R} shards of 128-column tiles"
+            m = random_quick_linear(in_f, out_f // R, cfg.group_size, dev, gen)
+            m.tp_sharded = R > 1
+            return m
+
+        self.qkv_proj = lin(cfg.hidden_size, (nh + 2 * nkv) * hd)
+        self.o_proj = lin(cfg.hidden_size, cfg.hidden_size)
+        self.gate_up_proj = lin(cfg.hidden_size, 2 * cfg.intermediate_size)
+        self.down_proj = lin(cfg.intermediate_size, cfg.hidden_size)
         self.register_buffer("cache_k", torch.zeros(batch, nkv, cfg.max_seq_len, hd, dtype=torch.float16, device=dev), persistent=False)
         self.register_buffer("cache_v", torch.zeros(batch, nkv, cfg.max_seq_len, hd, dtype=torch.float16, device=dev), persistent=False)
 
@@ -120,7 +150,9 @@ class LlamaLikeQuickModel(nn.Module):
     def __init__(self, cfg: LlamaLikeConfig, batch: int, dev="cuda", seed: int = 0):
         super().__init__()
         self.cfg, self.batch = cfg, batch
-        gen = torch.Generator(device=dev); gen.manual_seed(seed)
+        import torch.distributed as dist
+        rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        gen = torch.Generator(device=dev); gen.manual_seed(seed + 1000 * rank)   # every rank draws its own column slabs
         self.embed = nn.Embedding(cfg.vocab_size, cfg.hidden_size, device=dev, dtype=torch.float16)
         self.blocks = nn.ModuleList([Block(cfg, dev, gen, batch) for _ in range(cfg.num_layers)])
         self.norm = RMSNorm(cfg.hidden_size, cfg.rms_eps, dev)

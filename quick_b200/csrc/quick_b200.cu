@@ -420,8 +420,27 @@ void plan(int M, int K, int N, int split_hint, unsigned flags, int* tok_out, int
   const int sms = device_sm_count();
   const int max_split = tok <= 32 ? 8 : 4;
   int split = 1;
-  // grow the cluster while the grid still under-fills the machine and every rank keeps >= 4 k-blocks
-  while (split * 2 <= max_split && tiles * split * 2 <= sms + sms / 4 && KB / (split * 2) >= 4) split *= 2;
+  if (tok <= 64) {
+    // Co-resident tiles (two CTAs per SM): pick the split with the smallest modelled time
+    //   waves(tiles*split over 2*SMs slots) x (stages per CTA x ~600 cycles of MMA-issuer time + fixed cost),
+    // fixed = setup + epilogue (~2500 cycles) + ~600 per extra cluster rank for the split-K exchange.  Constants
+    // from the in-kernel traces (profiles/README.md); the model reproduces the measured optimum for N = 4096
+    // (split 4 ~ 8) and moves the wide projections of a 7B layer (qkv: 96 tiles, down: 86 stages) off split 1 / 4.
+    const int slots = 2 * sms;
+    long best = -1;
+    for (int s = 1; s <= max_split; s *= 2) {
+      if (s > 1 && KB / s < 4) break;                      // every rank keeps >= 2 stages
+      const int stages = ((KB + s - 1) / s + 1) / 2;
+      // a partly filled last wave costs less than a full one but more than its share: midpoint of both (x2)
+      const long ctas = static_cast<long>(tiles) * s;
+      const long waves2 = (ctas + slots - 1) / slots * slots + (ctas > slots ? ctas : slots);   // (ceil + continuous) * slots
+      const long cost = waves2 * (stages * 600L + 2500L + 600L * (s - 1));
+      if (best < 0 || cost < best) { best = cost; split = s; }
+    }
+  } else {
+    // one CTA per SM: grow the cluster while the grid still under-fills the machine and every rank keeps >= 4 k-blocks
+    while (split * 2 <= max_split && tiles * split * 2 <= sms + sms / 4 && KB / (split * 2) >= 4) split *= 2;
+  }
   *tok_out = tok;
   *split_out = split;
 }

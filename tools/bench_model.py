@@ -16,20 +16,33 @@ ap.add_argument("--layers", type=int, default=0, help="override layer count (0 =
 ap.add_argument("--impl", default="quick_b200", choices=["quick_b200", "reference"])
 ap.add_argument("--out", default="")
 args = ap.parse_args()
+# tensor parallel: `python -m torch.distributed.run --nproc-per-node R tools/bench_model.py --model llama-2-70b`
+# (one process per GPU; every linear column-parallel + one NCCL all-gather, SURVEY §8e / BASELINE config 5)
+world = int(os.environ.get("WORLD_SIZE", 1)); rank = int(os.environ.get("RANK", 0))
+if world > 1:
+    import torch.distributed as dist
+    os.environ.setdefault("NCCL_DEBUG", "NONE")
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
 cfg = PRESETS[args.model]
 if args.layers:
     cfg.num_layers = args.layers
 cfg.max_seq_len = args.ctx + args.gen
 rows = []
+torch.manual_seed(1234)   # replicated parts (embedding, lm_head) and the prompt are identical on every rank
 for bs in args.batch:
     model = LlamaLikeQuickModel(cfg, bs)
     if args.impl == "reference":
         from oracle.build_ref import load_ref
         model.ref_mod = load_ref(); assert model.ref_mod is not None
     r = benchmark_generation(model, args.ctx, args.gen)
-    r.update({"model": args.model, "impl": args.impl, "layers": cfg.num_layers, "weight_GB": round(model.weight_bytes() / 1e9, 2),
-              "mem_GB": round(torch.cuda.max_memory_allocated() / 1e9, 2)})
-    rows.append(r); print(json.dumps(r), flush=True)
+    r.update({"model": args.model, "impl": args.impl, "layers": cfg.num_layers, "weight_GB_per_rank": round(model.weight_bytes() / 1e9, 2),
+              "mem_GB": round(torch.cuda.max_memory_allocated() / 1e9, 2), "tp": world})
+    rows.append(r)
+    if rank == 0:
+        print(json.dumps(r), flush=True)
     del model; torch.cuda.empty_cache()
-if args.out:
+if args.out and rank == 0:
     json.dump(rows, open(args.out, "w"), indent=1)
+if world > 1:
+    dist.destroy_process_group()
