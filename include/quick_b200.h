@@ -96,6 +96,12 @@ int qb200_gemm_w4a16_cfg(const void* A_fp16, const uint32_t* wq, const uint32_t*
 int qb200_gemm_w4a16_ex(const void* A_fp16, const uint32_t* wq, const uint32_t* sz, const void* bias_fp16_or_null,
                         void* C_fp16, int M, int K, int N, int G, int tok, int split, unsigned flags, void* stream);
 
+/* Same with a fused residual: C = residual + fp16(A·W + bias), residual fp16 [M][N] or NULL (the `x + proj(...)` of a
+ * decoder layer, reference modules/fused/block.py:61-74, without a separate add kernel).  C may alias residual. */
+int qb200_gemm_w4a16_fused(const void* A_fp16, const uint32_t* wq, const uint32_t* sz, const void* bias_fp16_or_null,
+                           const void* residual_fp16_or_null, void* C_fp16, int M, int K, int N, int G, int tok, int split,
+                           unsigned flags, void* stream);
+
 /* Reports the configuration qb200_gemm_w4a16 would pick. */
 int qb200_gemm_plan(int M, int K, int N, int G, int split_k_hint, int* tok, int* split, int* ctas);
 /* Same for a given set of launch flags (the independent plan never splits K). */
@@ -111,6 +117,18 @@ int qb200_gemm_forward_quick(const void* A_fp16, const int32_t* qweight, const v
 /* CUDA-core cross-check of the same contraction (tests only; never dispatched to by the hot path). */
 int qb200_gemm_w4a16_simt(const void* A_fp16, const uint32_t* wq, const uint32_t* sz, void* C_fp16,
                           int M, int K, int N, int G, void* stream);
+
+/* ---- Decoder-layer glue: the kernels between the GEMMs of a Llama-like layer.  The reference's fused
+ * modules call awq_ext for these (modules/fused/norm.py:18, attn.py:100-245, mlp.py:52-76); awq_ext is not in its tree. ---- */
+/* y[rows][H] = fp16(fp16(x * rsqrt(mean(x^2) + eps)) * weight), statistics in fp32. */
+int qb200_rmsnorm(const void* x_fp16, const void* weight_fp16, void* y_fp16, int rows, int H, float eps, void* stream);
+/* qkv [B][T][(nh + 2 nkv) hd] -> rotary-embedded q_out [B][nh][T][hd]; rotary k and plain v are written into the static
+ * caches [B][nkv][S][hd] at positions pos[t] (int64 device array); cos/sin tables are [S][hd] fp16. */
+int qb200_rope_kv_update(const void* qkv_fp16, const void* cos_table_fp16, const void* sin_table_fp16, const long long* pos,
+                         void* q_out_fp16, void* cache_k_fp16, void* cache_v_fp16, int B, int T, int nh, int nkv, int hd, int S,
+                         void* stream);
+/* act[rows][I] = silu(g) * u for gate_up rows [g | u] of width 2I. */
+int qb200_silu_mul(const void* gate_up_fp16, void* act_fp16, long long rows, int I, void* stream);
 
 /* ---- HOST-buffer handle API (the end-to-end path: H2D, GEMM, D2H inside the call) ---- */
 typedef struct qb200_linear qb200_linear;

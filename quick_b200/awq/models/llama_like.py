@@ -16,7 +16,14 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+import quick_kernels
+
 from ..modules.linear.quick import WQLinear_QUICK
+
+# Decoder-layer glue (RMSNorm, rotary + KV-cache update, SiLU·up, residual add) through the library's fused kernels
+# (C-ABI qb200_rmsnorm / qb200_rope_kv_update / qb200_silu_mul / qb200_gemm_w4a16_fused) instead of ~30 small torch
+# kernels per layer; FUSED_GLUE = False keeps the plain torch expressions (the parity reference of the tests).
+FUSED_GLUE = True
 
 
 @dataclass
@@ -65,6 +72,11 @@ class RMSNorm(nn.Module):
         self.eps = eps
 
     def forward(self, x):
+        if x.is_cuda and FUSED_GLUE:
+            return quick_kernels.rmsnorm(x, self.weight, self.eps)      # one kernel instead of seven
+        return self.forward_torch(x)
+
+    def forward_torch(self, x):
         v = x.float()
         return (v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + self.eps)).half() * self.weight
 
@@ -87,14 +99,18 @@ def _gather_columns(local: torch.Tensor) -> torch.Tensor:
     return gathered.view(R, flat.shape[0], n_local).permute(1, 0, 2).reshape(lead + (R * n_local,))
 
 
-def _linear(m: WQLinear_QUICK, x, ref_mod=None):
-    """Route through the B200 kernel, or (baseline runs only) through the unmodified reference kernel."""
+def _linear(m: WQLinear_QUICK, x, ref_mod=None, residual=None):
+    """Route through the B200 kernel, or (baseline runs only) through the unmodified reference kernel.
+    residual: returns residual + linear(x) (fused into the GEMM epilogue unless the output is column-sharded)."""
     if ref_mod is None:
-        y = m(x)
-        return _gather_columns(y) if getattr(m, "tp_sharded", False) else y
+        if getattr(m, "tp_sharded", False):
+            y = _gather_columns(m(x))
+            return y if residual is None else residual + y
+        return m(x, residual if FUSED_GLUE else None) if (residual is None or FUSED_GLUE) else residual + m(x)
     split = m.k_split_1 if m.out_features > m.in_features else m.k_split_2      # quick.py:161-164
     out = ref_mod.gemm_forward_cuda_quick(x.reshape(-1, x.shape[-1]), m.qweight, m.scales, m.qzeros, split)
-    return out.reshape(x.shape[:-1] + (m.out_features,))
+    out = out.reshape(x.shape[:-1] + (m.out_features,))
+    return out if residual is None else residual + out
 
 
 class Block(nn.Module):
@@ -122,23 +138,31 @@ class Block(nn.Module):
         self.register_buffer("cache_k", torch.zeros(batch, nkv, cfg.max_seq_len, hd, dtype=torch.float16, device=dev), persistent=False)
         self.register_buffer("cache_v", torch.zeros(batch, nkv, cfg.max_seq_len, hd, dtype=torch.float16, device=dev), persistent=False)
 
-    def forward(self, x, cos, sin, pos_idx, attn_mask, ref_mod=None):
+    def forward(self, x, cos, sin, pos_idx, attn_mask, ref_mod=None, rope=None):
         cfg = self.cfg
         B, T, _ = x.shape
         hd, nh, nkv = cfg.head_dim, cfg.num_heads, cfg.num_kv_heads
         qkv = _linear(self.qkv_proj, self.norm_1(x), ref_mod)
-        q, k, v = qkv.split([nh * hd, nkv * hd, nkv * hd], dim=-1)
-        q = q.view(B, T, nh, hd).transpose(1, 2)
-        k = k.view(B, T, nkv, hd).transpose(1, 2)
-        v = v.view(B, T, nkv, hd).transpose(1, 2)
-        q, k = _rope(q, cos, sin), _rope(k, cos, sin)
-        self.cache_k.index_copy_(2, pos_idx, k)
-        self.cache_v.index_copy_(2, pos_idx, v)
+        if FUSED_GLUE and qkv.is_cuda:
+            # rotary embedding of q and k + KV-cache update in one kernel (rope tables are indexed by position)
+            q = quick_kernels.rope_kv_update(qkv, rope[0], rope[1], pos_idx, self.cache_k, self.cache_v, nh, nkv)
+        else:
+            q, k, v = qkv.split([nh * hd, nkv * hd, nkv * hd], dim=-1)
+            q = q.view(B, T, nh, hd).transpose(1, 2)
+            k = k.view(B, T, nkv, hd).transpose(1, 2)
+            v = v.view(B, T, nkv, hd).transpose(1, 2)
+            q, k = _rope(q, cos, sin), _rope(k, cos, sin)
+            self.cache_k.index_copy_(2, pos_idx, k)
+            self.cache_v.index_copy_(2, pos_idx, v)
         o = F.scaled_dot_product_attention(q, self.cache_k, self.cache_v, attn_mask=attn_mask, enable_gqa=(nkv != nh))
-        x = x + _linear(self.o_proj, o.transpose(1, 2).reshape(B, T, nh * hd), ref_mod)
+        x = _linear(self.o_proj, o.transpose(1, 2).reshape(B, T, nh * hd), ref_mod, residual=x)
         gu = _linear(self.gate_up_proj, self.norm_2(x), ref_mod)
-        g, u = gu.split(cfg.intermediate_size, dim=-1)
-        return x + _linear(self.down_proj, F.silu(g) * u, ref_mod)
+        if FUSED_GLUE and gu.is_cuda:
+            act = quick_kernels.silu_mul(gu)
+        else:
+            g, u = gu.split(cfg.intermediate_size, dim=-1)
+            act = F.silu(g) * u
+        return _linear(self.down_proj, act, ref_mod, residual=x)
 
 
 def _rope(t, cos, sin):
@@ -175,7 +199,7 @@ class LlamaLikeQuickModel(nn.Module):
         keys = torch.arange(cfg.max_seq_len, device=x.device)
         attn_mask = keys[None, :] <= pos_idx[:, None]
         for blk in self.blocks:
-            x = blk(x, cos, sin, pos_idx, attn_mask, self.ref_mod)
+            x = blk(x, cos, sin, pos_idx, attn_mask, self.ref_mod, (self.rope_cos, self.rope_sin))
         return self.lm_head(self.norm(x[:, -1:, :]))
 
     def weight_bytes(self):

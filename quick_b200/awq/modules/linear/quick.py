@@ -114,10 +114,13 @@ class WQLinear_QUICK(nn.Module):
         return self._b200
 
     @torch.no_grad()
-    def forward(self, x):
+    def forward(self, x, residual=None):
+        """residual (same shape as the output): returns residual + linear(x), the add fused into the GEMM epilogue."""
         out_shape = x.shape[:-1] + (self.out_features,)
         wq, sz = self._prepacked()
-        out = quick_kernels.gemm_forward_b200(x.reshape(-1, x.shape[-1]), wq, sz, self.bias, self.out_features, self.group_size)
+        res2d = None if residual is None else residual.reshape(-1, self.out_features)
+        out = quick_kernels.gemm_forward_b200(x.reshape(-1, x.shape[-1]), wq, sz, self.bias, self.out_features, self.group_size,
+                                              False, res2d)
         return out.reshape(out_shape)
 
     @torch.no_grad()

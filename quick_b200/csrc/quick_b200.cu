@@ -281,6 +281,98 @@ __global__ void gemm_simt_kernel(const __half* __restrict__ A, const uint32_t* _
 }
 
 // ------------------------------------------------------------------------------------------------
+// Decoder-layer glue kernels: what sits between the GEMMs of a Llama-like layer.  The reference's
+// fused modules do the same jobs with awq_ext kernels that are not part of its tree (modules/fused/norm.py:18
+// layernorm_forward_cuda, attn.py:100-245 RoPE + cache update, mlp.py:52-76 silu * up).  Arithmetic follows the
+// torch expressions of quick_b200/awq/models/llama_like.py step by step (same roundings), so they are drop-ins.
+// ------------------------------------------------------------------------------------------------
+
+// y = fp16( fp16( x * rsqrt(mean(x^2) + eps) ) * w ), statistics in fp32.  One CTA per row.
+__global__ void rmsnorm_kernel(const __half* __restrict__ x, const __half* __restrict__ w, __half* __restrict__ y, int H, float eps) {
+  const __half* xr = x + static_cast<size_t>(blockIdx.x) * H;
+  __half* yr = y + static_cast<size_t>(blockIdx.x) * H;
+  float ss = 0.f;
+  for (int i = threadIdx.x * 8; i < H; i += blockDim.x * 8) {
+    const uint4 v = *reinterpret_cast<const uint4*>(xr + i);
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); ss += f.x * f.x + f.y * f.y; }
+  }
+  __shared__ float red[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) red[0] = rsqrtf(t / static_cast<float>(H) + eps);
+  }
+  __syncthreads();
+  const float r = red[0];
+  for (int i = threadIdx.x * 8; i < H; i += blockDim.x * 8) {
+    const uint4 v = *reinterpret_cast<const uint4*>(xr + i);
+    const uint4 wv = *reinterpret_cast<const uint4*>(w + i);
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+    const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      oh[j] = __hmul2(__floats2half2_rn(f.x * r, f.y * r), wh[j]);
+    }
+    *reinterpret_cast<uint4*>(yr + i) = o;
+  }
+}
+
+// qkv [B][T][(nh + 2 nkv) * hd] -> q_rot [B][nh][T][hd]; k_rot, v written into the static caches [B][nkv][S][hd] at pos[t].
+// rope(t) = fp16(fp16(t * cos) + fp16(rot(t) * sin)), rot = (-t2, t1) over the two halves of the head (same as _rope()).
+__global__ void rope_kv_kernel(const __half* __restrict__ qkv, const __half* __restrict__ cosb, const __half* __restrict__ sinb,
+                               const long long* __restrict__ pos, __half* __restrict__ q_out, __half* __restrict__ cache_k,
+                               __half* __restrict__ cache_v, int T, int nh, int nkv, int hd, int S) {
+  const int head = blockIdx.x;            // 0 .. nh + 2 nkv - 1
+  const int t = blockIdx.y, b = blockIdx.z;
+  const int width = (nh + 2 * nkv) * hd;
+  const __half* src = qkv + (static_cast<size_t>(b) * T + t) * width + static_cast<size_t>(head) * hd;
+  const long long p = pos[t];
+  const int half_hd = hd >> 1;
+  for (int i = threadIdx.x; i < hd; i += blockDim.x) {
+    const __half v = src[i];
+    if (head >= nh + nkv) {               // value head: plain copy into the cache
+      cache_v[((static_cast<size_t>(b) * nkv + (head - nh - nkv)) * S + p) * hd + i] = v;
+      continue;
+    }
+    const __half c = cosb[static_cast<size_t>(p) * hd + i], sn = sinb[static_cast<size_t>(p) * hd + i];
+    const __half other = i < half_hd ? __hneg(src[i + half_hd]) : src[i - half_hd];
+    const __half r = __hadd_rn(__hmul_rn(v, c), __hmul_rn(other, sn));   // _rn: no contraction into fma, torch rounds each step
+    if (head < nh) q_out[((static_cast<size_t>(b) * nh + head) * T + t) * hd + i] = r;
+    else cache_k[((static_cast<size_t>(b) * nkv + (head - nh)) * S + p) * hd + i] = r;
+  }
+}
+
+// act[M][I] = fp16( fp16(silu(g)) * u ),  gu = [g | u] per row ([M][2I]); silu in fp32 like torch's half kernel.
+__global__ void silu_mul_kernel(const __half* __restrict__ gu, __half* __restrict__ act, size_t M, int I) {
+  const size_t idx = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  if (idx >= M * static_cast<size_t>(I)) return;
+  const size_t m = idx / I;
+  const int i = static_cast<int>(idx % I);
+  const uint4 g = *reinterpret_cast<const uint4*>(gu + m * 2 * I + i);
+  const uint4 u = *reinterpret_cast<const uint4*>(gu + m * 2 * I + I + i);
+  const __half2* gh = reinterpret_cast<const __half2*>(&g);
+  const __half2* uh = reinterpret_cast<const __half2*>(&u);
+  uint4 o;
+  __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __half22float2(gh[j]);
+    oh[j] = __hmul2(__floats2half2_rn(f.x / (1.f + expf(-f.x)), f.y / (1.f + expf(-f.y))), uh[j]);
+  }
+  *reinterpret_cast<uint4*>(act + idx) = o;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Tensor-map encode (driver entry point fetched through the runtime: no link-time libcuda dependency)
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -572,6 +664,11 @@ int qb200_gemm_w4a16_cfg(const void* A, const uint32_t* wq, const uint32_t* sz, 
 
 int qb200_gemm_w4a16_ex(const void* A, const uint32_t* wq, const uint32_t* sz, const void* bias, void* C, int M, int K,
                         int N, int G, int tok, int split, unsigned flags, void* stream) {
+  return qb200_gemm_w4a16_fused(A, wq, sz, bias, nullptr, C, M, K, N, G, tok, split, flags, stream);
+}
+
+int qb200_gemm_w4a16_fused(const void* A, const uint32_t* wq, const uint32_t* sz, const void* bias, const void* residual,
+                           void* C, int M, int K, int N, int G, int tok, int split, unsigned flags, void* stream) {
   int rc = qb200_check_shape(M, K, N, G);
   if (rc) return rc;
   if (M == 0) return QB200_OK;
@@ -586,6 +683,8 @@ int qb200_gemm_w4a16_ex(const void* A, const uint32_t* wq, const uint32_t* sz, c
   }
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(wq) & 15))
     return fail(QB200_EINVAL, "A and wq must be 16-byte aligned");
+  if (residual != nullptr && ((reinterpret_cast<uintptr_t>(residual) & 15) || (reinterpret_cast<uintptr_t>(C) & 15)))
+    return fail(QB200_EINVAL, "residual and C must be 16-byte aligned");
   const int KB = K / 64;
   if (split < 1 || split > KB) return fail(QB200_EINVAL, "split %d out of range for K=%d", split, K);
   const int kbps = (KB + split - 1) / split;
@@ -600,6 +699,7 @@ int qb200_gemm_w4a16_ex(const void* A, const uint32_t* wq, const uint32_t* sz, c
   args.wq = wq;
   args.sz = sz;
   args.bias = reinterpret_cast<const __half*>(bias);
+  args.residual = reinterpret_cast<const __half*>(residual);
   args.C = reinterpret_cast<__half*>(C);
   args.M = M;
   args.K = K;
@@ -654,6 +754,43 @@ int qb200_gemm_w4a16_simt(const void* A, const uint32_t* wq, const uint32_t* sz,
   }
   gemm_simt_kernel<<<dim3(N / 128, M), 128, static_cast<size_t>(K) * 2, as_stream(stream)>>>(
       reinterpret_cast<const __half*>(A), wq, sz, reinterpret_cast<__half*>(C), M, K, N, G);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  QB_CUDA(cudaGetLastError());
+  return QB200_OK;
+}
+
+int qb200_rmsnorm(const void* x, const void* weight, void* y, int rows, int H, float eps, void* stream) {
+  if (rows < 0 || H <= 0 || H % 8 != 0) return fail(QB200_EINVAL, "rmsnorm: H must be a positive multiple of 8");
+  if (rows == 0) return QB200_OK;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(y)) & 15)
+    return fail(QB200_EINVAL, "rmsnorm: pointers must be 16-byte aligned");
+  const int threads = H >= 4096 ? 512 : H >= 1024 ? 128 : 64;
+  rmsnorm_kernel<<<rows, threads, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(weight),
+                                                         reinterpret_cast<__half*>(y), H, eps);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  QB_CUDA(cudaGetLastError());
+  return QB200_OK;
+}
+
+int qb200_rope_kv_update(const void* qkv, const void* cos_table, const void* sin_table, const long long* pos, void* q_out,
+                         void* cache_k, void* cache_v, int B, int T, int nh, int nkv, int hd, int S, void* stream) {
+  if (B <= 0 || T <= 0 || nh <= 0 || nkv <= 0 || hd <= 0 || hd % 2 != 0 || S <= 0) return fail(QB200_EINVAL, "rope_kv_update: bad dimensions");
+  if (T > 65535 || B > 65535) return fail(QB200_EINVAL, "rope_kv_update: T and B must be <= 65535");
+  rope_kv_kernel<<<dim3(nh + 2 * nkv, T, B), hd >= 128 ? 128 : 64, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __half*>(qkv), reinterpret_cast<const __half*>(cos_table), reinterpret_cast<const __half*>(sin_table),
+      pos, reinterpret_cast<__half*>(q_out), reinterpret_cast<__half*>(cache_k), reinterpret_cast<__half*>(cache_v), T, nh, nkv, hd, S);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  QB_CUDA(cudaGetLastError());
+  return QB200_OK;
+}
+
+int qb200_silu_mul(const void* gate_up, void* act, long long rows, int I, void* stream) {
+  if (rows < 0 || I <= 0 || I % 8 != 0) return fail(QB200_EINVAL, "silu_mul: I must be a positive multiple of 8");
+  if (rows == 0) return QB200_OK;
+  if ((reinterpret_cast<uintptr_t>(gate_up) | reinterpret_cast<uintptr_t>(act)) & 15) return fail(QB200_EINVAL, "silu_mul: pointers must be 16-byte aligned");
+  const size_t vecs = static_cast<size_t>(rows) * I / 8;
+  silu_mul_kernel<<<static_cast<unsigned>((vecs + 255) / 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __half*>(gate_up), reinterpret_cast<__half*>(act), static_cast<size_t>(rows), I);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   QB_CUDA(cudaGetLastError());
   return QB200_OK;

@@ -142,7 +142,8 @@ std::vector<torch::Tensor> prepack_quick(torch::Tensor kernel, torch::Tensor sca
 // independent = true passes QB200_GEMM_INDEPENDENT (include/quick_b200.h): the caller guarantees that the operands
 // are not produced by a kernel that may still be running (e.g. sibling projections of one activation tensor).
 torch::Tensor gemm_forward_b200(torch::Tensor in_feats, torch::Tensor wq, torch::Tensor sz,
-                                c10::optional<torch::Tensor> bias, int64_t N, int64_t G, bool independent) {
+                                c10::optional<torch::Tensor> bias, int64_t N, int64_t G, bool independent,
+                                c10::optional<torch::Tensor> residual) {
   TORCH_CHECK(in_feats.dim() == 2 && in_feats.is_cuda(), "in_feats must be a 2-D CUDA tensor (there is no CPU path)");
   const at::cuda::OptionalCUDAGuard device_guard(device_of(in_feats));
   torch::Tensor x = in_feats.contiguous();
@@ -157,21 +158,77 @@ torch::Tensor gemm_forward_b200(torch::Tensor in_feats, torch::Tensor wq, torch:
     TORCH_CHECK(b.numel() == N && b.scalar_type() == torch::kHalf, "bias must be fp16 [N]");
     bias_ptr = b.data_ptr<at::Half>();
   }
+  // residual (fp16 [M, N]): out = residual + fp16(x·W + bias), fused into the epilogue (qb200_gemm_w4a16_fused)
+  const void* res_ptr = nullptr;
+  torch::Tensor r;
+  if (residual.has_value() && residual->defined()) {
+    r = residual->contiguous();
+    TORCH_CHECK(r.numel() == static_cast<int64_t>(M) * N && r.scalar_type() == torch::kHalf && r.is_cuda(), "residual must be CUDA fp16 [M, N]");
+    res_ptr = r.data_ptr<at::Half>();
+  }
   torch::Tensor out = torch::empty({M, N}, x.options());
   auto stream = at::cuda::getCurrentCUDAStream();
-  check(qb200_gemm_w4a16_ex(x.data_ptr<at::Half>(), reinterpret_cast<const uint32_t*>(wq.data_ptr<int>()),
-                            reinterpret_cast<const uint32_t*>(sz.data_ptr<int>()), bias_ptr, out.data_ptr<at::Half>(), M, K,
-                            static_cast<int>(N), static_cast<int>(G), /*tok*/ 0, /*split*/ 0,
-                            independent ? QB200_GEMM_INDEPENDENT : 0u, stream.stream()));
+  check(qb200_gemm_w4a16_fused(x.data_ptr<at::Half>(), reinterpret_cast<const uint32_t*>(wq.data_ptr<int>()),
+                               reinterpret_cast<const uint32_t*>(sz.data_ptr<int>()), bias_ptr, res_ptr, out.data_ptr<at::Half>(), M, K,
+                               static_cast<int>(N), static_cast<int>(G), /*tok*/ 0, /*split*/ 0,
+                               independent ? QB200_GEMM_INDEPENDENT : 0u, stream.stream()));
   return out;
 }
 
+// ---- decoder-layer glue (C-ABI qb200_rmsnorm / qb200_rope_kv_update / qb200_silu_mul) ----
+torch::Tensor rmsnorm(torch::Tensor x, torch::Tensor weight, double eps) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == torch::kHalf && weight.scalar_type() == torch::kHalf, "rmsnorm: CUDA fp16 tensors required");
+  const at::cuda::OptionalCUDAGuard device_guard(device_of(x));
+  torch::Tensor xc = x.contiguous(), w = weight.contiguous();
+  const int H = static_cast<int>(xc.size(-1));
+  TORCH_CHECK(w.numel() == H, "rmsnorm: weight must have H elements");
+  torch::Tensor y = torch::empty_like(xc);
+  check(qb200_rmsnorm(xc.data_ptr<at::Half>(), w.data_ptr<at::Half>(), y.data_ptr<at::Half>(), static_cast<int>(xc.numel() / H), H,
+                      static_cast<float>(eps), at::cuda::getCurrentCUDAStream().stream()));
+  return y;
+}
+
+torch::Tensor rope_kv_update(torch::Tensor qkv, torch::Tensor cos_table, torch::Tensor sin_table, torch::Tensor pos,
+                             torch::Tensor cache_k, torch::Tensor cache_v, int64_t nh, int64_t nkv) {
+  TORCH_CHECK(qkv.is_cuda() && qkv.dim() == 3 && qkv.scalar_type() == torch::kHalf, "rope_kv_update: qkv must be CUDA fp16 [B, T, (nh + 2 nkv) hd]");
+  TORCH_CHECK(cache_k.is_contiguous() && cache_v.is_contiguous() && cache_k.dim() == 4, "rope_kv_update: caches must be contiguous [B, nkv, S, hd]");
+  TORCH_CHECK(pos.scalar_type() == torch::kLong && pos.is_cuda(), "rope_kv_update: pos must be a CUDA int64 tensor");
+  const at::cuda::OptionalCUDAGuard device_guard(device_of(qkv));
+  torch::Tensor x = qkv.contiguous(), c = cos_table.contiguous(), s = sin_table.contiguous(), p = pos.contiguous();
+  const int B = static_cast<int>(x.size(0)), T = static_cast<int>(x.size(1));
+  const int hd = static_cast<int>(x.size(2) / (nh + 2 * nkv)), S = static_cast<int>(cache_k.size(2));
+  TORCH_CHECK(x.size(2) == (nh + 2 * nkv) * hd && cache_k.size(3) == hd && cache_k.size(1) == nkv && cache_k.size(0) >= B, "rope_kv_update: shape mismatch");
+  TORCH_CHECK(c.size(-1) == hd && c.size(0) >= S && p.numel() == T, "rope_kv_update: table / pos shape mismatch");
+  torch::Tensor q = torch::empty({B, nh, T, hd}, x.options());
+  check(qb200_rope_kv_update(x.data_ptr<at::Half>(), c.data_ptr<at::Half>(), s.data_ptr<at::Half>(),
+                             reinterpret_cast<const long long*>(p.data_ptr<int64_t>()), q.data_ptr<at::Half>(),
+                             cache_k.data_ptr<at::Half>(), cache_v.data_ptr<at::Half>(), B, T, static_cast<int>(nh),
+                             static_cast<int>(nkv), hd, S, at::cuda::getCurrentCUDAStream().stream()));
+  return q;
+}
+
+torch::Tensor silu_mul(torch::Tensor gate_up) {
+  TORCH_CHECK(gate_up.is_cuda() && gate_up.scalar_type() == torch::kHalf, "silu_mul: CUDA fp16 tensor required");
+  const at::cuda::OptionalCUDAGuard device_guard(device_of(gate_up));
+  torch::Tensor gu = gate_up.contiguous();
+  const int64_t I = gu.size(-1) / 2;
+  auto shape = gu.sizes().vec();
+  shape.back() = I;
+  torch::Tensor act = torch::empty(shape, gu.options());
+  check(qb200_silu_mul(gu.data_ptr<at::Half>(), act.data_ptr<at::Half>(), static_cast<long long>(gu.numel() / (2 * I)), static_cast<int>(I),
+                       at::cuda::getCurrentCUDAStream().stream()));
+  return act;
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.def("rmsnorm", &rmsnorm, "RMSNorm (fp16 in/out, fp32 statistics)");
+  m.def("rope_kv_update", &rope_kv_update, "rotary embedding of q/k + static KV-cache update; returns q [B, nh, T, hd]");
+  m.def("silu_mul", &silu_mul, "silu(gate) * up for rows [gate | up]");
   m.def("gemm_forward_cuda_quick", &gemm_forward_cuda_quick, "QUICK AWQ GEMM kernel.");
   m.def("prepack_quick", &prepack_quick, "QUICK layout -> B200 layout (wq, sz)");
   m.def("gemm_forward_b200", &gemm_forward_b200, "W4A16 GEMM on B200-layout weights (bias fused)", pybind11::arg("in_feats"),
         pybind11::arg("wq"), pybind11::arg("sz"), pybind11::arg("bias"), pybind11::arg("N"), pybind11::arg("G"),
-        pybind11::arg("independent") = false);
+        pybind11::arg("independent") = false, pybind11::arg("residual") = pybind11::none());
   m.def("cache_stats", [] {
     std::lock_guard<std::mutex> lock(g_mu);
     return std::vector<int64_t>{static_cast<int64_t>(g_cache.size()), static_cast<int64_t>(g_hits), static_cast<int64_t>(g_misses)};

@@ -382,6 +382,7 @@ struct GemmArgs {
   const uint32_t* wq;
   const uint32_t* sz;
   const __half* bias;
+  const __half* residual;   // optional [M][N] fp16: C = residual + fp16(A·W + bias), the add in fp16 like torch's x + linear(x)
   __half* C;
   int M, K, N, G;
   int kb_per_split;   // k64 blocks per cluster rank
@@ -497,6 +498,15 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
 }
 __device__ __forceinline__ float2 unpack_half2(uint32_t v) {
   return __half22float2(*reinterpret_cast<__half2*>(&v));
+}
+// a + b on eight packed fp16 values (residual + GEMM result, one rounding each like torch's fp16 add)
+__device__ __forceinline__ uint4 hadd2x4(uint4 a, uint4 b) {
+  uint4 r;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r.x) : "r"(a.x), "r"(b.x));
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r.y) : "r"(a.y), "r"(b.y));
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r.z) : "r"(a.z), "r"(b.z));
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r.w) : "r"(a.w), "r"(b.w));
+  return r;
 }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   uint32_t v;
@@ -882,7 +892,12 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
 #pragma unroll
           for (int i = 0; i < PIECE; ++i) {
             const int m = m_base + j0 + i;
-            if (m < args.M) args.C[static_cast<size_t>(m) * args.N + n0 + ch] = __float2half_rn(acc[i]);
+            if (m < args.M) {
+              const size_t off = static_cast<size_t>(m) * args.N + n0 + ch;
+              __half h = __float2half_rn(acc[i]);
+              if (args.residual != nullptr) h = __hadd(args.residual[off], h);
+              args.C[off] = h;
+            }
           }
         } else {
 #pragma unroll
@@ -898,8 +913,10 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
         for (int row = tid >> 4; row < SLICE; row += (kEpilogueWarps * 32) / 16) {
           const int m = m_base + row;
           if (m < args.M) {
-            const uint4 v = lds128(smem_out + static_cast<uint32_t>(row * kChan * 2 + chunk * 16));
-            *reinterpret_cast<uint4*>(args.C + static_cast<size_t>(m) * args.N + n0 + chunk * 8) = v;
+            uint4 v = lds128(smem_out + static_cast<uint32_t>(row * kChan * 2 + chunk * 16));
+            const size_t off = static_cast<size_t>(m) * args.N + n0 + chunk * 8;
+            if (args.residual != nullptr) v = hadd2x4(*reinterpret_cast<const uint4*>(args.residual + off), v);
+            *reinterpret_cast<uint4*>(args.C + off) = v;
           }
         }
       }
@@ -998,8 +1015,10 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
       for (int row = tid >> 4; row < SLICE; row += (kEpilogueWarps * 32) / 16) {
         const int m = m_base + row;
         if (m < args.M) {
-          const uint4 v = lds128(smem_out + static_cast<uint32_t>(row * kChan * 2 + chunk * 16));
-          *reinterpret_cast<uint4*>(args.C + static_cast<size_t>(m) * args.N + n0 + chunk * 8) = v;
+          uint4 v = lds128(smem_out + static_cast<uint32_t>(row * kChan * 2 + chunk * 16));
+          const size_t off = static_cast<size_t>(m) * args.N + n0 + chunk * 8;
+          if (args.residual != nullptr) v = hadd2x4(*reinterpret_cast<const uint4*>(args.residual + off), v);
+          *reinterpret_cast<uint4*>(args.C + off) = v;
         }
       }
       if (threadIdx.x == 0) QB_TRACE(3, 0, 3);

@@ -374,6 +374,58 @@ def test_repeated_launches_are_deterministic_and_never_hang(ops):
                 assert torch.equal(out, first[it % 6]), (M, tok, split, it)
 
 
+def test_decoder_glue_kernels_match_the_torch_expressions(ops):
+    """RMSNorm, rotary + KV-cache update, SiLU*up and the residual fused into the GEMM epilogue
+    against the plain torch expressions of the runner (FUSED_GLUE = False path).  The residual add and the rotary /
+    cache update replicate torch's fp16 roundings exactly; RMSNorm and SiLU may differ by one fp16 ulp (reduction
+    order, expf)."""
+    import quick_kernels
+    from quick_b200.awq.models.llama_like import RMSNorm, _rope
+    import torch.nn.functional as F
+    torch.manual_seed(3)
+    # RMSNorm
+    for (rows, H) in ((1, 4096), (67, 4096), (5, 512), (3, 11008)):
+        x = (torch.randn(rows, H, device="cuda") * 2).half()
+        n = RMSNorm(H, 1e-5, "cuda"); n.weight.data = (1 + 0.1 * torch.randn(H, device="cuda")).half()
+        got, want = quick_kernels.rmsnorm(x, n.weight, 1e-5), n.forward_torch(x)
+        assert torch.allclose(got.float(), want.float(), rtol=2e-3, atol=1e-4), (rows, H)
+        assert (got != want).float().mean().item() < 0.02          # almost everywhere bit-identical
+    # SiLU * up
+    for (rows, I) in ((1, 11008), (33, 1024), (128, 14336)):
+        gu = (torch.randn(rows, 2 * I, device="cuda") * 3).half()
+        want = F.silu(gu[:, :I]) * gu[:, I:]
+        got = quick_kernels.silu_mul(gu)
+        assert got.shape == want.shape and torch.allclose(got.float(), want.float(), rtol=2e-3, atol=1e-4)
+        assert (got != want).float().mean().item() < 0.01
+    # rotary + cache update (GQA and MHA, prefill and single-token decode)
+    for (B, T, nh, nkv, hd, S) in ((2, 5, 8, 2, 64, 32), (1, 1, 32, 32, 128, 256), (3, 16, 4, 4, 128, 64)):
+        qkv = torch.randn(B, T, (nh + 2 * nkv) * hd, device="cuda").half()
+        inv = 1.0 / (10000.0 ** (torch.arange(0, hd, 2, device="cuda").float() / hd))
+        ang = torch.outer(torch.arange(S, device="cuda").float(), inv); ang = torch.cat((ang, ang), -1)
+        cos_t, sin_t = ang.cos().half(), ang.sin().half()
+        pos = torch.arange(3, 3 + T, device="cuda")
+        ck, cv = (torch.randn(B, nkv, S, hd, device="cuda").half() for _ in range(2))
+        ck2, cv2 = ck.clone(), cv.clone()
+        q, k, v = qkv.split([nh * hd, nkv * hd, nkv * hd], dim=-1)
+        q = q.view(B, T, nh, hd).transpose(1, 2); k = k.view(B, T, nkv, hd).transpose(1, 2); v = v.view(B, T, nkv, hd).transpose(1, 2)
+        cos, sin = cos_t.index_select(0, pos)[None, None], sin_t.index_select(0, pos)[None, None]
+        q_want, k_want = _rope(q, cos, sin), _rope(k, cos, sin)
+        ck.index_copy_(2, pos, k_want); cv.index_copy_(2, pos, v)
+        q_got = quick_kernels.rope_kv_update(qkv, cos_t, sin_t, pos, ck2, cv2, nh, nkv)
+        assert torch.equal(q_got, q_want) and torch.equal(ck2, ck) and torch.equal(cv2, cv), (B, T, nh, nkv, hd)
+    # residual fused into the GEMM epilogue: every epilogue path (direct store, staged store, split-K, large tiles)
+    K, N, G = 1024, 512, 128
+    q_, z_, s_, qw, qz, sc, W16 = make_gpu_case(ops, K, N, G)
+    wq, sz, *_ = ops.prepack(qw, qz, sc)
+    bias = torch.randn(N, device="cuda").half()
+    for M in (1, 16, 40, 100, 200, 300):
+        x = torch.from_numpy(qo.make_activations(M, K, seed=M)).cuda()
+        res = torch.randn(M, N, device="cuda").half()
+        plain = quick_kernels.gemm_forward_b200(x, wq, sz, bias, N, G)
+        fused = quick_kernels.gemm_forward_b200(x, wq, sz, bias, N, G, False, res)
+        assert torch.equal(fused, res + plain), M
+
+
 def test_llama_like_runner_matches_dense_fp16_model(ops):
     """the minimal runner (all linears through the tcgen05 kernel, CUDA-graph-free here) against
     the same network with every WQLinear_QUICK replaced by its dequantised fp16 weight and torch.matmul."""
@@ -394,7 +446,13 @@ def test_llama_like_runner_matches_dense_fp16_model(ops):
             dense[id(m)] = ops.dequantize(wq, sz, K, N, G)
     import quick_b200.awq.models.llama_like as ll
     orig = ll._linear
-    ll._linear = lambda m, x, ref_mod=None: (x.reshape(-1, x.shape[-1]).float() @ dense[id(m)].float()).half().reshape(x.shape[:-1] + (m.out_features,))
+    def dense_linear(m, x, ref_mod=None, residual=None):
+        y = (x.reshape(-1, x.shape[-1]).float() @ dense[id(m)].float()).half().reshape(x.shape[:-1] + (m.out_features,))
+        return y if residual is None else residual + y
+
+    ll._linear = dense_linear
+    fused = ll.FUSED_GLUE
+    ll.FUSED_GLUE = False            # the dense reference uses the plain torch expressions for norm / rope / silu / residual
     try:
         for blk in model.blocks:
             blk.cache_k.zero_(); blk.cache_v.zero_()
@@ -402,6 +460,7 @@ def test_llama_like_runner_matches_dense_fp16_model(ops):
         ref_nxt = model(ref_logits.argmax(-1).view(2, 1), torch.tensor([24], device="cuda"))
     finally:
         ll._linear = orig
+        ll.FUSED_GLUE = fused
     for a, b in ((logits, ref_logits), (nxt, ref_nxt)):
         rms = b.float().pow(2).mean().sqrt().item()
         assert (a.float() - b.float()).abs().max().item() <= 3e-2 * rms + 1e-3, "runner logits drifted from the dense model"
