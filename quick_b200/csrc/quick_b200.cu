@@ -289,6 +289,10 @@ __global__ void gemm_simt_kernel(const __half* __restrict__ A, const uint32_t* _
 
 // y = fp16( fp16( x * rsqrt(mean(x^2) + eps) ) * w ), statistics in fp32.  One CTA per row.
 __global__ void rmsnorm_kernel(const __half* __restrict__ x, const __half* __restrict__ w, __half* __restrict__ y, int H, float eps) {
+  // programmatic dependent launch: let the next kernel (usually a GEMM: barrier init, TMEM, weight prefetch) start
+  // now; our own input comes from the previous kernel, so wait for it before the first load
+  qb200::pdl_launch_dependents();
+  qb200::pdl_wait_prior_grid();
   const __half* xr = x + static_cast<size_t>(blockIdx.x) * H;
   __half* yr = y + static_cast<size_t>(blockIdx.x) * H;
   float ss = 0.f;
@@ -332,6 +336,8 @@ __global__ void rmsnorm_kernel(const __half* __restrict__ x, const __half* __res
 __global__ void rope_kv_kernel(const __half* __restrict__ qkv, const __half* __restrict__ cosb, const __half* __restrict__ sinb,
                                const long long* __restrict__ pos, __half* __restrict__ q_out, __half* __restrict__ cache_k,
                                __half* __restrict__ cache_v, int T, int nh, int nkv, int hd, int S) {
+  qb200::pdl_launch_dependents();
+  qb200::pdl_wait_prior_grid();
   const int head = blockIdx.x;            // 0 .. nh + 2 nkv - 1
   const int t = blockIdx.y, b = blockIdx.z;
   const int width = (nh + 2 * nkv) * hd;
@@ -354,6 +360,8 @@ __global__ void rope_kv_kernel(const __half* __restrict__ qkv, const __half* __r
 
 // act[M][I] = fp16( fp16(silu(g)) * u ),  gu = [g | u] per row ([M][2I]); silu in fp32 like torch's half kernel.
 __global__ void silu_mul_kernel(const __half* __restrict__ gu, __half* __restrict__ act, size_t M, int I) {
+  qb200::pdl_launch_dependents();
+  qb200::pdl_wait_prior_grid();
   const size_t idx = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   if (idx >= M * static_cast<size_t>(I)) return;
   const size_t m = idx / I;
@@ -423,6 +431,23 @@ bool use_pdl() {   // QB200_NO_PDL=1 disables programmatic dependent launch (A/B
   static int v = -1;
   if (v < 0) { const char* e = getenv("QB200_NO_PDL"); v = (e && e[0] == '1') ? 0 : 1; }
   return v == 1;
+}
+
+// Launch with the programmatic-stream-serialization attribute (the kernel must call griddepcontrol.wait before it
+// touches its inputs); plain launch when PDL is disabled.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 std::atomic<int> g_variant{0};         // tile-configuration variant (qb200_debug_set_variant): 0 = default
@@ -765,10 +790,9 @@ int qb200_rmsnorm(const void* x, const void* weight, void* y, int rows, int H, f
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(y)) & 15)
     return fail(QB200_EINVAL, "rmsnorm: pointers must be 16-byte aligned");
   const int threads = H >= 4096 ? 512 : H >= 1024 ? 128 : 64;
-  rmsnorm_kernel<<<rows, threads, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(weight),
-                                                         reinterpret_cast<__half*>(y), H, eps);
+  QB_CUDA(launch_pdl(rmsnorm_kernel, dim3(rows), dim3(threads), as_stream(stream), reinterpret_cast<const __half*>(x),
+                     reinterpret_cast<const __half*>(weight), reinterpret_cast<__half*>(y), H, eps));
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  QB_CUDA(cudaGetLastError());
   return QB200_OK;
 }
 
@@ -776,11 +800,11 @@ int qb200_rope_kv_update(const void* qkv, const void* cos_table, const void* sin
                          void* cache_k, void* cache_v, int B, int T, int nh, int nkv, int hd, int S, void* stream) {
   if (B <= 0 || T <= 0 || nh <= 0 || nkv <= 0 || hd <= 0 || hd % 2 != 0 || S <= 0) return fail(QB200_EINVAL, "rope_kv_update: bad dimensions");
   if (T > 65535 || B > 65535) return fail(QB200_EINVAL, "rope_kv_update: T and B must be <= 65535");
-  rope_kv_kernel<<<dim3(nh + 2 * nkv, T, B), hd >= 128 ? 128 : 64, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __half*>(qkv), reinterpret_cast<const __half*>(cos_table), reinterpret_cast<const __half*>(sin_table),
-      pos, reinterpret_cast<__half*>(q_out), reinterpret_cast<__half*>(cache_k), reinterpret_cast<__half*>(cache_v), T, nh, nkv, hd, S);
+  QB_CUDA(launch_pdl(rope_kv_kernel, dim3(nh + 2 * nkv, T, B), dim3(hd >= 128 ? 128 : 64), as_stream(stream),
+                     reinterpret_cast<const __half*>(qkv), reinterpret_cast<const __half*>(cos_table),
+                     reinterpret_cast<const __half*>(sin_table), pos, reinterpret_cast<__half*>(q_out),
+                     reinterpret_cast<__half*>(cache_k), reinterpret_cast<__half*>(cache_v), T, nh, nkv, hd, S));
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  QB_CUDA(cudaGetLastError());
   return QB200_OK;
 }
 
@@ -789,10 +813,9 @@ int qb200_silu_mul(const void* gate_up, void* act, long long rows, int I, void* 
   if (rows == 0) return QB200_OK;
   if ((reinterpret_cast<uintptr_t>(gate_up) | reinterpret_cast<uintptr_t>(act)) & 15) return fail(QB200_EINVAL, "silu_mul: pointers must be 16-byte aligned");
   const size_t vecs = static_cast<size_t>(rows) * I / 8;
-  silu_mul_kernel<<<static_cast<unsigned>((vecs + 255) / 256), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __half*>(gate_up), reinterpret_cast<__half*>(act), static_cast<size_t>(rows), I);
+  QB_CUDA(launch_pdl(silu_mul_kernel, dim3(static_cast<unsigned>((vecs + 255) / 256)), dim3(256), as_stream(stream),
+                     reinterpret_cast<const __half*>(gate_up), reinterpret_cast<__half*>(act), static_cast<size_t>(rows), I));
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  QB_CUDA(cudaGetLastError());
   return QB200_OK;
 }
 
