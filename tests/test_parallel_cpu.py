@@ -52,3 +52,24 @@ def test_column_parallel_allgather_world2_gloo():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), K, N, G, ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+def _runner_gather_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from quick_b200.awq.models.llama_like import _gather_columns, tp_world
+    local = (torch.arange(2 * 3 * 4, dtype=torch.float32).reshape(2, 3, 4) + 100 * rank).half()
+    full = _gather_columns(local)
+    want = torch.cat([(torch.arange(24, dtype=torch.float32).reshape(2, 3, 4) + 100 * r).half() for r in range(world)], dim=-1)
+    ret[rank] = bool(tp_world() == world and full.shape == (2, 3, 4 * world) and torch.equal(full, want))
+    dist.destroy_process_group()
+
+
+def test_runner_tensor_parallel_gather_world2_gloo():
+    """The runner's tensor-parallel reassembly (column slabs -> full width, rank-major order) on CPU."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_runner_gather_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
