@@ -175,6 +175,34 @@ def cpu_baseline(sample_sets=1):
             "seconds": dt}
 
 
+def model_tokens(world, rank):
+    """Second half of BASELINE.json's metric: Llama-2-7B AWQ w4 g128 tokens/s (random-init weights of that
+    architecture, prefill = decode = 128, the reference's examples/benchmark.py methodology) through the minimal
+    runner; with N > 1 ranks every linear is column-parallel with one NCCL all-gather (tensor parallel).
+    Reported beside the GEMM sweep, never mixed into `value`; failures are reported, not raised."""
+    try:
+        import copy
+        from quick_b200.awq.models.llama_like import PRESETS, LlamaLikeQuickModel, benchmark_generation
+        cfg = copy.deepcopy(PRESETS["llama-2-7b"])
+        cfg.max_seq_len = 256
+        for n_out in (cfg.hidden_size, 3 * cfg.hidden_size, 2 * cfg.intermediate_size):
+            if n_out % (128 * world) != 0:
+                return {"unsupported": f"N={n_out} does not split into {world} column shards of 128-channel tiles"}
+        rows = []
+        for bs in (1, 64):
+            torch.manual_seed(1234)
+            m = LlamaLikeQuickModel(cfg, bs)
+            r = benchmark_generation(m, 128, 128)
+            rows.append({"batch": bs, "decode_tokens_per_s": round(r["decode_tokens_per_s"], 1),
+                         "prefill_tokens_per_s": round(r["prefill_tokens_per_s"], 1), "decode_ms_per_step": round(r["decode_ms_per_step"], 3)})
+            del m
+            torch.cuda.empty_cache()
+        return {"model": "llama-2-7b shapes, random-init, w4 g128", "prefill": 128, "decode": 128, "tensor_parallel": world,
+                "cuda_graph_decode": True, "rows": rows}
+    except Exception as e:  # the GEMM sweep is the contract; the model leg must never take the JSON line down
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
 def run_mine(args):
     from quick_b200 import _lib, ops
     rank, world, local = dist_setup(args.gpus)
@@ -322,6 +350,7 @@ def run_mine(args):
         for h in handles:
             h.close()
 
+    model = model_tokens(world, rank) if args.model else None
     cpu = cpu_baseline() if (rank == 0 and world == 1 and args.cpu_baseline) else None
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 3), "unit": "TOPS", "n_gpus": world, "steps": args.steps,
@@ -333,7 +362,7 @@ def run_mine(args):
                                      "launches (each GEMM waits for its predecessor before loading activations)",
                            "parallelism": f"{world} x independent column shards of 4096 outputs (no collective)"},
                 "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "roofline_m1": roof_m1,
-                "sweep": sweep, "independent": independent, "cpu_baseline": cpu}
+                "sweep": sweep, "independent": independent, "llama2_7b_tokens_per_s": model, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
@@ -419,6 +448,7 @@ def main():
     ap.add_argument("--impl", default="quick_b200", choices=["quick_b200", "reference"])
     ap.add_argument("--no-e2e", dest="e2e", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-model", dest="model", action="store_false", help="skip the Llama-2-7B tokens/s leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
