@@ -102,6 +102,21 @@ int qb200_gemm_w4a16_fused(const void* A_fp16, const uint32_t* wq, const uint32_
                            const void* residual_fp16_or_null, void* C_fp16, int M, int K, int N, int G, int tok, int split,
                            unsigned flags, void* stream);
 
+/* Fused GEMM + all-gather for column-parallel (tensor-parallel) linears: this rank computes its N output columns and the
+ * epilogue stores the slab straight into the full-width buffers of ALL ranks — C_peers[r] is rank r's [rows][ld_c] buffer
+ * mapped into this process (CUDA IPC / torch symmetric memory; C_peers[rank] is the local one), the slab lands at column
+ * col0 (= rank * N) — so the transfer over NVLink rides on the GEMM's own stores instead of a separate NCCL all-gather and
+ * re-layout copy.  residual (optional) is this rank's local full-width [rows][ld_c] tensor, read at the same columns.
+ * Follow it with qb200_peer_barrier on the same stream before anything reads the gathered rows.  The reference has no
+ * multi-GPU path for this operator; the NCCL baseline is quick_b200/parallel.py. */
+int qb200_gemm_w4a16_allgather(const void* A_fp16, const uint32_t* wq, const uint32_t* sz, const void* bias_fp16_or_null,
+                               const void* residual_fp16_or_null, void* const* C_peers, int n_peers, int ld_c, int col0,
+                               int M, int K, int N, int G, int tok, int split, unsigned flags, void* stream);
+/* All ranks meet: rank publishes a fresh epoch (device counter *epoch_counter, bumped by the kernel) into slot [rank] of
+ * every peer's flag array and waits for all n_peers slots of its own array.  flag_arrays[r] = rank r's array of >= n_peers
+ * zero-initialised uint32 in peer-mapped memory.  Traps after ~2 s instead of hanging if a peer never arrives. */
+int qb200_peer_barrier(unsigned* epoch_counter, unsigned* const* flag_arrays, int rank, int n_peers, void* stream);
+
 /* Reports the configuration qb200_gemm_w4a16 would pick. */
 int qb200_gemm_plan(int M, int K, int N, int G, int split_k_hint, int* tok, int* split, int* ctas);
 /* Same for a given set of launch flags (the independent plan never splits K). */

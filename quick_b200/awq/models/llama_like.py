@@ -99,10 +99,23 @@ def _gather_columns(local: torch.Tensor) -> torch.Tensor:
     return gathered.view(R, flat.shape[0], n_local).permute(1, 0, 2).reshape(lead + (R * n_local,))
 
 
+# Tensor-parallel exchange: "peer" = fused GEMM + all-gather over peer memory (quick_b200.parallel.PeerGatherWorkspace),
+# "nccl" = kernel + one all_gather_into_tensor + re-layout copy (the baseline).  QB200_TP_MODE selects.
+import os as _os
+TP_MODE = _os.environ.get("QB200_TP_MODE", "peer")
+
+
 def _linear(m: WQLinear_QUICK, x, ref_mod=None, residual=None):
     """Route through the B200 kernel, or (baseline runs only) through the unmodified reference kernel.
-    residual: returns residual + linear(x) (fused into the GEMM epilogue unless the output is column-sharded)."""
+    residual: returns residual + linear(x) (fused into the GEMM epilogue)."""
     if ref_mod is None:
+        ws = getattr(m, "peer_ws", None)
+        if ws is not None:
+            wq, sz = m._prepacked()
+            x2d = x.reshape(-1, x.shape[-1])
+            res2d = None if residual is None else residual.reshape(-1, ws.n_total)
+            y = ws.gemm(x2d, wq, sz, m.out_features, m.group_size, bias=m.bias, residual=res2d)
+            return y.reshape(x.shape[:-1] + (ws.n_total,))
         if getattr(m, "tp_sharded", False):
             y = _gather_columns(m(x))
             return y if residual is None else residual + y
@@ -114,7 +127,7 @@ def _linear(m: WQLinear_QUICK, x, ref_mod=None, residual=None):
 
 
 class Block(nn.Module):
-    def __init__(self, cfg: LlamaLikeConfig, dev, gen, batch: int):
+    def __init__(self, cfg: LlamaLikeConfig, dev, gen, batch: int, peer_ws=None):
         super().__init__()
         self.cfg = cfg
         hd, nh, nkv = cfg.head_dim, cfg.num_heads, cfg.num_kv_heads
@@ -129,6 +142,8 @@ class Block(nn.Module):
             assert out_f % (128 * R) == 0, f"N={out_f} does not split into {R} shards of 128-column tiles"
             m = random_quick_linear(in_f, out_f // R, cfg.group_size, dev, gen)
             m.tp_sharded = R > 1
+            if R > 1 and TP_MODE == "peer":
+                m.peer_ws = peer_ws(out_f)       # one workspace per projection width, shared by all layers
             return m
 
         self.qkv_proj = lin(cfg.hidden_size, (nh + 2 * nkv) * hd)
@@ -178,7 +193,17 @@ class LlamaLikeQuickModel(nn.Module):
         rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
         gen = torch.Generator(device=dev); gen.manual_seed(seed + 1000 * rank)   # every rank draws its own column slabs
         self.embed = nn.Embedding(cfg.vocab_size, cfg.hidden_size, device=dev, dtype=torch.float16)
-        self.blocks = nn.ModuleList([Block(cfg, dev, gen, batch) for _ in range(cfg.num_layers)])
+        # tensor parallel, peer mode: one symmetric full-width output buffer per projection width (rows = the largest
+        # token count a forward can carry), shared by all layers — consecutive uses are separated by other barriers
+        self._peer_ws = {}
+
+        def peer_ws(n_total):
+            if n_total not in self._peer_ws:
+                from ...parallel import PeerGatherWorkspace
+                self._peer_ws[n_total] = PeerGatherWorkspace(batch * cfg.max_seq_len, n_total)
+            return self._peer_ws[n_total]
+
+        self.blocks = nn.ModuleList([Block(cfg, dev, gen, batch, peer_ws) for _ in range(cfg.num_layers)])
         self.norm = RMSNorm(cfg.hidden_size, cfg.rms_eps, dev)
         self.lm_head = nn.Linear(cfg.hidden_size, cfg.vocab_size, bias=False, device=dev, dtype=torch.float16)
         inv = 1.0 / (cfg.rope_theta ** (torch.arange(0, cfg.head_dim, 2, device=dev).float() / cfg.head_dim))

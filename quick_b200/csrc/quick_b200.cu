@@ -380,6 +380,30 @@ __global__ void silu_mul_kernel(const __half* __restrict__ gu, __half* __restric
   *reinterpret_cast<uint4*>(act + idx) = o;
 }
 
+// Cross-GPU hand-over for the fused all-gather: every rank bumps its own epoch counter, publishes the epoch in its slot
+// of every peer's flag array (peer-mapped memory) and waits until all peers have published the same epoch in ITS array.
+// Launched right behind the GEMM on the same stream: the GEMM's peer stores are complete (kernel boundary) before the
+// flags go out, and whatever runs next on this stream sees every peer's slab.  The epoch lives on the device, so a
+// CUDA-graph replay hands out fresh epochs.
+struct PeerFlagPtrs { unsigned* p[8]; };
+__global__ void peer_barrier_kernel(unsigned* epoch_counter, PeerFlagPtrs flags, int rank, int n_peers) {
+  __shared__ unsigned e_sh;
+  if (threadIdx.x == 0) e_sh = atomicAdd(epoch_counter, 1u) + 1u;
+  __syncthreads();
+  const unsigned e = e_sh;
+  if (threadIdx.x < n_peers) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags.p[threadIdx.x] + rank), "r"(e) : "memory");
+    const unsigned* mine = flags.p[rank] + threadIdx.x;
+    const long long t0 = clock64();
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if (clock64() - t0 > 4000000000ll) __trap();   // ~2 s: a lost peer traps instead of hanging the GPU
+    } while (static_cast<int>(v - e) < 0);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Tensor-map encode (driver entry point fetched through the runtime: no link-time libcuda dependency)
 // ------------------------------------------------------------------------------------------------
@@ -564,6 +588,12 @@ void plan(int M, int K, int N, int split_hint, unsigned flags, int* tok_out, int
 
 }  // namespace
 
+namespace {
+int gemm_impl(const void* A, const uint32_t* wq, const uint32_t* sz, const void* bias, const void* residual, void* C,
+              void* const* C_peers, int n_peers, int ld_c, int col0, int M, int K, int N, int G, int tok, int split,
+              unsigned flags, void* stream);
+}
+
 // ------------------------------------------------------------------------------------------------
 // C-ABI
 // ------------------------------------------------------------------------------------------------
@@ -694,6 +724,25 @@ int qb200_gemm_w4a16_ex(const void* A, const uint32_t* wq, const uint32_t* sz, c
 
 int qb200_gemm_w4a16_fused(const void* A, const uint32_t* wq, const uint32_t* sz, const void* bias, const void* residual,
                            void* C, int M, int K, int N, int G, int tok, int split, unsigned flags, void* stream) {
+  return gemm_impl(A, wq, sz, bias, residual, C, nullptr, 0, N, 0, M, K, N, G, tok, split, flags, stream);
+}
+
+int qb200_gemm_w4a16_allgather(const void* A, const uint32_t* wq, const uint32_t* sz, const void* bias, const void* residual,
+                               void* const* C_peers, int n_peers, int ld_c, int col0, int M, int K, int N, int G, int tok,
+                               int split, unsigned flags, void* stream) {
+  if (n_peers < 1 || n_peers > 8 || C_peers == nullptr) return fail(QB200_EINVAL, "allgather: 1..8 peer buffers required");
+  if (ld_c < col0 + N || col0 < 0 || (ld_c % 8) != 0 || (col0 % 8) != 0) return fail(QB200_EINVAL, "allgather: bad ld_c / col0");
+  for (int p = 0; p < n_peers; ++p)
+    if (C_peers[p] == nullptr || (reinterpret_cast<uintptr_t>(C_peers[p]) & 15)) return fail(QB200_EINVAL, "allgather: peer buffer %d is null or unaligned", p);
+  return gemm_impl(A, wq, sz, bias, residual, nullptr, C_peers, n_peers, ld_c, col0, M, K, N, G, tok, split, flags, stream);
+}
+
+}  // extern "C" (reopened below)
+
+namespace {
+int gemm_impl(const void* A, const uint32_t* wq, const uint32_t* sz, const void* bias, const void* residual, void* C,
+              void* const* C_peers, int n_peers, int ld_c, int col0, int M, int K, int N, int G, int tok, int split,
+              unsigned flags, void* stream) {
   int rc = qb200_check_shape(M, K, N, G);
   if (rc) return rc;
   if (M == 0) return QB200_OK;
@@ -710,6 +759,7 @@ int qb200_gemm_w4a16_fused(const void* A, const uint32_t* wq, const uint32_t* sz
     return fail(QB200_EINVAL, "A and wq must be 16-byte aligned");
   if (residual != nullptr && ((reinterpret_cast<uintptr_t>(residual) & 15) || (reinterpret_cast<uintptr_t>(C) & 15)))
     return fail(QB200_EINVAL, "residual and C must be 16-byte aligned");
+  if ((ld_c % 8) != 0 && (residual != nullptr || n_peers > 0)) return fail(QB200_EINVAL, "row stride must be a multiple of 8");
   const int KB = K / 64;
   if (split < 1 || split > KB) return fail(QB200_EINVAL, "split %d out of range for K=%d", split, K);
   const int kbps = (KB + split - 1) / split;
@@ -726,6 +776,10 @@ int qb200_gemm_w4a16_fused(const void* A, const uint32_t* wq, const uint32_t* sz
   args.bias = reinterpret_cast<const __half*>(bias);
   args.residual = reinterpret_cast<const __half*>(residual);
   args.C = reinterpret_cast<__half*>(C);
+  args.n_peers = n_peers;
+  args.ldc = ld_c;
+  args.col0 = col0;
+  for (int p = 0; p < 8; ++p) args.peerC[p] = p < n_peers ? reinterpret_cast<__half*>(C_peers[p]) : nullptr;
   args.M = M;
   args.K = K;
   args.N = N;
@@ -744,6 +798,9 @@ int qb200_gemm_w4a16_fused(const void* A, const uint32_t* wq, const uint32_t* sz
   }
   return fail(QB200_EINVAL, "unsupported token tile %d", tok);
 }
+}  // namespace
+
+extern "C" {
 
 int qb200_gemm_w4a16(const void* A, const uint32_t* wq, const uint32_t* sz, const void* bias, void* C, int M, int K,
                      int N, int G, int split_k_hint, void* stream) {
@@ -779,6 +836,20 @@ int qb200_gemm_w4a16_simt(const void* A, const uint32_t* wq, const uint32_t* sz,
   }
   gemm_simt_kernel<<<dim3(N / 128, M), 128, static_cast<size_t>(K) * 2, as_stream(stream)>>>(
       reinterpret_cast<const __half*>(A), wq, sz, reinterpret_cast<__half*>(C), M, K, N, G);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  QB_CUDA(cudaGetLastError());
+  return QB200_OK;
+}
+
+int qb200_peer_barrier(unsigned* epoch_counter, unsigned* const* flag_arrays, int rank, int n_peers, void* stream) {
+  if (n_peers < 1 || n_peers > 8 || rank < 0 || rank >= n_peers || epoch_counter == nullptr || flag_arrays == nullptr)
+    return fail(QB200_EINVAL, "peer_barrier: bad arguments");
+  PeerFlagPtrs f{};
+  for (int p = 0; p < n_peers; ++p) {
+    if (flag_arrays[p] == nullptr) return fail(QB200_EINVAL, "peer_barrier: null flag array %d", p);
+    f.p[p] = flag_arrays[p];
+  }
+  peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(epoch_counter, f, rank, n_peers);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   QB_CUDA(cudaGetLastError());
   return QB200_OK;

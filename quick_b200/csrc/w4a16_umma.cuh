@@ -384,6 +384,11 @@ struct GemmArgs {
   const __half* bias;
   const __half* residual;   // optional [M][N] fp16: C = residual + fp16(A·W + bias), the add in fp16 like torch's x + linear(x)
   __half* C;
+  // Fused all-gather (column-parallel linears): the output slab is stored into the buffers of ALL n_peers ranks
+  // (peer-mapped pointers, this rank's included) at column offset col0 of rows ldc wide; plain GEMM: n_peers = 0,
+  // ldc = N, col0 = 0 and C is the only destination.
+  __half* peerC[8];
+  int n_peers, ldc, col0;
   int M, K, N, G;
   int kb_per_split;   // k64 blocks per cluster rank
   unsigned flags;     // QB200_GEMM_* (include/quick_b200.h)
@@ -893,10 +898,11 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
           for (int i = 0; i < PIECE; ++i) {
             const int m = m_base + j0 + i;
             if (m < args.M) {
-              const size_t off = static_cast<size_t>(m) * args.N + n0 + ch;
+              const size_t off = static_cast<size_t>(m) * args.ldc + args.col0 + n0 + ch;
               __half h = __float2half_rn(acc[i]);
               if (args.residual != nullptr) h = __hadd(args.residual[off], h);
-              args.C[off] = h;
+              if (args.n_peers == 0) args.C[off] = h;
+              else for (int p = 0; p < args.n_peers; ++p) args.peerC[p][off] = h;
             }
           }
         } else {
@@ -914,9 +920,10 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
           const int m = m_base + row;
           if (m < args.M) {
             uint4 v = lds128(smem_out + static_cast<uint32_t>(row * kChan * 2 + chunk * 16));
-            const size_t off = static_cast<size_t>(m) * args.N + n0 + chunk * 8;
+            const size_t off = static_cast<size_t>(m) * args.ldc + args.col0 + n0 + chunk * 8;
             if (args.residual != nullptr) v = hadd2x4(*reinterpret_cast<const uint4*>(args.residual + off), v);
-            *reinterpret_cast<uint4*>(args.C + off) = v;
+            if (args.n_peers == 0) *reinterpret_cast<uint4*>(args.C + off) = v;
+            else for (int p = 0; p < args.n_peers; ++p) *reinterpret_cast<uint4*>(args.peerC[p] + off) = v;
           }
         }
       }
@@ -1016,9 +1023,10 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
         const int m = m_base + row;
         if (m < args.M) {
           uint4 v = lds128(smem_out + static_cast<uint32_t>(row * kChan * 2 + chunk * 16));
-          const size_t off = static_cast<size_t>(m) * args.N + n0 + chunk * 8;
+          const size_t off = static_cast<size_t>(m) * args.ldc + args.col0 + n0 + chunk * 8;
           if (args.residual != nullptr) v = hadd2x4(*reinterpret_cast<const uint4*>(args.residual + off), v);
-          *reinterpret_cast<uint4*>(args.C + off) = v;
+          if (args.n_peers == 0) *reinterpret_cast<uint4*>(args.C + off) = v;
+          else for (int p = 0; p < args.n_peers; ++p) *reinterpret_cast<uint4*>(args.peerC[p] + off) = v;
         }
       }
       if (threadIdx.x == 0) QB_TRACE(3, 0, 3);

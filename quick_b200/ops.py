@@ -139,6 +139,31 @@ def gemm(x: torch.Tensor, wq: torch.Tensor, sz: torch.Tensor, N: int, G: int, bi
     return out
 
 
+def gemm_allgather(x: torch.Tensor, wq: torch.Tensor, sz: torch.Tensor, N: int, G: int, peer_ptrs, ld_c: int, col0: int,
+                   bias: torch.Tensor | None = None, residual: torch.Tensor | None = None, independent: bool = False) -> None:
+    """Fused GEMM + all-gather: this rank's [M, N] slab goes to column col0 of every peer buffer (peer_ptrs: device
+    pointers of the [rows, ld_c] buffers of all ranks, mapped into this process).  See quick_b200.parallel."""
+    _require_cuda(x, wq, sz, bias, residual)
+    lib = _lib.load()
+    assert x.dim() == 2 and x.dtype == torch.float16
+    x = x.contiguous()
+    M, K = x.shape
+    if residual is not None:
+        assert residual.is_contiguous() and residual.dtype == torch.float16 and tuple(residual.shape) == (M, ld_c)
+    arr = (C.c_void_p * len(peer_ptrs))(*peer_ptrs)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.qb200_gemm_w4a16_allgather(_ptr(x), _ptr(wq), _ptr(sz), _ptr(bias), _ptr(residual), arr, len(peer_ptrs), ld_c,
+                                                  col0, M, K, N, G, 0, 0, 1 if independent else 0, _stream_ptr()))
+
+
+def peer_barrier(epoch: torch.Tensor, flag_ptrs, rank: int) -> None:
+    """qb200_peer_barrier on the current stream (epoch: 1-element int32 device tensor owned by the caller)."""
+    lib = _lib.load()
+    arr = (C.c_void_p * len(flag_ptrs))(*flag_ptrs)
+    with torch.cuda.device(epoch.device):
+        _lib.check(lib.qb200_peer_barrier(_ptr(epoch), arr, rank, len(flag_ptrs), _stream_ptr()))
+
+
 def gemm_simt(x: torch.Tensor, wq: torch.Tensor, sz: torch.Tensor, N: int, G: int) -> torch.Tensor:
     """CUDA-core cross-check of the same contraction (tests only)."""
     _require_cuda(x, wq, sz)

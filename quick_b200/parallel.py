@@ -67,3 +67,51 @@ class ColumnParallelQuickLinear(torch.nn.Module):
         # rank-major slabs -> natural column order
         out = gathered.view(self.world, M, self.shard.n_local).permute(1, 0, 2).reshape(M, self.shard.n_total)
         return out.reshape(x.shape[:-1] + (self.shard.n_total,))
+
+
+class PeerGatherWorkspace:
+    """Fused GEMM + all-gather over peer memory (C-ABI qb200_gemm_w4a16_allgather + qb200_peer_barrier).
+
+    One full-width [max_rows, n_total] fp16 output buffer per rank in torch symmetric memory (every rank's buffer is
+    mapped into every process), a small symmetric flag array and a device epoch counter.  `gemm()` makes this rank's
+    GEMM store its column slab into all ranks' buffers and then meets the peers; the returned tensor is a view of the
+    local buffer holding the complete rows in natural column order — no NCCL call, no re-layout copy.
+    A workspace may be shared by calls that are separated by at least one other peer barrier (e.g. one workspace
+    per projection type of a decoder layer): the barrier in between proves every rank is done reading the old rows."""
+
+    def __init__(self, max_rows: int, n_total: int, group=None, device=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        if not (1 <= self.world <= 8):
+            raise ValueError("peer gather supports 1..8 ranks (one NVLink domain)")
+        device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.max_rows, self.n_total = max_rows, n_total
+        self.buf = symm_mem.empty((max_rows, n_total), dtype=torch.float16, device=device)
+        self.flags = symm_mem.empty(64, dtype=torch.int32, device=device)
+        self.flags.zero_()
+        hb = symm_mem.rendezvous(self.buf, self.group)
+        hf = symm_mem.rendezvous(self.flags, self.group)
+        self.buf_ptrs = [int(p) for p in hb.buffer_ptrs]
+        self.flag_ptrs = [int(p) for p in hf.buffer_ptrs]
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        self._handles = (hb, hf)
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)          # every rank's flags are zero before anybody signals
+
+    def gemm(self, x2d: torch.Tensor, wq: torch.Tensor, sz: torch.Tensor, n_local: int, G: int, bias=None, residual=None):
+        """x2d [M, K] fp16 -> view [M, n_total] of the local buffer with every rank's slab in place.
+        residual: local full-width [M, n_total] tensor added to this rank's columns before they are sent."""
+        from . import ops
+        M = x2d.shape[0]
+        if M > self.max_rows:
+            raise ValueError(f"M={M} exceeds the workspace ({self.max_rows} rows)")
+        ops.gemm_allgather(x2d, wq, sz, n_local, G, self.buf_ptrs, self.n_total, self.rank * n_local, bias=bias, residual=residual)
+        ops.peer_barrier(self.epoch, self.flag_ptrs, self.rank)
+        return self.buf[:M]
+
+    def release(self):
+        """Extra meeting point: call after the last read of the gathered rows when the NEXT use of this workspace
+        is not separated from this one by another peer barrier (back-to-back calls on one workspace)."""
+        from . import ops
+        ops.peer_barrier(self.epoch, self.flag_ptrs, self.rank)

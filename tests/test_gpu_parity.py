@@ -426,6 +426,49 @@ def test_decoder_glue_kernels_match_the_torch_expressions(ops):
         assert torch.equal(fused, res + plain), M
 
 
+def test_fused_allgather_stores_on_one_gpu(ops):
+    """qb200_gemm_w4a16_allgather with the 'peers' being several local buffers: every destination receives the slab at
+    column col0 of ld_c-wide rows (all epilogue paths), the rest of the rows is untouched, the fused residual is read at
+    the same columns; qb200_peer_barrier with a single rank returns."""
+    K, N, G = 1024, 512, 128
+    q_, z_, s_, qw, qz, sc, W16 = make_gpu_case(ops, K, N, G)
+    wq, sz, *_ = ops.prepack(qw, qz, sc)
+    ld, col0 = 3 * N, N
+    for M in (1, 16, 40, 100, 300):
+        x = torch.from_numpy(qo.make_activations(M, K, seed=M)).cuda()
+        plain = ops.gemm(x, wq, sz, N, G)
+        bufs = [torch.full((M, ld), 7.0, device="cuda", dtype=torch.float16) for _ in range(3)]
+        ops.gemm_allgather(x, wq, sz, N, G, [b.data_ptr() for b in bufs], ld, col0)
+        for b in bufs:
+            assert torch.equal(b[:, col0:col0 + N], plain), M
+            assert (b[:, :col0] == 7).all() and (b[:, col0 + N:] == 7).all()
+        res = torch.randn(M, ld, device="cuda").half()
+        out = torch.zeros(M, ld, device="cuda", dtype=torch.float16)
+        ops.gemm_allgather(x, wq, sz, N, G, [out.data_ptr()], ld, col0, residual=res)
+        assert torch.equal(out[:, col0:col0 + N], res[:, col0:col0 + N] + plain), M
+    flags = torch.zeros(64, dtype=torch.int32, device="cuda")
+    epoch = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for i in range(3):
+        ops.peer_barrier(epoch, [flags.data_ptr()], 0)
+    torch.cuda.synchronize()
+    assert epoch.item() == 3 and flags[0].item() == 3
+    with pytest.raises(ValueError):
+        ops.gemm_allgather(x, wq, sz, N, G, [out.data_ptr()], N - 8, 0)      # ld_c < col0 + N
+
+
+def test_fused_allgather_two_gpus_matches_nccl():
+    """2 ranks (torchrun): fused GEMM + all-gather over peer memory == kernel + NCCL all-gather, eager and under
+    CUDA-graph replay (tools/tp_check.py).  Skipped on a single-GPU box."""
+    import subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29577", os.path.join(root, "tools", "tp_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "TP_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_llama_like_runner_matches_dense_fp16_model(ops):
     """the minimal runner (all linears through the tcgen05 kernel, CUDA-graph-free here) against
     the same network with every WQLinear_QUICK replaced by its dequantised fp16 weight and torch.matmul."""
