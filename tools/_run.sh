@@ -1,5 +1,9 @@
 mkdir -p gpurun_out
-( time timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 tools/tp_check.py ) > gpurun_out/tp_check.log 2>&1; rc=$?; echo "tp_check rc=$rc"; grep -v "^\[W\|Warning" gpurun_out/tp_check.log | tail -25 | cut -c1-200
-[ $rc -ne 0 ] && exit 1
-( time timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29542 tools/bench_model.py --model llama-2-70b --batch 1 8 32 --out gpurun_out/model_llama2_70b_tp2_peer.json ) > gpurun_out/model_70b_tp2_peer.log 2>&1; echo "70b peer rc=$?"; grep '^{' gpurun_out/model_70b_tp2_peer.log | cut -c1-230; tail -3 gpurun_out/model_70b_tp2_peer.log | cut -c1-200
-( time timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29543 tools/bench_model.py --model llama-2-7b --batch 1 64 --out gpurun_out/model_llama2_7b_tp2_peer.json ) > gpurun_out/model_7b_tp2_peer.log 2>&1; echo "7b peer rc=$?"; grep '^{' gpurun_out/model_7b_tp2_peer.log | cut -c1-230
+N=$(nvidia-smi -L | wc -l); echo "gpus=$N"
+( time timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29551 tools/tp_check.py ) > gpurun_out/tp_check_n$N.log 2>&1; echo "tp_check rc=$?"; grep "TP_CHECK\|False" gpurun_out/tp_check_n$N.log | head
+( time timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29552 bench.py --gpus $N --steps 10 --warmup 3 ) > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err; echo "bench rc=$?"; tail -2 gpurun_out/bench_${N}gpu.err
+python - <<PY
+import json
+d=json.loads([l for l in open('gpurun_out/bench_${N}gpu.json').read().strip().splitlines() if l.startswith('{')][-1])
+print(d['n_gpus'], d['value'], d['e2e']['value'], d['independent']['value'], d['llama2_7b_tokens_per_s'])
+PY
