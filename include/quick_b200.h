@@ -107,11 +107,14 @@ int qb200_gemm_w4a16_fused(const void* A_fp16, const uint32_t* wq, const uint32_
  * mapped into this process (CUDA IPC / torch symmetric memory; C_peers[rank] is the local one), the slab lands at column
  * col0 (= rank * N) — so the transfer over NVLink rides on the GEMM's own stores instead of a separate NCCL all-gather and
  * re-layout copy.  residual (optional) is this rank's local full-width [rows][ld_c] tensor, read at the same columns.
+ * C_multicast (optional): the NVSwitch multicast mapping of the same buffers (torch symmetric memory `multicast_ptr`);
+ * when given, every store is ONE multimem.st that the switch replicates to all ranks instead of a loop over C_peers.
  * Follow it with qb200_peer_barrier on the same stream before anything reads the gathered rows.  The reference has no
  * multi-GPU path for this operator; the NCCL baseline is quick_b200/parallel.py. */
 int qb200_gemm_w4a16_allgather(const void* A_fp16, const uint32_t* wq, const uint32_t* sz, const void* bias_fp16_or_null,
-                               const void* residual_fp16_or_null, void* const* C_peers, int n_peers, int ld_c, int col0,
-                               int M, int K, int N, int G, int tok, int split, unsigned flags, void* stream);
+                               const void* residual_fp16_or_null, void* const* C_peers, void* C_multicast_or_null,
+                               int n_peers, int ld_c, int col0, int M, int K, int N, int G, int tok, int split,
+                               unsigned flags, void* stream);
 /* All ranks meet: rank publishes a fresh epoch (device counter *epoch_counter, bumped by the kernel) into slot [rank] of
  * every peer's flag array and waits for all n_peers slots of its own array.  flag_arrays[r] = rank r's array of >= n_peers
  * zero-initialised uint32 in peer-mapped memory.  Traps after ~2 s instead of hanging if a peer never arrives. */

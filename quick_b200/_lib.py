@@ -58,7 +58,7 @@ def load() -> C.CDLL:
     lib.qb200_gemm_w4a16_ex.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, C.c_uint, vp]
     lib.qb200_gemm_plan.argtypes = [i32, i32, i32, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.qb200_gemm_w4a16_fused.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, C.c_uint, vp]
-    lib.qb200_gemm_w4a16_allgather.argtypes = [vp, vp, vp, vp, vp, C.POINTER(vp), i32, i32, i32, i32, i32, i32, i32, i32, i32, C.c_uint, vp]
+    lib.qb200_gemm_w4a16_allgather.argtypes = [vp, vp, vp, vp, vp, C.POINTER(vp), vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, C.c_uint, vp]
     lib.qb200_peer_barrier.argtypes = [vp, C.POINTER(vp), i32, i32, vp]
     lib.qb200_rmsnorm.argtypes = [vp, vp, vp, i32, i32, C.c_float, vp]
     lib.qb200_rope_kv_update.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]

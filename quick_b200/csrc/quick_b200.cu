@@ -728,13 +728,14 @@ int qb200_gemm_w4a16_fused(const void* A, const uint32_t* wq, const uint32_t* sz
 }
 
 int qb200_gemm_w4a16_allgather(const void* A, const uint32_t* wq, const uint32_t* sz, const void* bias, const void* residual,
-                               void* const* C_peers, int n_peers, int ld_c, int col0, int M, int K, int N, int G, int tok,
-                               int split, unsigned flags, void* stream) {
+                               void* const* C_peers, void* C_multicast, int n_peers, int ld_c, int col0, int M, int K, int N,
+                               int G, int tok, int split, unsigned flags, void* stream) {
   if (n_peers < 1 || n_peers > 8 || C_peers == nullptr) return fail(QB200_EINVAL, "allgather: 1..8 peer buffers required");
   if (ld_c < col0 + N || col0 < 0 || (ld_c % 8) != 0 || (col0 % 8) != 0) return fail(QB200_EINVAL, "allgather: bad ld_c / col0");
   for (int p = 0; p < n_peers; ++p)
     if (C_peers[p] == nullptr || (reinterpret_cast<uintptr_t>(C_peers[p]) & 15)) return fail(QB200_EINVAL, "allgather: peer buffer %d is null or unaligned", p);
-  return gemm_impl(A, wq, sz, bias, residual, nullptr, C_peers, n_peers, ld_c, col0, M, K, N, G, tok, split, flags, stream);
+  if (C_multicast != nullptr && (reinterpret_cast<uintptr_t>(C_multicast) & 15)) return fail(QB200_EINVAL, "allgather: multicast pointer unaligned");
+  return gemm_impl(A, wq, sz, bias, residual, C_multicast, C_peers, n_peers, ld_c, col0, M, K, N, G, tok, split, flags, stream);
 }
 
 }  // extern "C" (reopened below)
@@ -775,7 +776,8 @@ int gemm_impl(const void* A, const uint32_t* wq, const uint32_t* sz, const void*
   args.sz = sz;
   args.bias = reinterpret_cast<const __half*>(bias);
   args.residual = reinterpret_cast<const __half*>(residual);
-  args.C = reinterpret_cast<__half*>(C);
+  args.C = n_peers > 0 ? nullptr : reinterpret_cast<__half*>(C);
+  args.mcC = n_peers > 0 ? reinterpret_cast<__half*>(C) : nullptr;   // gemm_impl's C doubles as the multicast pointer in peer mode
   args.n_peers = n_peers;
   args.ldc = ld_c;
   args.col0 = col0;

@@ -388,6 +388,7 @@ struct GemmArgs {
   // (peer-mapped pointers, this rank's included) at column offset col0 of rows ldc wide; plain GEMM: n_peers = 0,
   // ldc = N, col0 = 0 and C is the only destination.
   __half* peerC[8];
+  __half* mcC;        // optional NVSwitch multicast mapping of the same buffers: ONE multimem.st reaches every rank
   int n_peers, ldc, col0;
   int M, K, N, G;
   int kb_per_split;   // k64 blocks per cluster rank
@@ -503,6 +504,15 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
 }
 __device__ __forceinline__ float2 unpack_half2(uint32_t v) {
   return __half22float2(*reinterpret_cast<__half2*>(&v));
+}
+// NVSwitch multicast stores (multimem.st on a multicast mapping: the switch replicates the write to every rank's copy)
+__device__ __forceinline__ void multimem_st_v4(void* p, uint4 v) {
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)),
+               "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+               : "memory");
+}
+__device__ __forceinline__ void multimem_st_b32(void* p, uint32_t v) {
+  asm volatile("multimem.st.weak.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 // a + b on eight packed fp16 values (residual + GEMM result, one rounding each like torch's fp16 add)
 __device__ __forceinline__ uint4 hadd2x4(uint4 a, uint4 b) {
@@ -901,8 +911,16 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
               const size_t off = static_cast<size_t>(m) * args.ldc + args.col0 + n0 + ch;
               __half h = __float2half_rn(acc[i]);
               if (args.residual != nullptr) h = __hadd(args.residual[off], h);
-              if (args.n_peers == 0) args.C[off] = h;
-              else for (int p = 0; p < args.n_peers; ++p) args.peerC[p][off] = h;
+              if (args.n_peers == 0) {
+                args.C[off] = h;
+              } else if (args.mcC != nullptr) {
+                // multimem.st moves at least 32 bits: even lanes store their channel and the next one
+                const uint32_t mine = __half_as_ushort(h);
+                const uint32_t next = __shfl_down_sync(0xffffffffu, mine, 1);
+                if ((lane & 1) == 0) multimem_st_b32(args.mcC + off, mine | (next << 16));
+              } else {
+                for (int p = 0; p < args.n_peers; ++p) args.peerC[p][off] = h;
+              }
             }
           }
         } else {
@@ -923,6 +941,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
             const size_t off = static_cast<size_t>(m) * args.ldc + args.col0 + n0 + chunk * 8;
             if (args.residual != nullptr) v = hadd2x4(*reinterpret_cast<const uint4*>(args.residual + off), v);
             if (args.n_peers == 0) *reinterpret_cast<uint4*>(args.C + off) = v;
+            else if (args.mcC != nullptr) multimem_st_v4(args.mcC + off, v);
             else for (int p = 0; p < args.n_peers; ++p) *reinterpret_cast<uint4*>(args.peerC[p] + off) = v;
           }
         }
@@ -1026,6 +1045,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
           const size_t off = static_cast<size_t>(m) * args.ldc + args.col0 + n0 + chunk * 8;
           if (args.residual != nullptr) v = hadd2x4(*reinterpret_cast<const uint4*>(args.residual + off), v);
           if (args.n_peers == 0) *reinterpret_cast<uint4*>(args.C + off) = v;
+          else if (args.mcC != nullptr) multimem_st_v4(args.mcC + off, v);
           else for (int p = 0; p < args.n_peers; ++p) *reinterpret_cast<uint4*>(args.peerC[p] + off) = v;
         }
       }

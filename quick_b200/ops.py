@@ -140,7 +140,8 @@ def gemm(x: torch.Tensor, wq: torch.Tensor, sz: torch.Tensor, N: int, G: int, bi
 
 
 def gemm_allgather(x: torch.Tensor, wq: torch.Tensor, sz: torch.Tensor, N: int, G: int, peer_ptrs, ld_c: int, col0: int,
-                   bias: torch.Tensor | None = None, residual: torch.Tensor | None = None, independent: bool = False) -> None:
+                   bias: torch.Tensor | None = None, residual: torch.Tensor | None = None, independent: bool = False,
+                   multicast_ptr: int | None = None) -> None:
     """Fused GEMM + all-gather: this rank's [M, N] slab goes to column col0 of every peer buffer (peer_ptrs: device
     pointers of the [rows, ld_c] buffers of all ranks, mapped into this process).  See quick_b200.parallel."""
     _require_cuda(x, wq, sz, bias, residual)
@@ -152,8 +153,8 @@ def gemm_allgather(x: torch.Tensor, wq: torch.Tensor, sz: torch.Tensor, N: int, 
         assert residual.is_contiguous() and residual.dtype == torch.float16 and tuple(residual.shape) == (M, ld_c)
     arr = (C.c_void_p * len(peer_ptrs))(*peer_ptrs)
     with torch.cuda.device(x.device):
-        _lib.check(lib.qb200_gemm_w4a16_allgather(_ptr(x), _ptr(wq), _ptr(sz), _ptr(bias), _ptr(residual), arr, len(peer_ptrs), ld_c,
-                                                  col0, M, K, N, G, 0, 0, 1 if independent else 0, _stream_ptr()))
+        _lib.check(lib.qb200_gemm_w4a16_allgather(_ptr(x), _ptr(wq), _ptr(sz), _ptr(bias), _ptr(residual), arr, multicast_ptr or None,
+                                                  len(peer_ptrs), ld_c, col0, M, K, N, G, 0, 0, 1 if independent else 0, _stream_ptr()))
 
 
 def peer_barrier(epoch: torch.Tensor, flag_ptrs, rank: int) -> None:

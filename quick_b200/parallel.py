@@ -93,6 +93,17 @@ class PeerGatherWorkspace:
         hb = symm_mem.rendezvous(self.buf, self.group)
         hf = symm_mem.rendezvous(self.flags, self.group)
         self.buf_ptrs = [int(p) for p in hb.buffer_ptrs]
+        # NVSwitch multicast mapping of the same buffers (one multimem.st reaches every rank); QB200_TP_MULTICAST=0 keeps
+        # the loop of peer stores
+        import os
+        self.multicast_ptr = None
+        if os.environ.get("QB200_TP_MULTICAST", "1") == "1" and self.world > 1:
+            try:
+                if hb.has_multicast_support:
+                    mp_ = int(hb.multicast_ptr)
+                    self.multicast_ptr = mp_ if mp_ != 0 else None
+            except Exception:
+                self.multicast_ptr = None
         self.flag_ptrs = [int(p) for p in hf.buffer_ptrs]
         self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
         self._handles = (hb, hf)
@@ -106,7 +117,8 @@ class PeerGatherWorkspace:
         M = x2d.shape[0]
         if M > self.max_rows:
             raise ValueError(f"M={M} exceeds the workspace ({self.max_rows} rows)")
-        ops.gemm_allgather(x2d, wq, sz, n_local, G, self.buf_ptrs, self.n_total, self.rank * n_local, bias=bias, residual=residual)
+        ops.gemm_allgather(x2d, wq, sz, n_local, G, self.buf_ptrs, self.n_total, self.rank * n_local, bias=bias, residual=residual,
+                           multicast_ptr=self.multicast_ptr)
         ops.peer_barrier(self.epoch, self.flag_ptrs, self.rank)
         return self.buf[:M]
 

@@ -1,9 +1,5 @@
 mkdir -p gpurun_out
-N=$(nvidia-smi -L | wc -l); echo "gpus=$N"
-( time timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29551 tools/tp_check.py ) > gpurun_out/tp_check_n$N.log 2>&1; echo "tp_check rc=$?"; grep "TP_CHECK\|False" gpurun_out/tp_check_n$N.log | head
-( time timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29552 bench.py --gpus $N --steps 10 --warmup 3 ) > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err; echo "bench rc=$?"; tail -2 gpurun_out/bench_${N}gpu.err
-python - <<PY
-import json
-d=json.loads([l for l in open('gpurun_out/bench_${N}gpu.json').read().strip().splitlines() if l.startswith('{')][-1])
-print(d['n_gpus'], d['value'], d['e2e']['value'], d['independent']['value'], d['llama2_7b_tokens_per_s'])
-PY
+( time timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29561 tools/tp_check.py ) > gpurun_out/tp_check_mc.log 2>&1; rc=$?; echo "tp_check rc=$rc"; grep "TP_CHECK\|False\|multicast\|rror" gpurun_out/tp_check_mc.log | head
+[ $rc -ne 0 ] && exit 1
+( time timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29562 tools/bench_model.py --model llama-2-70b --batch 1 32 --out gpurun_out/model_llama2_70b_tp2_mc.json ) > gpurun_out/model_70b_tp2_mc.log 2>&1; echo "70b mc rc=$?"; grep '^{' gpurun_out/model_70b_tp2_mc.log | cut -c1-230
+( time QB200_TP_MULTICAST=0 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29563 tools/bench_model.py --model llama-2-70b --batch 1 32 ) > gpurun_out/model_70b_tp2_nomc.log 2>&1; echo "70b nomc rc=$?"; grep '^{' gpurun_out/model_70b_tp2_nomc.log | cut -c1-230

@@ -24,6 +24,7 @@ for (K, N, G, Ms) in ((1024, 1024, 128, (1, 16, 100)), (4096, 4096, 128, (1, 64,
     wq, sz, *_ = ops.prepack(sh.qweight, sh.qzeros, sh.scales)
     ws = PeerGatherWorkspace(max(Ms), N)
     keep += [lin, ws]
+    if rank == 0: print("multicast:", ws.multicast_ptr is not None, flush=True)
     for M in Ms:
         x = torch.randn(M, K, device="cuda", generator=g).half()
         res = torch.randn(M, N, device="cuda", generator=g).half()
