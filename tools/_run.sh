@@ -1,5 +1,16 @@
 mkdir -p gpurun_out
-( time timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29561 tools/tp_check.py ) > gpurun_out/tp_check_mc.log 2>&1; rc=$?; echo "tp_check rc=$rc"; grep "TP_CHECK\|False\|multicast\|rror" gpurun_out/tp_check_mc.log | head
-[ $rc -ne 0 ] && exit 1
-( time timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29562 tools/bench_model.py --model llama-2-70b --batch 1 32 --out gpurun_out/model_llama2_70b_tp2_mc.json ) > gpurun_out/model_70b_tp2_mc.log 2>&1; echo "70b mc rc=$?"; grep '^{' gpurun_out/model_70b_tp2_mc.log | cut -c1-230
-( time QB200_TP_MULTICAST=0 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29563 tools/bench_model.py --model llama-2-70b --batch 1 32 ) > gpurun_out/model_70b_tp2_nomc.log 2>&1; echo "70b nomc rc=$?"; grep '^{' gpurun_out/model_70b_tp2_nomc.log | cut -c1-230
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke.log
+( time timeout 900 python -m pytest tests -m gpu -x -q -rs ) > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu.log
+( time timeout 400 python bench.py --impl reference --steps 10 --warmup 3 ) > gpurun_out/bench_ref_final.json 2> gpurun_out/bench_ref_final.err; echo "bench ref rc=$?"
+( time timeout 400 python bench.py --steps 20 --warmup 3 ) > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_final.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:umma -c 900 --csv --log-file gpurun_out/launches_bench.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-model > gpurun_out/bench_under_ncu.log 2>&1; echo "ncu list rc=$?"
+for m in 1 256 512; do timeout 300 ncu --set full --clock-control none --import-source on -k regex:umma -s 10 -c 2 -f -o gpurun_out/full_M$m python tools/ncu_one.py $m > gpurun_out/ncu_full_M$m.log 2>&1; echo "ncu full M=$m rc=$?"; done
+for m in 1 256; do timeout 300 ncu --set full --clock-control none --import-source on -k regex:umma -s 10 -c 2 -f -o gpurun_out/full_indep_M$m python tools/ncu_one.py $m indep > gpurun_out/ncu_full_indep_M$m.log 2>&1; echo "ncu full indep M=$m rc=$?"; done
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_final.json').read().strip().splitlines()[0])
+print(d['value'], d['e2e']['value'], d['independent']['value'], d['clocks'], d['llama2_7b_tokens_per_s'])
+for r in d['sweep']: print(r)
+r=json.loads(open('gpurun_out/bench_ref_final.json').read().strip().splitlines()[0])
+print('REF', r['value'], r['e2e'])
+PY
