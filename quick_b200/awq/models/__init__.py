@@ -1,0 +1,2 @@
+from .llama import LlamaAWQForCausalLM  # noqa: F401
+from .mistral import MistralAWQForCausalLM  # noqa: F401

@@ -127,12 +127,31 @@ def _linear(m: WQLinear_QUICK, x, ref_mod=None, residual=None):
 
 
 class Block(nn.Module):
-    def __init__(self, cfg: LlamaLikeConfig, dev, gen, batch: int, peer_ws=None):
+    def __init__(self, cfg: LlamaLikeConfig, dev, gen, batch: int, peer_ws=None, parts=None):
+        """parts: {"qkv_proj", "o_proj", "gate_up_proj", "down_proj": WQLinear_QUICK, "norm_1", "norm_2": fp16 weight}
+        taken from a loaded checkpoint (fuse_hf_model); without it the weights are random-init."""
         super().__init__()
         self.cfg = cfg
         hd, nh, nkv = cfg.head_dim, cfg.num_heads, cfg.num_kv_heads
         self.norm_1 = RMSNorm(cfg.hidden_size, cfg.rms_eps, dev)
         self.norm_2 = RMSNorm(cfg.hidden_size, cfg.rms_eps, dev)
+        if parts is not None:
+            if tp_world() != 1:
+                raise NotImplementedError("checkpoint-backed blocks are single-GPU; shard with layout.shard_columns first")
+            self.norm_1.weight.data = parts["norm_1"].detach().to(dev, torch.float16).contiguous()
+            self.norm_2.weight.data = parts["norm_2"].detach().to(dev, torch.float16).contiguous()
+            expect = {"qkv_proj": (cfg.hidden_size, (nh + 2 * nkv) * hd), "o_proj": (nh * hd, cfg.hidden_size),
+                      "gate_up_proj": (cfg.hidden_size, 2 * cfg.intermediate_size),
+                      "down_proj": (cfg.intermediate_size, cfg.hidden_size)}
+            for name, (k, n) in expect.items():
+                m = parts[name]
+                if (m.in_features, m.out_features) != (k, n):
+                    raise ValueError(f"{name}: ({m.in_features} -> {m.out_features}) does not match the config ({k} -> {n})")
+                m.tp_sharded = False
+                setattr(self, name, m)
+            self.register_buffer("cache_k", torch.zeros(batch, nkv, cfg.max_seq_len, hd, dtype=torch.float16, device=dev), persistent=False)
+            self.register_buffer("cache_v", torch.zeros(batch, nkv, cfg.max_seq_len, hd, dtype=torch.float16, device=dev), persistent=False)
+            return
         # Under torch.distributed every linear is column-parallel: this rank's module holds N/R output columns
         # (random-init, so the shard is generated directly instead of slicing a full weight with
         # layout.shard_columns) and _linear() all-gathers the slabs.  N/R must stay a multiple of 128.
@@ -186,13 +205,16 @@ def _rope(t, cos, sin):
 
 
 class LlamaLikeQuickModel(nn.Module):
-    def __init__(self, cfg: LlamaLikeConfig, batch: int, dev="cuda", seed: int = 0):
+    def __init__(self, cfg: LlamaLikeConfig, batch: int, dev="cuda", seed: int = 0, parts=None):
+        """parts: {"embed": nn.Embedding, "blocks": [Block parts], "norm": fp16 weight, "lm_head": nn.Linear} from a
+        loaded checkpoint (fuse_hf_model); without it everything is random-init (benchmarks)."""
         super().__init__()
         self.cfg, self.batch = cfg, batch
+        self._decode_graph = None
         import torch.distributed as dist
         rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
         gen = torch.Generator(device=dev); gen.manual_seed(seed + 1000 * rank)   # every rank draws its own column slabs
-        self.embed = nn.Embedding(cfg.vocab_size, cfg.hidden_size, device=dev, dtype=torch.float16)
+        self.embed = parts["embed"] if parts is not None else nn.Embedding(cfg.vocab_size, cfg.hidden_size, device=dev, dtype=torch.float16)
         # tensor parallel, peer mode: one symmetric full-width output buffer per projection width (rows = the largest
         # token count a forward can carry), shared by all layers — consecutive uses are separated by other barriers
         self._peer_ws = {}
@@ -203,9 +225,15 @@ class LlamaLikeQuickModel(nn.Module):
                 self._peer_ws[n_total] = PeerGatherWorkspace(batch * cfg.max_seq_len, n_total)
             return self._peer_ws[n_total]
 
-        self.blocks = nn.ModuleList([Block(cfg, dev, gen, batch, peer_ws) for _ in range(cfg.num_layers)])
-        self.norm = RMSNorm(cfg.hidden_size, cfg.rms_eps, dev)
-        self.lm_head = nn.Linear(cfg.hidden_size, cfg.vocab_size, bias=False, device=dev, dtype=torch.float16)
+        if parts is None:
+            self.blocks = nn.ModuleList([Block(cfg, dev, gen, batch, peer_ws) for _ in range(cfg.num_layers)])
+            self.norm = RMSNorm(cfg.hidden_size, cfg.rms_eps, dev)
+            self.lm_head = nn.Linear(cfg.hidden_size, cfg.vocab_size, bias=False, device=dev, dtype=torch.float16)
+        else:
+            self.blocks = nn.ModuleList([Block(cfg, dev, gen, batch, parts=p) for p in parts["blocks"]])
+            self.norm = RMSNorm(cfg.hidden_size, cfg.rms_eps, dev)
+            self.norm.weight.data = parts["norm"].detach().to(dev, torch.float16).contiguous()
+            self.lm_head = parts["lm_head"]
         inv = 1.0 / (cfg.rope_theta ** (torch.arange(0, cfg.head_dim, 2, device=dev).float() / cfg.head_dim))
         ang = torch.outer(torch.arange(cfg.max_seq_len, device=dev).float(), inv)
         ang = torch.cat((ang, ang), dim=-1)
@@ -214,8 +242,9 @@ class LlamaLikeQuickModel(nn.Module):
         self.ref_mod = None   # set to the oracle/_ref module to time the reference kernel inside the same runner
 
     @torch.no_grad()
-    def forward(self, input_ids: torch.Tensor, pos_idx: torch.Tensor):
-        """input_ids (B, T); pos_idx (T,) int64 device tensor of the cache positions being written."""
+    def forward(self, input_ids: torch.Tensor, pos_idx: torch.Tensor, all_logits: bool = False):
+        """input_ids (B, T); pos_idx (T,) int64 device tensor of the cache positions being written.  Returns the logits
+        of the last position (B, 1, V), or of every position with all_logits (perplexity-style evaluation)."""
         cfg = self.cfg
         x = self.embed(input_ids)
         cos = self.rope_cos.index_select(0, pos_idx)[None, None]
@@ -225,7 +254,88 @@ class LlamaLikeQuickModel(nn.Module):
         attn_mask = keys[None, :] <= pos_idx[:, None]
         for blk in self.blocks:
             x = blk(x, cos, sin, pos_idx, attn_mask, self.ref_mod, (self.rope_cos, self.rope_sin))
-        return self.lm_head(self.norm(x[:, -1:, :]))
+        return self.lm_head(self.norm(x if all_logits else x[:, -1:, :]))
+
+    # ---- generation on the static cache (what the reference gets from HF generate over its fused blocks,
+    # base.py:88-90 + modules/fused/attn.py:187-245: a start_pos that advances with every call)
+    def _decode_step(self, tok: torch.Tensor, pos: int, use_graph: bool):
+        dev = tok.device
+        if self._decode_graph is None:
+            self._decode_graph = {"tok": torch.zeros(self.batch, 1, dtype=torch.long, device=dev),
+                                  "pos": torch.zeros(1, dtype=torch.long, device=dev), "graph": None, "out": None}
+        st = self._decode_graph
+        st["tok"].copy_(tok)
+        st["pos"].fill_(pos)
+        if not (use_graph and dev.type == "cuda" and self.ref_mod is None):
+            return self(st["tok"], st["pos"])
+        if st["graph"] is None:
+            for _ in range(2):                      # idempotent warm-up: same token, same cache slot
+                self(st["tok"], st["pos"])
+            torch.cuda.synchronize(dev)
+            side, graph = torch.cuda.Stream(dev), torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(graph, stream=side):
+                    st["out"] = self(st["tok"], st["pos"])
+            torch.cuda.synchronize(dev)
+            st["graph"] = graph
+        st["graph"].replay()
+        return st["out"]
+
+    @staticmethod
+    def _pick(logits, do_sample, temperature, top_k, top_p, generator):
+        logits = logits[:, -1, :].float()
+        if not do_sample:
+            return logits.argmax(-1, keepdim=True)
+        logits = logits / max(float(temperature), 1e-5)
+        if top_k and top_k > 0:
+            kth = logits.topk(min(int(top_k), logits.shape[-1]), dim=-1).values[:, -1:]
+            logits = logits.masked_fill(logits < kth, float("-inf"))
+        if top_p is not None and top_p < 1.0:
+            srt, idx = logits.sort(dim=-1, descending=True)
+            cum = srt.softmax(-1).cumsum(-1)
+            drop = cum - srt.softmax(-1) > top_p          # keep the first token that crosses top_p
+            srt = srt.masked_fill(drop, float("-inf"))
+            logits = torch.full_like(logits, float("-inf")).scatter(-1, idx, srt)
+        return torch.multinomial(logits.softmax(-1), 1, generator=generator)
+
+    @torch.no_grad()
+    def generate(self, input_ids=None, max_new_tokens: Optional[int] = None, do_sample: bool = False,
+                 temperature: float = 1.0, top_k: int = 0, top_p: float = 1.0, eos_token_id=None, pad_token_id=None,
+                 attention_mask=None, use_graph: bool = True, generator=None, inputs=None, **unused):
+        """Greedy / sampled continuation: prefill of the prompt, then one CUDA-graph replay per token.  Returns
+        (B, prompt + new) token ids like HF ``generate``.  The batch must equal the cache batch the model was built
+        with (``from_quantized(batch_size=…)``, the reference's AWQ_BATCH_SIZE); prompts must be unpadded."""
+        cfg = self.cfg
+        ids = input_ids if input_ids is not None else inputs
+        if ids is None or ids.dim() != 2:
+            raise ValueError("generate needs input_ids of shape (batch, prompt_len)")
+        B, T = ids.shape
+        if B != self.batch:
+            raise ValueError(f"batch {B} != the KV-cache batch {self.batch} this model was built with (batch_size=…)")
+        if attention_mask is not None and not bool(torch.as_tensor(attention_mask).bool().all()):
+            raise NotImplementedError("padded prompts are not supported by the static-cache runner")
+        max_new = int(max_new_tokens) if max_new_tokens is not None else cfg.max_seq_len - T
+        if T < 1 or max_new < 1 or T + max_new > cfg.max_seq_len:
+            raise ValueError(f"prompt {T} + new {max_new} tokens exceed the cache length {cfg.max_seq_len}")
+        dev = self.embed.weight.device
+        ids = ids.to(dev)
+        eos = None
+        if eos_token_id is not None:
+            eos = torch.as_tensor(eos_token_id, device=dev).reshape(-1)
+            pad = int(pad_token_id) if pad_token_id is not None else int(eos[0])
+        logits = self(ids, torch.arange(T, device=dev))
+        done = torch.zeros(B, 1, dtype=torch.bool, device=dev)
+        out = [ids]
+        for i in range(max_new):
+            tok = self._pick(logits, do_sample, temperature, top_k, top_p, generator)
+            if eos is not None:
+                tok = torch.where(done, torch.full_like(tok, pad), tok)
+                done = done | (tok[..., None] == eos).any(-1)
+            out.append(tok)
+            if i + 1 == max_new or (eos is not None and bool(done.all())):
+                break
+            logits = self._decode_step(tok, T + i, use_graph)
+        return torch.cat(out, dim=1)
 
     def weight_bytes(self):
         n = 0
@@ -280,3 +390,55 @@ def benchmark_generation(model: LlamaLikeQuickModel, n_context: int, n_generate:
     med = times[len(times) // 2]
     return {"batch": B, "prefill_len": n_context, "decode_len": n_generate, "prefill_tokens_per_s": n_context * B / prefill_s,
             "decode_tokens_per_s": B / med, "decode_ms_per_step": med * 1e3, "cuda_graph": graph is not None}
+
+
+def fuse_hf_model(model, batch_size: int = 1, max_seq_len: Optional[int] = None):
+    """Swap a loaded HF Llama/Mistral ``…ForCausalLM`` whose decoder linears are WQLinear_QUICK for the fused runner,
+    in place (the job of the reference's LlamaFuser / MistralFuser, models/llama.py:79-126): q‖k‖v and gate‖up are
+    concatenated in the QUICK layout (also for grouped-query attention, which the reference's QUICK_cat rejects,
+    fused_utils.py:139-142), norms / embedding / lm_head are taken over, ``model.model`` becomes the runner and
+    ``model.forward`` / ``model.generate`` route to it.  max_seq_len defaults to config.max_new_tokens like the
+    reference (llama.py:115), capped at a sliding window if the family has one."""
+    from ..utils.fused_utils import fuse_quick_linears
+    hc = model.config
+    layers = model.model.layers
+    attn0 = layers[0].self_attn
+    for name in ("q_proj", "k_proj", "v_proj", "o_proj"):
+        if not isinstance(getattr(attn0, name), WQLinear_QUICK):
+            raise TypeError(f"self_attn.{name} is {type(getattr(attn0, name)).__name__}, not WQLinear_QUICK — "
+                            "fuse_layers needs every decoder linear quantized (modules_to_not_convert must be empty)")
+    rope = getattr(hc, "rope_parameters", None) or {}
+    if rope.get("rope_type", "default") != "default" or getattr(hc, "rope_scaling", None) not in (None, {}, rope):
+        raise NotImplementedError(f"rotary embedding variant {rope or hc.rope_scaling} is not implemented in the fused runner")
+    theta = rope.get("rope_theta") or getattr(hc, "rope_theta", None) or 10000.0
+    nh, nkv = hc.num_attention_heads, getattr(hc, "num_key_value_heads", None) or hc.num_attention_heads
+    if getattr(hc, "head_dim", None) not in (None, hc.hidden_size // nh):
+        raise NotImplementedError("head_dim != hidden_size / num_attention_heads")
+    seq = int(max_seq_len or getattr(hc, "max_new_tokens", None) or 2048)
+    window = getattr(hc, "sliding_window", None)
+    if window:
+        seq = min(seq, int(window))
+    cfg = LlamaLikeConfig(hc.hidden_size, hc.intermediate_size, len(layers), nh, nkv, hc.vocab_size, seq,
+                          attn0.q_proj.group_size, float(hc.rms_norm_eps), float(theta))
+    dev = attn0.q_proj.qweight.device
+    blocks = []
+    for layer in layers:
+        a, mlp = layer.self_attn, layer.mlp
+        blocks.append({"qkv_proj": fuse_quick_linears(a.q_proj, a.k_proj, a.v_proj), "o_proj": a.o_proj,
+                       "gate_up_proj": fuse_quick_linears(mlp.gate_proj, mlp.up_proj), "down_proj": mlp.down_proj,
+                       "norm_1": layer.input_layernorm.weight, "norm_2": layer.post_attention_layernorm.weight})
+        for mod, names in ((a, ("q_proj", "k_proj", "v_proj")), (mlp, ("gate_proj", "up_proj"))):
+            for n in names:
+                delattr(mod, n)          # the fused copies replace them: free the memory layer by layer
+    runner = LlamaLikeQuickModel(cfg, batch_size, dev, parts={"embed": model.model.embed_tokens, "blocks": blocks,
+                                                              "norm": model.model.norm.weight, "lm_head": model.lm_head})
+    model.model = runner
+    model.qb200_fused = True
+
+    def fused_forward(input_ids=None, **kwargs):
+        ids = input_ids.to(dev)
+        return runner(ids, torch.arange(ids.shape[1], device=dev), all_logits=True)
+
+    model.forward = fused_forward
+    model.generate = runner.generate
+    return model

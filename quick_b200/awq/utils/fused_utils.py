@@ -26,6 +26,24 @@ def QUICK_cat(*input_layers: torch.Tensor, options: str, reshape_dims: Optional[
     return torch.cat(layers_to_cat, dim=1).reshape(H, -1)
 
 
+def fuse_quick_linears(*mods: WQLinear_QUICK) -> WQLinear_QUICK:
+    """One WQLinear_QUICK computing the N-concatenation of the given ones (same K and group size, any widths):
+    q‖k‖v, gate‖up."""
+    first = mods[0]
+    if any((m.in_features, m.group_size, m.w_bit) != (first.in_features, first.group_size, first.w_bit) for m in mods):
+        raise ValueError("fused linears must share in_features, group size and bit width")
+    has_bias = [m.bias is not None for m in mods]
+    if any(has_bias) and not all(has_bias):
+        raise ValueError("either all or none of the fused linears may have a bias")
+    out = WQLinear_QUICK(first.w_bit, first.group_size, first.in_features, sum(m.out_features for m in mods), False,
+                         "meta", first.k_split_1, first.k_split_2)
+    out.qweight = QUICK_cat(*(m.qweight for m in mods), options="qweight")
+    out.qzeros = QUICK_cat(*(m.qzeros for m in mods), options="qzeros")
+    out.scales = QUICK_cat(*(m.scales for m in mods), options="scales")
+    out.bias = torch.cat([m.bias for m in mods], dim=0) if all(has_bias) else None
+    return out
+
+
 def fuse_qkv_quick(module, q_proj, k_proj, v_proj):
     qkv_layer = WQLinear_QUICK(
         q_proj.w_bit,
