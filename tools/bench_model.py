@@ -14,6 +14,8 @@ ap.add_argument("--ctx", type=int, default=128)
 ap.add_argument("--gen", type=int, default=128)
 ap.add_argument("--layers", type=int, default=0, help="override layer count (0 = preset)")
 ap.add_argument("--impl", default="quick_b200", choices=["quick_b200", "reference"])
+ap.add_argument("--generate", action="store_true", help="also time model.generate() (the user-facing call of the plugin "
+                "surface: prefill + graph decode + token pick + host loop), wall clock around the call")
 ap.add_argument("--out", default="")
 args = ap.parse_args()
 # tensor parallel: `python -m torch.distributed.run --nproc-per-node R tools/bench_model.py --model llama-2-70b`
@@ -36,6 +38,16 @@ for bs in args.batch:
         from oracle.build_ref import load_ref
         model.ref_mod = load_ref(); assert model.ref_mod is not None
     r = benchmark_generation(model, args.ctx, args.gen)
+    if args.generate and world == 1 and args.impl == "quick_b200":
+        import time
+        ids = torch.randint(0, cfg.vocab_size, (bs, args.ctx), device="cuda")
+        model.generate(ids, max_new_tokens=4)          # builds the decode graph
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        seq = model.generate(ids, max_new_tokens=args.gen)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        assert seq.shape == (bs, args.ctx + args.gen)
+        r["generate_tokens_per_s"] = round(bs * args.gen / dt, 1)     # includes the prefill of ctx tokens
+        r["generate_s"] = round(dt, 4)
     r.update({"model": args.model, "impl": args.impl, "layers": cfg.num_layers, "weight_GB_per_rank": round(model.weight_bytes() / 1e9, 2),
               "mem_GB": round(torch.cuda.max_memory_allocated() / 1e9, 2), "tp": world})
     rows.append(r)
