@@ -211,6 +211,7 @@ class LlamaLikeQuickModel(nn.Module):
         super().__init__()
         self.cfg, self.batch = cfg, batch
         self._decode_graph = None
+        self.start_pos = 0        # next free cache slot for the stateful HF-style calls (fuse_hf_model) and generate()
         import torch.distributed as dist
         rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
         gen = torch.Generator(device=dev); gen.manual_seed(seed + 1000 * rank)   # every rank draws its own column slabs
@@ -335,7 +336,30 @@ class LlamaLikeQuickModel(nn.Module):
             if i + 1 == max_new or (eos is not None and bool(done.all())):
                 break
             logits = self._decode_step(tok, T + i, use_graph)
+        self.start_pos = T + len(out) - 2          # cache slots written: the prompt and every token fed back
         return torch.cat(out, dim=1)
+
+    @torch.no_grad()
+    def forward_stateful(self, input_ids=None, use_cache=True, **kwargs):
+        """The calling convention of the reference's fused model (modules/fused/model.py:76-109, attn.py:111-233,
+        fused_utils.py:17-29): the cache position is module state — a multi-token call is a new prefill at position 0,
+        a single-token call appends at the current position (one CUDA-graph replay).  ``out[0]`` / ``out.logits`` are
+        the logits of every input position, as examples/benchmark.py:47-60 expects."""
+        from transformers.modeling_outputs import CausalLMOutputWithPast
+        dev = self.embed.weight.device
+        ids = torch.as_tensor(input_ids, device=dev)
+        B, T = ids.shape
+        if B != self.batch:
+            raise ValueError(f"batch {B} != the KV-cache batch {self.batch} this model was built with (batch_size=…)")
+        start = self.start_pos if (T == 1 and use_cache) else 0
+        if start + T > self.cfg.max_seq_len:
+            raise ValueError(f"position {start} + {T} tokens exceed the cache length {self.cfg.max_seq_len} (max_new_tokens=…)")
+        if T == 1:
+            logits = self._decode_step(ids, start, use_graph=True).clone()
+        else:
+            logits = self(ids, torch.arange(start, start + T, device=dev), all_logits=True)
+        self.start_pos = start + T
+        return CausalLMOutputWithPast(logits=logits)
 
     def weight_bytes(self):
         n = 0
@@ -435,10 +459,6 @@ def fuse_hf_model(model, batch_size: int = 1, max_seq_len: Optional[int] = None)
     model.model = runner
     model.qb200_fused = True
 
-    def fused_forward(input_ids=None, **kwargs):
-        ids = input_ids.to(dev)
-        return runner(ids, torch.arange(ids.shape[1], device=dev), all_logits=True)
-
-    model.forward = fused_forward
+    model.forward = runner.forward_stateful
     model.generate = runner.generate
     return model

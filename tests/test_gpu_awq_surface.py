@@ -87,7 +87,20 @@ def test_quantize_save_load_forward_generate(tmp_path, built):
     fused = AutoAWQForCausalLM.from_quantized(out, fuse_layers=True, max_new_tokens=64, batch_size=2)
     runner = fused.model.model
     assert fused.model.qb200_fused and runner.cfg.num_kv_heads == 2 and runner.cfg.max_seq_len == 64
-    _close(fused(probe), ref, "fused runner, all positions")
+    res = fused(probe)
+    _close(res.logits, ref, "fused runner, all positions")
+    # the reference's stateful convention (examples/benchmark.py:47-60): single-token calls append to the cache
+    seq = probe
+    for _ in range(3):
+        tok = res[0][:, -1].max(1)[1].unsqueeze(1)
+        seq = torch.cat([seq, tok], 1)
+        res = fused(tok, use_cache=True)
+        assert res.logits.shape == (2, 1, 512) and runner.start_pos == seq.shape[1]
+        with torch.no_grad():
+            _close(res.logits[:, -1], dense(seq).logits[:, -1], f"stateful decode at position {seq.shape[1] - 1}")
+    res = fused(probe)                      # a multi-token call starts over at position 0
+    assert runner.start_pos == 16
+    _close(res.logits, ref, "fused runner, second prefill")
 
     def consistent(seq, n_new, what):
         """every generated token must be (within tolerance) the arg-max of the dense model on the same prefix"""
