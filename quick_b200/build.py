@@ -35,17 +35,19 @@ def _newer(target: str, sources: list[str]) -> bool:
 def build_lib(force: bool = False, verbose: bool = False, defines: tuple[str, ...] = (), out: str | None = None) -> str:
     """defines/out: development builds only (e.g. ("QB200_TRACE", "QB200_VARIANTS") -> libquick_b200_dev.so,
     selected with the QB200_LIB environment variable); the product library is built without defines."""
-    srcs = [os.path.join(CSRC, "quick_b200.cu"), os.path.join(CSRC, "w4a16_umma.cuh"),
+    srcs = [os.path.join(CSRC, "quick_b200.cu"), os.path.join(CSRC, "w4a16_umma.cuh"), os.path.join(CSRC, "w4a16_gemv.cuh"),
             os.path.join(ROOT, "include", "quick_b200.h")]
     target = out or LIB
     if not force and _newer(target, srcs):
         return target
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", target, srcs[0]]
+    tmp = target + ".tmp"      # built aside and renamed: a process that has the old file mapped keeps its inode
+    cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", tmp, srcs[0]]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)
+    os.replace(tmp, target)
     return target
 
 
@@ -80,7 +82,8 @@ def build_ext(force: bool = False, verbose: bool = False) -> str:
         verbose=verbose,
         is_python_module=False,
     )
-    shutil.copy2(os.path.join(bdir, "quick_kernels.so"), EXT)
+    shutil.copy2(os.path.join(bdir, "quick_kernels.so"), EXT + ".tmp")
+    os.replace(EXT + ".tmp", EXT)
     return EXT
 
 
