@@ -35,7 +35,7 @@ def _newer(target: str, sources: list[str]) -> bool:
 def build_lib(force: bool = False, verbose: bool = False, defines: tuple[str, ...] = (), out: str | None = None) -> str:
     """defines/out: development builds only (e.g. ("QB200_TRACE", "QB200_VARIANTS") -> libquick_b200_dev.so,
     selected with the QB200_LIB environment variable); the product library is built without defines."""
-    srcs = [os.path.join(CSRC, "quick_b200.cu"), os.path.join(CSRC, "w4a16_umma.cuh"), os.path.join(CSRC, "w4a16_gemv.cuh"),
+    srcs = [os.path.join(CSRC, "quick_b200.cu"), os.path.join(CSRC, "w4a16_umma.cuh"),
             os.path.join(ROOT, "include", "quick_b200.h")]
     target = out or LIB
     if not force and _newer(target, srcs):

@@ -11,11 +11,6 @@
 
 #include "../../include/quick_b200.h"
 #include "w4a16_umma.cuh"
-#include "w4a16_gemv.cuh"
-
-#ifndef QB200_GEMV_DEFAULT_MAX_M
-#define QB200_GEMV_DEFAULT_MAX_M 0   // ordered plan: largest M routed to the GEMV path unless QB200_GEMV_MAX_M says otherwise
-#endif
 
 namespace {
 
@@ -534,51 +529,6 @@ int dispatch_variant(int split, const CUtensorMap& map, const qb200::GemmArgs& a
   return dispatch_split<TOK, 0>(split, map, args, m_tiles, st);
 }
 
-// GEMV path (w4a16_gemv.cuh): M <= 4 token rows, one CTA per 32 output channels, no cluster.
-// QB200_GEMV_MAX_M (0..4) = largest M the ordered plan routes to it (0 disables it); explicit tok = 1 always selects it.
-int gemv_max_m() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("QB200_GEMV_MAX_M");
-    v = e ? atoi(e) : QB200_GEMV_DEFAULT_MAX_M;
-    if (v < 0) v = 0;
-    if (v > qb200::kGemvMaxRows) v = qb200::kGemvMaxRows;
-  }
-  return v;
-}
-constexpr int kGemvSmemLimit = 227 * 1024;
-int gemv_rows(int M) { return M <= 1 ? 1 : M <= 2 ? 2 : 4; }
-bool gemv_fits(int M, int K, int G) {
-  const int hpg = G / 32;
-  return M >= 1 && M <= qb200::kGemvMaxRows && hpg >= 1 && (hpg & (hpg - 1)) == 0 && G % 32 == 0 &&
-         qb200::gemv_smem_bytes(gemv_rows(M), K) <= kGemvSmemLimit;
-}
-
-template <int MROWS>
-int launch_gemv(const void* A, const qb200::GemmArgs& args, cudaStream_t stream) {
-  auto kfn = qb200::w4a16_gemv_kernel<MROWS>;
-  static bool attr_set = false;   // per instantiation
-  if (!attr_set) {
-    QB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemvSmemLimit));
-    QB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    attr_set = true;
-  }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(args.N / qb200::kGemvCh);
-  cfg.blockDim = dim3(qb200::kGemvThreads);
-  cfg.dynamicSmemBytes = qb200::gemv_smem_bytes(MROWS, args.K);
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  const bool pdl = use_pdl() && g_skip_pdl_once.exchange(0, std::memory_order_relaxed) == 0;
-  cfg.numAttrs = pdl ? 1 : 0;
-  QB_CUDA(cudaLaunchKernelEx(&cfg, kfn, reinterpret_cast<const __half*>(A), args));
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return QB200_OK;
-}
-
 int check_device() {
   static int ok = -1;
   if (ok < 0) {
@@ -598,13 +548,8 @@ int check_device() {
 //   independent        — QB200_GEMM_INDEPENDENT launches overlap each other, so throughput wins: no split-K
 //                        (no exchange, one CTA per 128-channel tile streams the whole K) and the largest token
 //                        tile, which leaves the other SMs to the neighbouring GEMMs.
-void plan(int M, int K, int N, int G, int split_hint, unsigned flags, int* tok_out, int* split_out, bool allow_gemv = true) {
+void plan(int M, int K, int N, int split_hint, unsigned flags, int* tok_out, int* split_out) {
   (void)split_hint;   // the reference's split_k_iters is accepted but only a hint
-  if (allow_gemv && !(flags & QB200_GEMM_INDEPENDENT) && M <= gemv_max_m() && gemv_fits(M, K, G)) {
-    *tok_out = 1;     // decode-sized input: the weight-streaming GEMV (tok = 1 names that path)
-    *split_out = 1;
-    return;
-  }
   if (flags & QB200_GEMM_INDEPENDENT) {
     *tok_out = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
     *split_out = 1;
@@ -760,10 +705,10 @@ int qb200_gemm_plan_ex(int M, int K, int N, int G, int split_k_hint, unsigned fl
   int rc = qb200_check_shape(M, K, N, G);
   if (rc) return rc;
   int t, s;
-  plan(M, K, N, G, split_k_hint, flags, &t, &s);
+  plan(M, K, N, split_k_hint, flags, &t, &s);
   if (tok) *tok = t;
   if (split) *split = s;
-  if (ctas) *ctas = t == 1 ? N / qb200::kGemvCh : (N / 128) * ((M + t - 1) / t) * s;
+  if (ctas) *ctas = (N / 128) * ((M + t - 1) / t) * s;
   return QB200_OK;
 }
 
@@ -807,7 +752,7 @@ int gemm_impl(const void* A, const uint32_t* wq, const uint32_t* sz, const void*
   if (flags & ~QB200_GEMM_INDEPENDENT) return fail(QB200_EINVAL, "unknown flags 0x%x", flags);
   if (tok == 0 || split == 0) {
     int t, s;
-    plan(M, K, N, G, 0, flags, &t, &s, /*allow_gemv=*/n_peers == 0 && tok == 0);
+    plan(M, K, N, 0, flags, &t, &s);
     if (tok == 0) tok = t;
     if (split == 0) split = s;
   }
@@ -823,16 +768,9 @@ int gemm_impl(const void* A, const uint32_t* wq, const uint32_t* sz, const void*
   const int m_tiles = (M + tok - 1) / tok;
   if (m_tiles > 65535) return fail(QB200_EINVAL, "M too large for one launch");
 
-  if (tok == 1) {
-    if (n_peers > 0) return fail(QB200_EINVAL, "the GEMV path (tok = 1) has no fused all-gather mode");
-    if (!gemv_fits(M, K, G)) return fail(QB200_EINVAL, "the GEMV path (tok = 1) takes M <= %d, a power-of-two group size and K <= %d for that M",
-                                         qb200::kGemvMaxRows, (kGemvSmemLimit - qb200::kGemvRingBytes) / (2 * gemv_rows(M > 0 ? M : 1)) / 64 * 64);
-  }
   CUtensorMap map;
-  if (tok != 1) {
-    rc = make_x_tensor_map(&map, A, M, K, tok);
-    if (rc) return rc;
-  }
+  rc = make_x_tensor_map(&map, A, M, K, tok);
+  if (rc) return rc;
   qb200::GemmArgs args;
   args.wq = wq;
   args.sz = sz;
@@ -854,12 +792,6 @@ int gemm_impl(const void* A, const uint32_t* wq, const uint32_t* sz, const void*
   args.trace = g_trace;
   cudaStream_t st = as_stream(stream);
   switch (tok) {
-    case 1:
-      switch (gemv_rows(M)) {
-        case 1: return launch_gemv<1>(A, args, st);
-        case 2: return launch_gemv<2>(A, args, st);
-        default: return launch_gemv<4>(A, args, st);
-      }
     case 16: return dispatch_variant<16>(split, map, args, m_tiles, st);
     case 32: return dispatch_variant<32>(split, map, args, m_tiles, st);
     case 64: return dispatch_variant<64>(split, map, args, m_tiles, st);
@@ -877,7 +809,7 @@ int qb200_gemm_w4a16(const void* A, const uint32_t* wq, const uint32_t* sz, cons
   int rc = qb200_check_shape(M, K, N, G);
   if (rc) return rc;
   int tok, split;
-  plan(M, K, N, G, split_k_hint, 0u, &tok, &split);
+  plan(M, K, N, split_k_hint, 0u, &tok, &split);
   return qb200_gemm_w4a16_cfg(A, wq, sz, bias, C, M, K, N, G, tok, split, stream);
 }
 
