@@ -8,7 +8,9 @@ nor ``load_checkpoint_and_dispatch``, base.py:309-316, exist in this environment
   * the skeleton is built on the meta device, its decoder-layer linears are swapped for ``WQLinear_QUICK`` (init only,
     base.py:406-415), storage is allocated on ONE target device and the checkpoint tensors are copied in file by file;
   * ``device_map`` accepts None / "auto" / "balanced" / "cuda[:i]" / "cpu" / {"": dev} — one device.  Models that need
-    several GPUs run tensor-parallel under torchrun (quick_b200.parallel), not layer-scattered;
+    several GPUs run tensor-parallel: under torchrun every rank loads the checkpoint, ``fuse_layers`` keeps its N/R
+    output columns of every linear (layout.shard_columns) and the runner all-gathers (fused GEMM + all-gather over
+    peer memory, or NCCL) — not layer-scattered;
   * AWQ "GEMM"-layout checkpoints (what public AWQ checkpoints ship) load too: each linear's tensors go through the
     bit-exact GEMM → QUICK converter (WQLinear_QUICK.from_awq_gemm) — the reference cannot do that without the fp16 model;
   * ``fuse_layers=True`` swaps the HF decoder for the library's fused runner (fused q‖k‖v and gate‖up GEMMs, fused glue
@@ -76,7 +78,12 @@ def _resolve_device(device_map) -> torch.device:
                                       "parallelism for models larger than one GPU)")
         device_map = vals.pop()
     if device_map in (None, "auto", "balanced", "balanced_low_0", "sequential"):
-        return torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        if not torch.cuda.is_available():
+            return torch.device("cpu")
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and "LOCAL_RANK" in os.environ:
+            return torch.device("cuda", int(os.environ["LOCAL_RANK"]))      # one process per GPU (torchrun)
+        return torch.device("cuda", torch.cuda.current_device())
     if isinstance(device_map, int):
         return torch.device("cuda", device_map)
     return torch.device(device_map)

@@ -86,6 +86,25 @@ def tp_world() -> int:
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
+def _tp_rank() -> int:
+    import torch.distributed as dist
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def shard_quick_linear(m: WQLinear_QUICK, rank: int, world: int) -> WQLinear_QUICK:
+    """The column-parallel shard `rank` of `world` of a packed linear: output columns [rank·N/world, (rank+1)·N/world)
+    as a WQLinear_QUICK of its own (layout.shard_columns: the inverse of QUICK_cat; N/world must stay a multiple of
+    the 128-column tile)."""
+    from ...layout import shard_columns
+    if m.out_features % (128 * world) != 0:
+        raise ValueError(f"N={m.out_features} does not split into {world} shards of 128-column tiles")
+    n_local = m.out_features // world
+    out = WQLinear_QUICK(m.w_bit, m.group_size, m.in_features, n_local, False, "meta", m.k_split_1, m.k_split_2)
+    out.qweight, out.qzeros, out.scales = shard_columns(m.qweight, m.qzeros, m.scales, rank, world)
+    out.bias = None if m.bias is None else m.bias[rank * n_local:(rank + 1) * n_local].clone()
+    return out
+
+
 def _gather_columns(local: torch.Tensor) -> torch.Tensor:
     """Tensor-parallel linears (BASELINE config 5): every rank holds N/R output columns of each
     weight and computes its (.., N/R) slab with the same kernel; ONE all-gather (NCCL over NVLink) rebuilds the
@@ -136,8 +155,7 @@ class Block(nn.Module):
         self.norm_1 = RMSNorm(cfg.hidden_size, cfg.rms_eps, dev)
         self.norm_2 = RMSNorm(cfg.hidden_size, cfg.rms_eps, dev)
         if parts is not None:
-            if tp_world() != 1:
-                raise NotImplementedError("checkpoint-backed blocks are single-GPU; shard with layout.shard_columns first")
+            R = tp_world()
             self.norm_1.weight.data = parts["norm_1"].detach().to(dev, torch.float16).contiguous()
             self.norm_2.weight.data = parts["norm_2"].detach().to(dev, torch.float16).contiguous()
             expect = {"qkv_proj": (cfg.hidden_size, (nh + 2 * nkv) * hd), "o_proj": (nh * hd, cfg.hidden_size),
@@ -147,7 +165,11 @@ class Block(nn.Module):
                 m = parts[name]
                 if (m.in_features, m.out_features) != (k, n):
                     raise ValueError(f"{name}: ({m.in_features} -> {m.out_features}) does not match the config ({k} -> {n})")
-                m.tp_sharded = False
+                if R > 1:       # tensor parallel: this rank keeps its N/R output columns, the rest is freed
+                    m = shard_quick_linear(m, _tp_rank(), R)
+                    if TP_MODE == "peer":
+                        m.peer_ws = peer_ws(n)
+                m.tp_sharded = R > 1
                 setattr(self, name, m)
             self.register_buffer("cache_k", torch.zeros(batch, nkv, cfg.max_seq_len, hd, dtype=torch.float16, device=dev), persistent=False)
             self.register_buffer("cache_v", torch.zeros(batch, nkv, cfg.max_seq_len, hd, dtype=torch.float16, device=dev), persistent=False)
@@ -231,7 +253,7 @@ class LlamaLikeQuickModel(nn.Module):
             self.norm = RMSNorm(cfg.hidden_size, cfg.rms_eps, dev)
             self.lm_head = nn.Linear(cfg.hidden_size, cfg.vocab_size, bias=False, device=dev, dtype=torch.float16)
         else:
-            self.blocks = nn.ModuleList([Block(cfg, dev, gen, batch, parts=p) for p in parts["blocks"]])
+            self.blocks = nn.ModuleList([Block(cfg, dev, gen, batch, peer_ws, parts=p) for p in parts["blocks"]])
             self.norm = RMSNorm(cfg.hidden_size, cfg.rms_eps, dev)
             self.norm.weight.data = parts["norm"].detach().to(dev, torch.float16).contiguous()
             self.lm_head = parts["lm_head"]
@@ -297,7 +319,11 @@ class LlamaLikeQuickModel(nn.Module):
             drop = cum - srt.softmax(-1) > top_p          # keep the first token that crosses top_p
             srt = srt.masked_fill(drop, float("-inf"))
             logits = torch.full_like(logits, float("-inf")).scatter(-1, idx, srt)
-        return torch.multinomial(logits.softmax(-1), 1, generator=generator)
+        tok = torch.multinomial(logits.softmax(-1), 1, generator=generator)
+        if tp_world() > 1:          # tensor parallel: every rank must feed the same token back — rank 0's draw wins
+            import torch.distributed as dist
+            dist.broadcast(tok, src=0)
+        return tok
 
     @torch.no_grad()
     def generate(self, input_ids=None, max_new_tokens: Optional[int] = None, do_sample: bool = False,
