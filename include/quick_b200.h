@@ -145,6 +145,16 @@ int qb200_rmsnorm(const void* x_fp16, const void* weight_fp16, void* y_fp16, int
 int qb200_rope_kv_update(const void* qkv_fp16, const void* cos_table_fp16, const void* sin_table_fp16, const long long* pos,
                          void* q_out_fp16, void* cache_k_fp16, void* cache_v_fp16, int B, int T, int nh, int nkv, int hd, int S,
                          void* stream);
+/* Decode-step attention fused with rotary embedding and KV-cache update: qkv [B][1][(nh + 2 nkv) hd] -> out [B][1][nh hd];
+ * rotary k and plain v are written into the static caches [B][nkv][S][hd] at position pos[0] and the pos[0] + 1 cached
+ * positions are attended (softmax in fp32, scale = 1/sqrt(hd) usually).  The reference does this in
+ * QuantAttentionFused.forward's single-token branch (quick/awq/modules/fused/attn.py:187-245) through awq_ext kernels
+ * that are not part of its tree.  qb200_attn_decode_smem_bytes returns -1 when the configuration is not supported
+ * (nh / nkv > 8, hd not in {64, 128, 256}, or a cache too long for shared memory). */
+int qb200_attn_decode_smem_bytes(int nh, int nkv, int hd, int S);
+int qb200_attn_decode(const void* qkv_fp16, const void* cos_table_fp16, const void* sin_table_fp16, const long long* pos,
+                      void* out_fp16, void* cache_k_fp16, void* cache_v_fp16, int B, int nh, int nkv, int hd, int S, float scale,
+                      void* stream);
 /* act[rows][I] = silu(g) * u for gate_up rows [g | u] of width 2I. */
 int qb200_silu_mul(const void* gate_up_fp16, void* act_fp16, long long rows, int I, void* stream);
 

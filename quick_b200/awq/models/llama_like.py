@@ -24,6 +24,10 @@ from ..modules.linear.quick import WQLinear_QUICK
 # (C-ABI qb200_rmsnorm / qb200_rope_kv_update / qb200_silu_mul / qb200_gemm_w4a16_fused) instead of ~30 small torch
 # kernels per layer; FUSED_GLUE = False keeps the plain torch expressions (the parity reference of the tests).
 FUSED_GLUE = True
+# Decode steps (one new token): rotary embedding + KV-cache update + attention over the cache in ONE kernel
+# (qb200_attn_decode) instead of rope_kv_update + mask arithmetic + torch SDPA.  QB200_ATTN_DECODE=0 keeps the SDPA path.
+import os as _os0
+ATTN_DECODE = _os0.environ.get("QB200_ATTN_DECODE", "1") != "0"
 
 
 @dataclass
@@ -199,6 +203,12 @@ class Block(nn.Module):
         B, T, _ = x.shape
         hd, nh, nkv = cfg.head_dim, cfg.num_heads, cfg.num_kv_heads
         qkv = _linear(self.qkv_proj, self.norm_1(x), ref_mod)
+        if T == 1 and attn_mask is None:
+            # decode step on the fused path (the model decided: see LlamaLikeQuickModel._fused_decode_ok)
+            o = quick_kernels.attn_decode(qkv, rope[0], rope[1], pos_idx, self.cache_k, self.cache_v, nh, nkv)
+            x = _linear(self.o_proj, o, ref_mod, residual=x)
+            gu = _linear(self.gate_up_proj, self.norm_2(x), ref_mod)
+            return _linear(self.down_proj, quick_kernels.silu_mul(gu), ref_mod, residual=x)
         if FUSED_GLUE and qkv.is_cuda:
             # rotary embedding of q and k + KV-cache update in one kernel (rope tables are indexed by position)
             q = quick_kernels.rope_kv_update(qkv, rope[0], rope[1], pos_idx, self.cache_k, self.cache_v, nh, nkv)
@@ -233,6 +243,7 @@ class LlamaLikeQuickModel(nn.Module):
         super().__init__()
         self.cfg, self.batch = cfg, batch
         self._decode_graph = None
+        self._attn_decode_supported = None
         self.start_pos = 0        # next free cache slot for the stateful HF-style calls (fuse_hf_model) and generate()
         import torch.distributed as dist
         rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
@@ -264,17 +275,31 @@ class LlamaLikeQuickModel(nn.Module):
         self.register_buffer("rope_sin", ang.sin().half(), persistent=False)
         self.ref_mod = None   # set to the oracle/_ref module to time the reference kernel inside the same runner
 
+    def _fused_decode_ok(self, x) -> bool:
+        """One new token per sequence, CUDA, fused glue on, whole batch present, and a (heads, cache length) the
+        single-kernel decode attention supports; anything else takes the rope_kv_update + SDPA path."""
+        cfg = self.cfg
+        if not (ATTN_DECODE and FUSED_GLUE and x.is_cuda and x.shape[1] == 1 and x.shape[0] == self.batch):
+            return False
+        if self._attn_decode_supported is None:
+            self._attn_decode_supported = bool(quick_kernels.attn_decode_supported(cfg.num_heads, cfg.num_kv_heads, cfg.head_dim,
+                                                                                    cfg.max_seq_len))
+        return self._attn_decode_supported
+
     @torch.no_grad()
     def forward(self, input_ids: torch.Tensor, pos_idx: torch.Tensor, all_logits: bool = False):
         """input_ids (B, T); pos_idx (T,) int64 device tensor of the cache positions being written.  Returns the logits
         of the last position (B, 1, V), or of every position with all_logits (perplexity-style evaluation)."""
         cfg = self.cfg
         x = self.embed(input_ids)
-        cos = self.rope_cos.index_select(0, pos_idx)[None, None]
-        sin = self.rope_sin.index_select(0, pos_idx)[None, None]
-        # causal mask over the static cache: key j visible to query at position p iff j <= p
-        keys = torch.arange(cfg.max_seq_len, device=x.device)
-        attn_mask = keys[None, :] <= pos_idx[:, None]
+        if self._fused_decode_ok(x):
+            cos = sin = attn_mask = None      # qb200_attn_decode indexes the rotary tables and the cache by position itself
+        else:
+            cos = self.rope_cos.index_select(0, pos_idx)[None, None]
+            sin = self.rope_sin.index_select(0, pos_idx)[None, None]
+            # causal mask over the static cache: key j visible to query at position p iff j <= p
+            keys = torch.arange(cfg.max_seq_len, device=x.device)
+            attn_mask = keys[None, :] <= pos_idx[:, None]
         for blk in self.blocks:
             x = blk(x, cos, sin, pos_idx, attn_mask, self.ref_mod, (self.rope_cos, self.rope_sin))
         return self.lm_head(self.norm(x if all_logits else x[:, -1:, :]))

@@ -358,6 +358,145 @@ __global__ void rope_kv_kernel(const __half* __restrict__ qkv, const __half* __r
   }
 }
 
+// Decode-step attention (ONE new token per sequence) fused with the rotary embedding and the KV-cache update — the job of
+// the reference's QuantAttentionFused decode branch (modules/fused/attn.py:187-245: awq_ext.single_query_attention over
+// its rolling cache).  One CTA per (kv head, sequence): it rotates its k and the g = nh / nkv query heads that share it
+// (same arithmetic as rope_kv_kernel), writes k / v into the static caches [B][nkv][S][hd] at position p = pos[0],
+// scores the p + 1 visible positions (the new one from shared memory), softmaxes in fp32 and accumulates P·V — no mask
+// tensor, no q / k / v round trip through HBM, one launch instead of rope + mask arithmetic + SDPA.
+//   out [B][1][nh * hd] fp16 (the layout o_proj consumes).  Shared memory: q_rot g·hd, k, v (fp16) | scores g·S (fp32) |
+//   P·V partials (256 / (hd/2)) · g · hd (fp32) | 1 / sum per head.
+constexpr int kAttnThreads = 256;
+constexpr int kAttnMaxGroup = 8;
+__host__ __device__ constexpr size_t attn_decode_smem(int g, int hd, int S) {
+  return static_cast<size_t>(g + 2) * hd * 2 + static_cast<size_t>(g) * S * 4 +
+         static_cast<size_t>(kAttnThreads / (hd / 2)) * g * hd * 4 + kAttnMaxGroup * 4;
+}
+
+__global__ void __launch_bounds__(kAttnThreads)
+attn_decode_kernel(const __half* __restrict__ qkv, const __half* __restrict__ cosb, const __half* __restrict__ sinb,
+                   const long long* __restrict__ pos, __half* __restrict__ out, __half* __restrict__ cache_k,
+                   __half* __restrict__ cache_v, int nh, int nkv, int hd, int S, float scale) {
+  qb200::pdl_launch_dependents();
+  qb200::pdl_wait_prior_grid();
+  extern __shared__ __align__(16) uint8_t attn_smem[];
+  const int kvh = blockIdx.x, b = blockIdx.y, g = nh / nkv;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int p = static_cast<int>(pos[0]);
+  const int L = p + 1;                                   // visible positions 0 .. p
+  __half* qs = reinterpret_cast<__half*>(attn_smem);     // [g][hd]
+  __half* ks = qs + g * hd;                              // [hd]
+  __half* vs = ks + hd;                                  // [hd]
+  float* sc = reinterpret_cast<float*>(vs + hd);         // [g][S]
+  const int tpd = hd >> 1, nsl = kAttnThreads / tpd;     // threads per P·V slice (one half2 each), slices
+  float* red = sc + static_cast<size_t>(g) * S;          // [nsl][g][hd]
+  float* inv = red + static_cast<size_t>(nsl) * g * hd;  // [g]
+  const __half* src = qkv + static_cast<size_t>(b) * (nh + 2 * nkv) * hd;
+  const size_t crow = (static_cast<size_t>(b) * nkv + kvh) * S;   // first cache row of this (sequence, kv head)
+  const int half_hd = hd >> 1;
+
+  for (int idx = tid; idx < (g + 2) * hd; idx += kAttnThreads) {
+    const int hl = idx / hd, i = idx - hl * hd;
+    if (hl == g + 1) {                                   // value: plain copy
+      const __half v = src[static_cast<size_t>(nh + nkv + kvh) * hd + i];
+      vs[i] = v;
+      cache_v[(crow + p) * hd + i] = v;
+      continue;
+    }
+    const __half* hsrc = src + static_cast<size_t>(hl < g ? kvh * g + hl : nh + kvh) * hd;
+    const __half v = hsrc[i];
+    const __half c = cosb[static_cast<size_t>(p) * hd + i], sn = sinb[static_cast<size_t>(p) * hd + i];
+    const __half other = i < half_hd ? __hneg(hsrc[i + half_hd]) : hsrc[i - half_hd];
+    const __half r = __hadd_rn(__hmul_rn(v, c), __hmul_rn(other, sn));   // == rope_kv_kernel
+    if (hl < g) {
+      qs[hl * hd + i] = r;
+    } else {
+      ks[i] = r;
+      cache_k[(crow + p) * hd + i] = r;
+    }
+  }
+  __syncthreads();
+
+  for (int j = tid; j < L; j += kAttnThreads) {           // scores: one thread per position, all g heads at once
+    const __half* krow = j == p ? ks : cache_k + (crow + j) * hd;
+    float acc[kAttnMaxGroup];
+#pragma unroll
+    for (int h = 0; h < kAttnMaxGroup; ++h) acc[h] = 0.f;
+    for (int d = 0; d < hd; d += 8) {
+      const uint4 kv = *reinterpret_cast<const uint4*>(krow + d);
+      const __half2* k2 = reinterpret_cast<const __half2*>(&kv);
+      float2 kf[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) kf[u] = __half22float2(k2[u]);
+#pragma unroll
+      for (int h = 0; h < kAttnMaxGroup; ++h) {
+        if (h < g) {
+          const uint4 qv = *reinterpret_cast<const uint4*>(qs + h * hd + d);   // same address in every thread: broadcast
+          const __half2* q2 = reinterpret_cast<const __half2*>(&qv);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float2 qf = __half22float2(q2[u]);
+            acc[h] = fmaf(qf.x, kf[u].x, acc[h]);
+            acc[h] = fmaf(qf.y, kf[u].y, acc[h]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < kAttnMaxGroup; ++h)
+      if (h < g) sc[static_cast<size_t>(h) * S + j] = acc[h] * scale;
+  }
+  __syncthreads();
+
+  if (warp < g) {                                         // softmax of head `warp` over L scores, fp32
+    float* row = sc + static_cast<size_t>(warp) * S;
+    float m = -INFINITY;
+    for (int j = lane; j < L; j += 32) m = fmaxf(m, row[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+    for (int j = lane; j < L; j += 32) {
+      const float e = __expf(row[j] - m);
+      row[j] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) inv[warp] = 1.f / sum;
+  }
+  __syncthreads();
+
+  {                                                       // P·V: slice sl takes positions sl, sl + nsl, ...; thread = one half2 of the head dim
+    const int sl = tid / tpd, dl = (tid - sl * tpd) * 2;
+    float2 acc[kAttnMaxGroup];
+#pragma unroll
+    for (int h = 0; h < kAttnMaxGroup; ++h) acc[h] = make_float2(0.f, 0.f);
+    for (int j = sl; j < L; j += nsl) {
+      const __half* vrow = j == p ? vs : cache_v + (crow + j) * hd;
+      const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(vrow + dl));
+#pragma unroll
+      for (int h = 0; h < kAttnMaxGroup; ++h) {
+        if (h < g) {
+          const float pj = sc[static_cast<size_t>(h) * S + j];
+          acc[h].x = fmaf(pj, vf.x, acc[h].x);
+          acc[h].y = fmaf(pj, vf.y, acc[h].y);
+        }
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < kAttnMaxGroup; ++h)
+      if (h < g) *reinterpret_cast<float2*>(red + (static_cast<size_t>(sl) * g + h) * hd + dl) = acc[h];
+  }
+  __syncthreads();
+
+  for (int idx = tid; idx < g * hd; idx += kAttnThreads) {
+    const int h = idx / hd, d = idx - h * hd;
+    float t = 0.f;
+    for (int sl = 0; sl < nsl; ++sl) t += red[(static_cast<size_t>(sl) * g + h) * hd + d];
+    out[static_cast<size_t>(b) * nh * hd + static_cast<size_t>(kvh * g + h) * hd + d] = __float2half_rn(t * inv[h]);
+  }
+}
+
 // act[M][I] = fp16( fp16(silu(g)) * u ),  gu = [g | u] per row ([M][2I]); silu in fp32 like torch's half kernel.
 __global__ void silu_mul_kernel(const __half* __restrict__ gu, __half* __restrict__ act, size_t M, int I) {
   qb200::pdl_launch_dependents();
@@ -877,6 +1016,41 @@ int qb200_rope_kv_update(const void* qkv, const void* cos_table, const void* sin
                      reinterpret_cast<const __half*>(qkv), reinterpret_cast<const __half*>(cos_table),
                      reinterpret_cast<const __half*>(sin_table), pos, reinterpret_cast<__half*>(q_out),
                      reinterpret_cast<__half*>(cache_k), reinterpret_cast<__half*>(cache_v), T, nh, nkv, hd, S));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return QB200_OK;
+}
+
+int qb200_attn_decode_smem_bytes(int nh, int nkv, int hd, int S) {
+  if (nh <= 0 || nkv <= 0 || nh % nkv != 0 || nh / nkv > kAttnMaxGroup || (hd != 64 && hd != 128 && hd != 256) || S <= 0) return -1;
+  const size_t need = attn_decode_smem(nh / nkv, hd, S);
+  return need <= 200 * 1024 ? static_cast<int>(need) : -1;
+}
+
+int qb200_attn_decode(const void* qkv, const void* cos_table, const void* sin_table, const long long* pos, void* out,
+                      void* cache_k, void* cache_v, int B, int nh, int nkv, int hd, int S, float scale, void* stream) {
+  const int smem = qb200_attn_decode_smem_bytes(nh, nkv, hd, S);
+  if (B <= 0 || B > 65535 || smem < 0)
+    return fail(QB200_EINVAL, "attn_decode: needs nh %% nkv == 0, nh / nkv <= %d, hd in {64, 128, 256} and a cache that fits shared memory", kAttnMaxGroup);
+  if ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(cache_k) | reinterpret_cast<uintptr_t>(cache_v)) & 15)
+    return fail(QB200_EINVAL, "attn_decode: pointers must be 16-byte aligned");
+  static bool attr_set = false;
+  if (!attr_set) {
+    QB_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(nkv, B);
+  cfg.blockDim = dim3(kAttnThreads);
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl() ? 1 : 0;
+  QB_CUDA(cudaLaunchKernelEx(&cfg, attn_decode_kernel, reinterpret_cast<const __half*>(qkv), reinterpret_cast<const __half*>(cos_table),
+                             reinterpret_cast<const __half*>(sin_table), pos, reinterpret_cast<__half*>(out),
+                             reinterpret_cast<__half*>(cache_k), reinterpret_cast<__half*>(cache_v), nh, nkv, hd, S, scale));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return QB200_OK;
 }

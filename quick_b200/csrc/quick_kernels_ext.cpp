@@ -6,6 +6,7 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
 #include <torch/extension.h>
+#include <cmath>
 
 #include <mutex>
 #include <stdexcept>
@@ -207,6 +208,30 @@ torch::Tensor rope_kv_update(torch::Tensor qkv, torch::Tensor cos_table, torch::
   return q;
 }
 
+// Decode-step attention fused with rotary embedding + KV-cache update (C-ABI qb200_attn_decode): qkv [B, 1, (nh + 2 nkv) hd]
+// -> [B, 1, nh hd]; the caches are updated in place at position pos[0].
+torch::Tensor attn_decode(torch::Tensor qkv, torch::Tensor cos_table, torch::Tensor sin_table, torch::Tensor pos,
+                          torch::Tensor cache_k, torch::Tensor cache_v, int64_t nh, int64_t nkv) {
+  TORCH_CHECK(qkv.is_cuda() && qkv.dim() == 3 && qkv.size(1) == 1 && qkv.scalar_type() == torch::kHalf,
+              "attn_decode: qkv must be CUDA fp16 [B, 1, (nh + 2 nkv) hd]");
+  TORCH_CHECK(cache_k.is_contiguous() && cache_v.is_contiguous() && cache_k.dim() == 4 && cache_k.scalar_type() == torch::kHalf,
+              "attn_decode: caches must be contiguous fp16 [B, nkv, S, hd]");
+  TORCH_CHECK(pos.scalar_type() == torch::kLong && pos.is_cuda() && pos.numel() == 1, "attn_decode: pos must be a CUDA int64 tensor with one element");
+  const at::cuda::OptionalCUDAGuard device_guard(device_of(qkv));
+  torch::Tensor x = qkv.contiguous(), c = cos_table.contiguous(), s = sin_table.contiguous(), p = pos.contiguous();
+  const int B = static_cast<int>(x.size(0));
+  const int hd = static_cast<int>(x.size(2) / (nh + 2 * nkv)), S = static_cast<int>(cache_k.size(2));
+  TORCH_CHECK(x.size(2) == (nh + 2 * nkv) * hd && cache_k.size(3) == hd && cache_k.size(1) == nkv && cache_k.size(0) == B &&
+              cache_v.sizes() == cache_k.sizes(), "attn_decode: shape mismatch");
+  TORCH_CHECK(c.size(-1) == hd && c.size(0) >= S && s.sizes() == c.sizes(), "attn_decode: rotary table shape mismatch");
+  torch::Tensor out = torch::empty({B, 1, nh * hd}, x.options());
+  check(qb200_attn_decode(x.data_ptr<at::Half>(), c.data_ptr<at::Half>(), s.data_ptr<at::Half>(),
+                          reinterpret_cast<const long long*>(p.data_ptr<int64_t>()), out.data_ptr<at::Half>(),
+                          cache_k.data_ptr<at::Half>(), cache_v.data_ptr<at::Half>(), B, static_cast<int>(nh), static_cast<int>(nkv),
+                          hd, S, 1.0f / std::sqrt(static_cast<float>(hd)), at::cuda::getCurrentCUDAStream().stream()));
+  return out;
+}
+
 torch::Tensor silu_mul(torch::Tensor gate_up) {
   TORCH_CHECK(gate_up.is_cuda() && gate_up.scalar_type() == torch::kHalf, "silu_mul: CUDA fp16 tensor required");
   const at::cuda::OptionalCUDAGuard device_guard(device_of(gate_up));
@@ -224,6 +249,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("rmsnorm", &rmsnorm, "RMSNorm (fp16 in/out, fp32 statistics)");
   m.def("rope_kv_update", &rope_kv_update, "rotary embedding of q/k + static KV-cache update; returns q [B, nh, T, hd]");
   m.def("silu_mul", &silu_mul, "silu(gate) * up for rows [gate | up]");
+  m.def("attn_decode", &attn_decode, "one-token attention fused with rotary embedding + static KV-cache update; returns [B, 1, nh*hd]");
+  m.def("attn_decode_supported", [](int64_t nh, int64_t nkv, int64_t hd, int64_t S) {
+    return qb200_attn_decode_smem_bytes(static_cast<int>(nh), static_cast<int>(nkv), static_cast<int>(hd), static_cast<int>(S)) >= 0;
+  });
   m.def("gemm_forward_cuda_quick", &gemm_forward_cuda_quick, "QUICK AWQ GEMM kernel.");
   m.def("prepack_quick", &prepack_quick, "QUICK layout -> B200 layout (wq, sz)");
   m.def("gemm_forward_b200", &gemm_forward_b200, "W4A16 GEMM on B200-layout weights (bias fused)", pybind11::arg("in_feats"),

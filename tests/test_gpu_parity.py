@@ -507,3 +507,53 @@ def test_llama_like_runner_matches_dense_fp16_model(ops):
     for a, b in ((logits, ref_logits), (nxt, ref_nxt)):
         rms = b.float().pow(2).mean().sqrt().item()
         assert (a.float() - b.float()).abs().max().item() <= 3e-2 * rms + 1e-3, "runner logits drifted from the dense model"
+
+
+@pytest.mark.parametrize("nh,nkv,hd", [(8, 4, 64), (32, 32, 128), (32, 8, 128), (64, 8, 128)],
+                         ids=["tiny_gqa2_hd64", "mha_7b", "gqa4_mistral", "gqa8_70b"])
+def test_attn_decode_matches_rope_cache_update_plus_sdpa(ops, nh, nkv, hd):
+    """qb200_attn_decode (rotary + KV-cache update + one-token attention in one kernel) against the path it replaces
+    (qb200_rope_kv_update + torch SDPA over the masked static cache) and an fp32 softmax(q·kᵀ/√hd)·v of the same fp16
+    operands.  Cache writes must be bit-identical; outputs within 4e-3·rms + 1e-4 of the fp32 result (one fp16 rounding of
+    values up to ~4 rms).  Positions
+    beyond the current one hold NaN: they must never be read."""
+    import quick_kernels
+    import torch.nn.functional as F
+    S = 96
+    g = torch.Generator(device="cuda").manual_seed(nh * 131 + nkv)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, hd, 2, device="cuda").float() / hd))
+    ang = torch.outer(torch.arange(S, device="cuda").float(), inv)
+    ang = torch.cat((ang, ang), dim=-1)
+    cos, sin = ang.cos().half(), ang.sin().half()
+    assert quick_kernels.attn_decode_supported(nh, nkv, hd, S)
+    for B in (1, 3):
+        for p in (0, 1, 37, S - 1):
+            qkv = torch.randn(B, 1, (nh + 2 * nkv) * hd, device="cuda", generator=g).half()
+            ck = torch.randn(B, nkv, S, hd, device="cuda", generator=g).half()
+            cv = torch.randn(B, nkv, S, hd, device="cuda", generator=g).half()
+            ck[:, :, p + 1:] = float("nan"); cv[:, :, p + 1:] = float("nan")
+            pos = torch.tensor([p], device="cuda")
+            ck_ref, cv_ref = ck.clone(), cv.clone()
+            q = quick_kernels.rope_kv_update(qkv, cos, sin, pos, ck_ref, cv_ref, nh, nkv)          # [B, nh, 1, hd]
+            ck_new, cv_new = ck.clone(), cv.clone()
+            out = quick_kernels.attn_decode(qkv, cos, sin, pos, ck_new, cv_new, nh, nkv)
+            assert out.shape == (B, 1, nh * hd) and out.dtype == torch.float16
+            assert torch.equal(ck_new[:, :, :p + 1], ck_ref[:, :, :p + 1]) and torch.equal(cv_new[:, :, :p + 1], cv_ref[:, :, :p + 1])
+            assert torch.isnan(ck_new[:, :, p + 1:]).all() and torch.isnan(cv_new[:, :, p + 1:]).all()   # nothing else written
+            kf = ck_ref[:, :, :p + 1].float().repeat_interleave(nh // nkv, dim=1)                   # [B, nh, L, hd]
+            vf = cv_ref[:, :, :p + 1].float().repeat_interleave(nh // nkv, dim=1)
+            w = torch.softmax((q.float() @ kf.transpose(-1, -2)) / hd ** 0.5, dim=-1)
+            exact = (w @ vf).transpose(1, 2).reshape(B, 1, nh * hd)
+            rms = exact.pow(2).mean().sqrt().item()
+            err = (out.float() - exact).abs().max().item()
+            assert not torch.isnan(out).any() and err <= 4e-3 * rms + 1e-4, f"B={B} p={p}: max|err|={err:.3g} rms={rms:.3g}"
+            # the path it replaces, on the same cache
+            keys = torch.arange(S, device="cuda")
+            mask = keys[None, :] <= pos[:, None]
+            sd = F.scaled_dot_product_attention(q, torch.nan_to_num(ck_ref), torch.nan_to_num(cv_ref), attn_mask=mask, enable_gqa=(nkv != nh))
+            sd = sd.transpose(1, 2).reshape(B, 1, nh * hd)
+            assert (out.float() - sd.float()).abs().max().item() <= 1e-2 * rms + 5e-4, f"B={B} p={p}: differs from the SDPA path"
+    assert not quick_kernels.attn_decode_supported(32, 2, 128, 96) and not quick_kernels.attn_decode_supported(32, 8, 96, 96)
+    with pytest.raises(Exception):
+        quick_kernels.attn_decode(torch.zeros(1, 2, (nh + 2 * nkv) * hd, device="cuda", dtype=torch.float16), cos, sin,
+                                  torch.tensor([0], device="cuda"), ck_new[:1], cv_new[:1], nh, nkv)
