@@ -150,7 +150,7 @@ int qb200_rope_kv_update(const void* qkv_fp16, const void* cos_table_fp16, const
  * positions are attended (softmax in fp32, scale = 1/sqrt(hd) usually).  The reference does this in
  * QuantAttentionFused.forward's single-token branch (quick/awq/modules/fused/attn.py:187-245) through awq_ext kernels
  * that are not part of its tree.  qb200_attn_decode_smem_bytes returns -1 when the configuration is not supported
- * (nh / nkv > 8, hd not in {64, 128, 256}, or a cache too long for shared memory). */
+ * (nh / nkv not in {1, 2, 4, 8}, hd not in {64, 128, 256}, or a cache too long for shared memory). */
 int qb200_attn_decode_smem_bytes(int nh, int nkv, int hd, int S);
 int qb200_attn_decode(const void* qkv_fp16, const void* cos_table_fp16, const void* sin_table_fp16, const long long* pos,
                       void* out_fp16, void* cache_k_fp16, void* cache_v_fp16, int B, int nh, int nkv, int hd, int S, float scale,

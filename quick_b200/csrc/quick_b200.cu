@@ -373,27 +373,41 @@ __host__ __device__ constexpr size_t attn_decode_smem(int g, int hd, int S) {
          static_cast<size_t>(kAttnThreads / (hd / 2)) * g * hd * 4 + kAttnMaxGroup * 4;
 }
 
+template <int VEC>
+__device__ __forceinline__ void attn_load_row(const __half* p, float (&f)[VEC]) {   // VEC consecutive fp16 -> fp32
+  __align__(16) __half h[VEC];
+  if constexpr (VEC == 2) *reinterpret_cast<uint32_t*>(h) = *reinterpret_cast<const uint32_t*>(p);
+  else if constexpr (VEC == 4) *reinterpret_cast<uint2*>(h) = *reinterpret_cast<const uint2*>(p);
+  else *reinterpret_cast<uint4*>(h) = *reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int u = 0; u < VEC; ++u) f[u] = __half2float(h[u]);
+}
+
+template <int HD, int G>
 __global__ void __launch_bounds__(kAttnThreads)
 attn_decode_kernel(const __half* __restrict__ qkv, const __half* __restrict__ cosb, const __half* __restrict__ sinb,
                    const long long* __restrict__ pos, __half* __restrict__ out, __half* __restrict__ cache_k,
-                   __half* __restrict__ cache_v, int nh, int nkv, int hd, int S, float scale) {
+                   __half* __restrict__ cache_v, int nh, int nkv, int S, float scale) {
   qb200::pdl_launch_dependents();
   qb200::pdl_wait_prior_grid();
   extern __shared__ __align__(16) uint8_t attn_smem[];
-  const int kvh = blockIdx.x, b = blockIdx.y, g = nh / nkv;
+  constexpr int hd = HD, g = G;
+  constexpr int VEC = HD / 32;                           // halves of a row owned by one lane (2, 4 or 8)
+  constexpr int kWarps = kAttnThreads / 32;
+  constexpr int kBatch = 4;                              // cache rows a warp has in flight
+  const int kvh = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int p = static_cast<int>(pos[0]);
-  const int L = p + 1;                                   // visible positions 0 .. p
+  const int p = static_cast<int>(pos[0]);                // the new position; positions 0 .. p are visible
   __half* qs = reinterpret_cast<__half*>(attn_smem);     // [g][hd]
   __half* ks = qs + g * hd;                              // [hd]
   __half* vs = ks + hd;                                  // [hd]
   float* sc = reinterpret_cast<float*>(vs + hd);         // [g][S]
-  const int tpd = hd >> 1, nsl = kAttnThreads / tpd;     // threads per P·V slice (one half2 each), slices
+  constexpr int tpd = hd >> 1, nsl = kAttnThreads / tpd; // threads per P·V slice (one half2 each), slices
   float* red = sc + static_cast<size_t>(g) * S;          // [nsl][g][hd]
   float* inv = red + static_cast<size_t>(nsl) * g * hd;  // [g]
   const __half* src = qkv + static_cast<size_t>(b) * (nh + 2 * nkv) * hd;
   const size_t crow = (static_cast<size_t>(b) * nkv + kvh) * S;   // first cache row of this (sequence, kv head)
-  const int half_hd = hd >> 1;
+  constexpr int half_hd = hd >> 1;
 
   for (int idx = tid; idx < (g + 2) * hd; idx += kAttnThreads) {
     const int hl = idx / hd, i = idx - hl * hd;
@@ -417,37 +431,46 @@ attn_decode_kernel(const __half* __restrict__ qkv, const __half* __restrict__ co
   }
   __syncthreads();
 
-  for (int j = tid; j < L; j += kAttnThreads) {           // scores: one thread per position, all g heads at once
-    const __half* krow = j == p ? ks : cache_k + (crow + j) * hd;
-    float acc[kAttnMaxGroup];
+  {   // scores: a warp per position (one coalesced row read, lane = VEC consecutive dims), kBatch rows in flight per warp
+    float qf[G][VEC];                                    // this lane's slice of every query head of the group
 #pragma unroll
-    for (int h = 0; h < kAttnMaxGroup; ++h) acc[h] = 0.f;
-    for (int d = 0; d < hd; d += 8) {
-      const uint4 kv = *reinterpret_cast<const uint4*>(krow + d);
-      const __half2* k2 = reinterpret_cast<const __half2*>(&kv);
-      float2 kf[4];
+    for (int h = 0; h < G; ++h)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) kf[u] = __half22float2(k2[u]);
+      for (int u = 0; u < VEC; ++u) qf[h][u] = __half2float(qs[h * hd + lane * VEC + u]);
+    auto score = [&](const float (&kf)[VEC], int j) {
 #pragma unroll
-      for (int h = 0; h < kAttnMaxGroup; ++h) {
-        if (h < g) {
-          const uint4 qv = *reinterpret_cast<const uint4*>(qs + h * hd + d);   // same address in every thread: broadcast
-          const __half2* q2 = reinterpret_cast<const __half2*>(&qv);
+      for (int h = 0; h < G; ++h) {
+        float a = 0.f;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float2 qf = __half22float2(q2[u]);
-            acc[h] = fmaf(qf.x, kf[u].x, acc[h]);
-            acc[h] = fmaf(qf.y, kf[u].y, acc[h]);
-          }
-        }
+        for (int u = 0; u < VEC; ++u) a = fmaf(qf[h][u], kf[u], a);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) sc[static_cast<size_t>(h) * S + j] = a * scale;
+      }
+    };
+    const __half* kbase = cache_k + crow * hd + lane * VEC;
+    for (int j0 = warp; j0 < p; j0 += kWarps * kBatch) {            // cached positions 0 .. p-1 (warp-uniform bounds)
+      float kf[kBatch][VEC];
+#pragma unroll
+      for (int t = 0; t < kBatch; ++t) {
+        const int j = j0 + t * kWarps;
+        if (j < p) attn_load_row<VEC>(kbase + static_cast<size_t>(j) * hd, kf[t]);
+      }
+#pragma unroll
+      for (int t = 0; t < kBatch; ++t) {
+        const int j = j0 + t * kWarps;
+        if (j < p) score(kf[t], j);
       }
     }
-#pragma unroll
-    for (int h = 0; h < kAttnMaxGroup; ++h)
-      if (h < g) sc[static_cast<size_t>(h) * S + j] = acc[h] * scale;
+    if (warp == 0) {                                     // the new position, from shared memory
+      float kf[VEC];
+      attn_load_row<VEC>(ks + lane * VEC, kf);
+      score(kf, p);
+    }
   }
   __syncthreads();
 
+  const int L = p + 1;
   if (warp < g) {                                         // softmax of head `warp` over L scores, fp32
     float* row = sc + static_cast<size_t>(warp) * S;
     float m = -INFINITY;
@@ -466,32 +489,44 @@ attn_decode_kernel(const __half* __restrict__ qkv, const __half* __restrict__ co
   }
   __syncthreads();
 
-  {                                                       // P·V: slice sl takes positions sl, sl + nsl, ...; thread = one half2 of the head dim
+  {   // P·V: slice sl takes cached positions sl, sl + nsl, ... (8 rows in flight); thread = one half2 of the head dim
     const int sl = tid / tpd, dl = (tid - sl * tpd) * 2;
-    float2 acc[kAttnMaxGroup];
+    constexpr int kPV = 8;
+    float2 acc[G];
 #pragma unroll
-    for (int h = 0; h < kAttnMaxGroup; ++h) acc[h] = make_float2(0.f, 0.f);
-    for (int j = sl; j < L; j += nsl) {
-      const __half* vrow = j == p ? vs : cache_v + (crow + j) * hd;
-      const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(vrow + dl));
+    for (int h = 0; h < G; ++h) acc[h] = make_float2(0.f, 0.f);
+    auto fma_row = [&](float2 vf, int j) {
 #pragma unroll
-      for (int h = 0; h < kAttnMaxGroup; ++h) {
-        if (h < g) {
-          const float pj = sc[static_cast<size_t>(h) * S + j];
-          acc[h].x = fmaf(pj, vf.x, acc[h].x);
-          acc[h].y = fmaf(pj, vf.y, acc[h].y);
-        }
+      for (int h = 0; h < G; ++h) {
+        const float pj = sc[static_cast<size_t>(h) * S + j];
+        acc[h].x = fmaf(pj, vf.x, acc[h].x);
+        acc[h].y = fmaf(pj, vf.y, acc[h].y);
+      }
+    };
+    const __half* vbase = cache_v + crow * hd + dl;
+    for (int j0 = sl; j0 < p; j0 += nsl * kPV) {
+      __half2 v2[kPV];
+#pragma unroll
+      for (int t = 0; t < kPV; ++t) {
+        const int j = j0 + t * nsl;
+        if (j < p) v2[t] = *reinterpret_cast<const __half2*>(vbase + static_cast<size_t>(j) * hd);
+      }
+#pragma unroll
+      for (int t = 0; t < kPV; ++t) {
+        const int j = j0 + t * nsl;
+        if (j < p) fma_row(__half22float2(v2[t]), j);
       }
     }
+    if (sl == 0) fma_row(__half22float2(*reinterpret_cast<const __half2*>(vs + dl)), p);   // the new position
 #pragma unroll
-    for (int h = 0; h < kAttnMaxGroup; ++h)
-      if (h < g) *reinterpret_cast<float2*>(red + (static_cast<size_t>(sl) * g + h) * hd + dl) = acc[h];
+    for (int h = 0; h < G; ++h) *reinterpret_cast<float2*>(red + (static_cast<size_t>(sl) * g + h) * hd + dl) = acc[h];
   }
   __syncthreads();
 
   for (int idx = tid; idx < g * hd; idx += kAttnThreads) {
     const int h = idx / hd, d = idx - h * hd;
     float t = 0.f;
+#pragma unroll
     for (int sl = 0; sl < nsl; ++sl) t += red[(static_cast<size_t>(sl) * g + h) * hd + d];
     out[static_cast<size_t>(b) * nh * hd + static_cast<size_t>(kvh * g + h) * hd + d] = __float2half_rn(t * inv[h]);
   }
@@ -1021,7 +1056,9 @@ int qb200_rope_kv_update(const void* qkv, const void* cos_table, const void* sin
 }
 
 int qb200_attn_decode_smem_bytes(int nh, int nkv, int hd, int S) {
-  if (nh <= 0 || nkv <= 0 || nh % nkv != 0 || nh / nkv > kAttnMaxGroup || (hd != 64 && hd != 128 && hd != 256) || S <= 0) return -1;
+  if (nh <= 0 || nkv <= 0 || nh % nkv != 0 || (hd != 64 && hd != 128 && hd != 256) || S <= 0) return -1;
+  const int grp = nh / nkv;
+  if (grp != 1 && grp != 2 && grp != 4 && grp != 8) return -1;     // instantiated query-group sizes
   const size_t need = attn_decode_smem(nh / nkv, hd, S);
   return need <= 200 * 1024 ? static_cast<int>(need) : -1;
 }
@@ -1030,13 +1067,22 @@ int qb200_attn_decode(const void* qkv, const void* cos_table, const void* sin_ta
                       void* cache_k, void* cache_v, int B, int nh, int nkv, int hd, int S, float scale, void* stream) {
   const int smem = qb200_attn_decode_smem_bytes(nh, nkv, hd, S);
   if (B <= 0 || B > 65535 || smem < 0)
-    return fail(QB200_EINVAL, "attn_decode: needs nh %% nkv == 0, nh / nkv <= %d, hd in {64, 128, 256} and a cache that fits shared memory", kAttnMaxGroup);
+    return fail(QB200_EINVAL, "attn_decode: needs nh / nkv in {1, 2, 4, 8}, hd in {64, 128, 256} and a cache that fits shared memory (g*S*4 bytes <= ~190 KB)");
   if ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(cache_k) | reinterpret_cast<uintptr_t>(cache_v)) & 15)
     return fail(QB200_EINVAL, "attn_decode: pointers must be 16-byte aligned");
-  static bool attr_set = false;
-  if (!attr_set) {
-    QB_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+  using AttnFn = void (*)(const __half*, const __half*, const __half*, const long long*, __half*, __half*, __half*, int, int, int, float);
+  static const AttnFn table[3][4] = {
+      {attn_decode_kernel<64, 1>, attn_decode_kernel<64, 2>, attn_decode_kernel<64, 4>, attn_decode_kernel<64, 8>},
+      {attn_decode_kernel<128, 1>, attn_decode_kernel<128, 2>, attn_decode_kernel<128, 4>, attn_decode_kernel<128, 8>},
+      {attn_decode_kernel<256, 1>, attn_decode_kernel<256, 2>, attn_decode_kernel<256, 4>, attn_decode_kernel<256, 8>}};
+  static bool attr_set[12] = {};
+  const int grp = nh / nkv;
+  const int hi = hd == 64 ? 0 : hd == 128 ? 1 : 2, gi = grp == 1 ? 0 : grp == 2 ? 1 : grp == 4 ? 2 : 3;
+  const AttnFn kfn = table[hi][gi];
+  const int ki = hi * 4 + gi;
+  if (!attr_set[ki]) {
+    QB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set[ki] = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(nkv, B);
@@ -1048,9 +1094,9 @@ int qb200_attn_decode(const void* qkv, const void* cos_table, const void* sin_ta
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl() ? 1 : 0;
-  QB_CUDA(cudaLaunchKernelEx(&cfg, attn_decode_kernel, reinterpret_cast<const __half*>(qkv), reinterpret_cast<const __half*>(cos_table),
+  QB_CUDA(cudaLaunchKernelEx(&cfg, kfn, reinterpret_cast<const __half*>(qkv), reinterpret_cast<const __half*>(cos_table),
                              reinterpret_cast<const __half*>(sin_table), pos, reinterpret_cast<__half*>(out),
-                             reinterpret_cast<__half*>(cache_k), reinterpret_cast<__half*>(cache_v), nh, nkv, hd, S, scale));
+                             reinterpret_cast<__half*>(cache_k), reinterpret_cast<__half*>(cache_v), nh, nkv, S, scale));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return QB200_OK;
 }
