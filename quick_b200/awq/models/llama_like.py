@@ -28,6 +28,10 @@ FUSED_GLUE = True
 # (qb200_attn_decode) instead of rope_kv_update + mask arithmetic + torch SDPA.  QB200_ATTN_DECODE=0 keeps the SDPA path.
 import os as _os0
 ATTN_DECODE = _os0.environ.get("QB200_ATTN_DECODE", "1") != "0"
+# Measured on B200, Llama-2-7B shapes, cache length 192 (profiles/r1e_*): +1.6 % decode tok/s at batch 1, +2.5 % at 8,
+# -4 % at 64 (one CTA per (kv head, sequence) re-reads nothing but also shares nothing; cuDNN's kernel wins once there
+# are thousands of rows) -> larger batches keep the SDPA path.
+ATTN_DECODE_MAX_BATCH = int(_os0.environ.get("QB200_ATTN_DECODE_MAX_BATCH", "16"))
 
 
 @dataclass
@@ -276,10 +280,12 @@ class LlamaLikeQuickModel(nn.Module):
         self.ref_mod = None   # set to the oracle/_ref module to time the reference kernel inside the same runner
 
     def _fused_decode_ok(self, x) -> bool:
-        """One new token per sequence, CUDA, fused glue on, whole batch present, and a (heads, cache length) the
-        single-kernel decode attention supports; anything else takes the rope_kv_update + SDPA path."""
+        """One new token per sequence, CUDA, fused glue on, whole batch present, a batch small enough for it to pay
+        off, and a (heads, cache length) the single-kernel decode attention supports; anything else takes the
+        rope_kv_update + SDPA path."""
         cfg = self.cfg
-        if not (ATTN_DECODE and FUSED_GLUE and x.is_cuda and x.shape[1] == 1 and x.shape[0] == self.batch):
+        if not (ATTN_DECODE and FUSED_GLUE and x.is_cuda and x.shape[1] == 1 and x.shape[0] == self.batch
+                and self.batch <= ATTN_DECODE_MAX_BATCH):
             return False
         if self._attn_decode_supported is None:
             self._attn_decode_supported = bool(quick_kernels.attn_decode_supported(cfg.num_heads, cfg.num_kv_heads, cfg.head_dim,
