@@ -23,7 +23,7 @@ import gc
 import json
 import os
 import re
-from typing import Dict, List, Optional, Union
+from typing import Dict, List, Union
 
 import torch
 import torch.nn as nn

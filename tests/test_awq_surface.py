@@ -309,3 +309,25 @@ def test_auto_rejects_unknown_family_and_bare_ctor(tmp_path):
         AutoAWQForCausalLM()
     with pytest.raises(FileNotFoundError):
         AutoAWQForCausalLM.from_quantized(str(tmp_path / "missing"))
+
+
+def test_perplexity_windows_and_loss(tmp_path):
+    """evaluate_perplexity == exp(mean next-token NLL over non-overlapping windows) (reference eval_utils.py:20-66),
+    on the fp model (no GEMM kernel involved on CPU)."""
+    from quick_b200.awq.evaluation import evaluate_perplexity
+    model = AutoAWQForCausalLM.from_pretrained(_tiny_hf(tmp_path, layers=1), device_map="cpu", torch_dtype=torch.float32)
+    ids = torch.randint(0, 512, (1, 100), generator=torch.Generator().manual_seed(2))
+    ppl = evaluate_perplexity(model, None, ids, seqlen=32)
+    nll = []
+    with torch.no_grad():
+        for i in range(3):                                       # 100 // 32 windows, the tail is dropped
+            w = ids[:, 32 * i:32 * (i + 1)]
+            lg = model.model(w).logits.float()
+            nll.append(torch.nn.functional.cross_entropy(lg[0, :-1], w[0, 1:]) * 32)
+    assert abs(ppl - float(torch.exp(torch.stack(nll).sum() / 96))) < 1e-3 * ppl
+    assert 100 < ppl < 5000                                      # random-init model over a 512-token vocabulary
+    assert evaluate_perplexity(model, None, ids, seqlen=32, max_windows=1) > 0
+    with pytest.raises(ValueError):
+        evaluate_perplexity(model, None, ids, seqlen=256)
+    with pytest.raises(ValueError):
+        evaluate_perplexity(model, None, "text without tokenizer")
