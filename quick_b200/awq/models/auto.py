@@ -1,15 +1,18 @@
 """AutoAWQForCausalLM — same entry points and argument names as the reference (quick/awq/models/auto.py:27-99).
-Families: the ones BASELINE.json's configs name (Llama-2, Mistral) plus those that share the Llama decoder layout; the
+Families: the ones BASELINE.json's configs name (Llama-2, Mistral) plus Qwen2, which shares the Llama decoder layout
+(with biased q / k / v); the
 reference's other adapters (mpt, opt, falcon, bloom, gptj, …) wrap model code that is outside the W4A16 hot path."""
 import os
 
 from .base import BaseAWQForCausalLM
 from .llama import LlamaAWQForCausalLM
 from .mistral import MistralAWQForCausalLM
+from .qwen2 import Qwen2AWQForCausalLM
 
 AWQ_CAUSAL_LM_MODEL_MAP = {
     "llama": LlamaAWQForCausalLM,
     "mistral": MistralAWQForCausalLM,
+    "qwen2": Qwen2AWQForCausalLM,
 }
 
 

@@ -496,7 +496,7 @@ def fuse_hf_model(model, batch_size: int = 1, max_seq_len: Optional[int] = None)
     if getattr(hc, "head_dim", None) not in (None, hc.hidden_size // nh):
         raise NotImplementedError("head_dim != hidden_size / num_attention_heads")
     seq = int(max_seq_len or getattr(hc, "max_new_tokens", None) or 2048)
-    window = getattr(hc, "sliding_window", None)
+    window = getattr(hc, "sliding_window", None) if getattr(hc, "use_sliding_window", True) else None
     if window:
         seq = min(seq, int(window))
     cfg = LlamaLikeConfig(hc.hidden_size, hc.intermediate_size, len(layers), nh, nkv, hc.vocab_size, seq,

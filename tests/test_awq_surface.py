@@ -27,9 +27,11 @@ def _tiny_hf(tmp_path, family="llama", layers=2, tie=False):
     import transformers
     kw = dict(hidden_size=256, intermediate_size=512, num_hidden_layers=layers, num_attention_heads=4,
               num_key_value_heads=2, vocab_size=512, max_position_embeddings=128, tie_word_embeddings=tie)
-    cfg = transformers.LlamaConfig(**kw) if family == "llama" else transformers.MistralConfig(sliding_window=64, **kw)
+    cfg_cls, cls = {"llama": (transformers.LlamaConfig, transformers.LlamaForCausalLM),
+                    "mistral": (transformers.MistralConfig, transformers.MistralForCausalLM),
+                    "qwen2": (transformers.Qwen2Config, transformers.Qwen2ForCausalLM)}[family]
+    cfg = cfg_cls(sliding_window=64, **kw) if family == "mistral" else cfg_cls(**kw)
     torch.manual_seed(0)
-    cls = transformers.LlamaForCausalLM if family == "llama" else transformers.MistralForCausalLM
     model = cls(cfg).half()
     path = str(tmp_path / f"fp16_{family}")
     model.save_pretrained(path)
@@ -178,7 +180,7 @@ def test_shard_state_dict():
 
 
 # ---------------------------------------------------------------------------------------------- end to end on CPU
-@pytest.mark.parametrize("family", ["llama", "mistral"])
+@pytest.mark.parametrize("family", ["llama", "mistral", "qwen2"])
 def test_quantize_save_load_roundtrip(tmp_path, family):
     fp_path = _tiny_hf(tmp_path, family)
     model = AutoAWQForCausalLM.from_pretrained(fp_path, device_map="cpu", torch_dtype=torch.float32)
@@ -246,6 +248,11 @@ def test_quantize_save_load_roundtrip(tmp_path, family):
     assert torch.equal(fq, torch.cat([p[0] for p in q_parts], 1)) and torch.equal(fz, torch.cat([p[1] for p in q_parts], 1))
     assert torch.equal(fs, torch.cat([p[2] for p in q_parts], 1))
     assert blk.cache_k.shape == (3, 2, runner.cfg.max_seq_len, 64)
+    if family == "qwen2":                                                        # biased q / k / v: concatenated like the weights
+        a = ref_layer.self_attn
+        assert torch.equal(blk.qkv_proj.bias, torch.cat([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias]))
+    else:
+        assert blk.qkv_proj.bias is None
     with pytest.raises(RuntimeError, match="un-fused"):
         fused.save_quantized(str(tmp_path / "nope"))
     with pytest.raises(ValueError, match="KV-cache batch"):
