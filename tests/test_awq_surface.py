@@ -112,6 +112,24 @@ def test_search_matches_reference_quantizer(path):
     assert c.shape == d["clip_down"].shape
     same = np.isclose(c.numpy(), d["clip_down"], rtol=1e-6, atol=0)
     assert same.mean() > 0.995, f"clip thresholds differ in {(~same).sum()} of {same.size} groups"
+    # folding: the reference's scale_ln_fcs / scale_fc_fc / apply_clip (scale.py:16-26, 63-101) on the same layer
+    class Holder(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.norm = nn.LayerNorm(int(d["H"]))
+            self.mlp = mlp
+    layer = Holder()
+    layer.norm.weight.data = torch.from_numpy(d["norm_w"].copy()); layer.norm.bias.data = torch.from_numpy(d["norm_b"].copy())
+    feats = {"mlp.down_proj": h.clone()}
+    with torch.no_grad():
+        qz.apply_scale(layer, [("norm", ("mlp.gate_proj", "mlp.up_proj"), torch.from_numpy(d["scales_gate_up"].copy())),
+                               ("mlp.up_proj", ("mlp.down_proj",), torch.from_numpy(d["scales_down"].copy()))], feats)
+    for got, key in ((layer.norm.weight, "fold_norm_w"), (layer.norm.bias, "fold_norm_b"), (mlp.gate_proj.weight, "fold_gate"),
+                     (mlp.up_proj.weight, "fold_up"), (mlp.down_proj.weight, "fold_down")):
+        assert np.array_equal(got.detach().numpy(), d[key]), key
+    assert torch.equal(feats["mlp.down_proj"], h / torch.from_numpy(d["scales_down"]).view(1, -1))
+    qz.apply_clip(layer, [("mlp.down_proj", torch.from_numpy(d["clip_down"].copy()))])
+    assert np.array_equal(mlp.down_proj.weight.detach().numpy(), d["clip_applied_down"])
 
 
 def test_apply_scale_preserves_function():
