@@ -285,7 +285,7 @@ class LlamaLikeQuickModel(nn.Module):
         rope_kv_update + SDPA path."""
         cfg = self.cfg
         if not (ATTN_DECODE and FUSED_GLUE and x.is_cuda and x.shape[1] == 1 and x.shape[0] == self.batch
-                and self.batch <= ATTN_DECODE_MAX_BATCH):
+                and self.batch <= ATTN_DECODE_MAX_BATCH and tp_world() == 1):     # not yet validated on several GPUs
             return False
         if self._attn_decode_supported is None:
             self._attn_decode_supported = bool(quick_kernels.attn_decode_supported(cfg.num_heads, cfg.num_kv_heads, cfg.head_dim,
