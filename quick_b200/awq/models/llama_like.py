@@ -32,6 +32,9 @@ ATTN_DECODE = _os0.environ.get("QB200_ATTN_DECODE", "1") != "0"
 # -4 % at 64 (one CTA per (kv head, sequence) re-reads nothing but also shares nothing; cuDNN's kernel wins once there
 # are thousands of rows) -> larger batches keep the SDPA path.
 ATTN_DECODE_MAX_BATCH = int(_os0.environ.get("QB200_ATTN_DECODE_MAX_BATCH", "16"))
+# One CTA streams the whole cache of its (kv head, sequence): measured at a cache of 192 positions only; long caches
+# want the positions split over several CTAs (flash-decoding), which SDPA does -> keep it for caches beyond this.
+ATTN_DECODE_MAX_CACHE = int(_os0.environ.get("QB200_ATTN_DECODE_MAX_CACHE", "1024"))
 
 
 @dataclass
@@ -285,7 +288,8 @@ class LlamaLikeQuickModel(nn.Module):
         rope_kv_update + SDPA path."""
         cfg = self.cfg
         if not (ATTN_DECODE and FUSED_GLUE and x.is_cuda and x.shape[1] == 1 and x.shape[0] == self.batch
-                and self.batch <= ATTN_DECODE_MAX_BATCH and tp_world() == 1):     # not yet validated on several GPUs
+                and self.batch <= ATTN_DECODE_MAX_BATCH and cfg.max_seq_len <= ATTN_DECODE_MAX_CACHE
+                and tp_world() == 1):     # not yet validated on several GPUs
             return False
         if self._attn_decode_supported is None:
             self._attn_decode_supported = bool(quick_kernels.attn_decode_supported(cfg.num_heads, cfg.num_kv_heads, cfg.head_dim,
