@@ -183,8 +183,9 @@ unsigned long long qb200_launch_count(void);
 /* Debug only: device buffer of >= 6*256*4 int64 that CTA (0,0,0) of every later GEMM launch fills with
  * clock64() stamps per warp role and k-stage (NULL disables; disabled by default). */
 void qb200_debug_set_trace(void* device_buffer);
-/* Debug only: selects the alternative tile configurations (ring depths / warpgroup counts) compiled into
- * QB200_VARIANTS builds for A/B measurements; 0 = default.  No effect in the shipped library. */
+/* Debug only: forces one of the tile configurations (ring depths / warpgroup and issuer counts) compiled into
+ * QB200_VARIANTS builds for A/B measurements; -1 = the launch planner's choice (default).  No effect in the
+ * shipped library, where the planner always chooses. */
 void qb200_debug_set_variant(int variant);
 
 #ifdef __cplusplus

@@ -560,7 +560,10 @@ __global__ void silu_mul_kernel(const __half* __restrict__ gu, __half* __restric
 // flags go out, and whatever runs next on this stream sees every peer's slab.  The epoch lives on the device, so a
 // CUDA-graph replay hands out fresh epochs.
 struct PeerFlagPtrs { unsigned* p[8]; };
-__global__ void peer_barrier_kernel(unsigned* epoch_counter, PeerFlagPtrs flags, int rank, int n_peers) {
+// timeout_ns: 0 = wait for ever (like NCCL); otherwise a rank that has not seen all peers after that long (%globaltimer,
+// independent of the SM clock) traps so that a lost peer does not hang the GPU.  Host-side skew between ranks (rank-0-only
+// tokenizing, GC pauses, lazy relayout, graph capture) is legitimate, so the default is long (QB200_PEER_TIMEOUT_S, 120 s).
+__global__ void peer_barrier_kernel(unsigned* epoch_counter, PeerFlagPtrs flags, int rank, int n_peers, unsigned long long timeout_ns) {
   __shared__ unsigned e_sh;
   if (threadIdx.x == 0) e_sh = atomicAdd(epoch_counter, 1u) + 1u;
   __syncthreads();
@@ -569,11 +572,16 @@ __global__ void peer_barrier_kernel(unsigned* epoch_counter, PeerFlagPtrs flags,
     __threadfence_system();
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags.p[threadIdx.x] + rank), "r"(e) : "memory");
     const unsigned* mine = flags.p[rank] + threadIdx.x;
-    const long long t0 = clock64();
-    unsigned v;
+    unsigned long long t0 = 0;
+    unsigned v, polls = 0;
     do {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-      if (clock64() - t0 > 4000000000ll) __trap();   // ~2 s: a lost peer traps instead of hanging the GPU
+      if (timeout_ns != 0 && (++polls & 1023u) == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > timeout_ns) __trap();
+      }
     } while (static_cast<int>(v - e) < 0);
   }
 }
@@ -615,15 +623,39 @@ int make_x_tensor_map(CUtensorMap* map, const void* A, int M, int K, int tok) {
 // ------------------------------------------------------------------------------------------------
 // GEMM launch
 // ------------------------------------------------------------------------------------------------
-int device_sm_count() {
-  static int sms = -1;
-  if (sms < 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
-  }
-  return sms;
+// Everything CUDA keeps per device is cached per device here (a process may drive several GPUs: device_map,
+// the quantizer's work device, tests): SM count, architecture check, dynamic shared-memory opt-ins.
+constexpr int kMaxDevices = 64;
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+  return dev;
 }
+int device_sm_count() {
+  static std::atomic<int> sms[kMaxDevices];   // zero-initialised: 0 = not queried yet
+  const int dev = current_device();
+  if (dev < 0) return 148;
+  int v = sms[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    sms[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+// One bit per device: has cudaFuncSetAttribute(MaxDynamicSharedMemorySize) been applied to this kernel there?
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  template <typename F>
+  cudaError_t ensure(F&& set) {
+    const int dev = current_device();
+    if (dev < 0) return set();
+    const unsigned long long bit = 1ull << dev;
+    if (mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    const cudaError_t e = set();
+    if (e == cudaSuccess) mask.fetch_or(bit, std::memory_order_release);
+    return e;
+  }
+};
 
 bool use_pdl() {   // QB200_NO_PDL=1 disables programmatic dependent launch (A/B measurements)
   static int v = -1;
@@ -648,18 +680,41 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStre
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-std::atomic<int> g_variant{0};         // tile-configuration variant (qb200_debug_set_variant): 0 = default
-std::atomic<int> g_skip_pdl_once{0};   // set by the layout kernels: the GEMM that follows must not prefetch their output early
+std::atomic<int> g_variant{-1};        // tile-configuration variant forced by qb200_debug_set_variant (QB200_VARIANTS builds); -1 = planner
+// Streams on which a layout kernel has just written wq / sz: the next GEMM on THAT stream must not prefetch its
+// weights ahead of griddepcontrol.wait, so it launches without the programmatic attribute.  Tracked per stream
+// (a process-wide flag could be consumed by an unrelated GEMM on another stream or thread).
+std::mutex g_relayout_mu;
+cudaStream_t g_relayout_streams[16];
+int g_relayout_n = 0;
+std::atomic<int> g_relayout_overflow{0};
+void note_relayout(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_relayout_mu);
+  for (int i = 0; i < g_relayout_n; ++i)
+    if (g_relayout_streams[i] == st) return;
+  if (g_relayout_n == 16) {   // table full (16 streams with a pending relayout): be conservative, the next GEMM
+    g_relayout_overflow.store(1, std::memory_order_relaxed);   // launched anywhere serialises fully
+    return;
+  }
+  g_relayout_streams[g_relayout_n++] = st;
+}
+bool take_relayout(cudaStream_t st) {   // true: a layout kernel precedes this launch on the stream
+  std::lock_guard<std::mutex> lk(g_relayout_mu);
+  for (int i = 0; i < g_relayout_n; ++i) {
+    if (g_relayout_streams[i] == st) {
+      g_relayout_streams[i] = g_relayout_streams[--g_relayout_n];
+      return true;
+    }
+  }
+  return g_relayout_overflow.exchange(0, std::memory_order_relaxed) != 0;
+}
 
 template <int TOK, int SPLIT, int VAR>
 int launch_umma(const CUtensorMap& map, const qb200::GemmArgs& args, int m_tiles, cudaStream_t stream) {
   using Cfg = qb200::TileCfg<TOK, VAR>;
   auto kfn = qb200::w4a16_umma_kernel<TOK, SPLIT, VAR>;
-  static bool attr_set = false;   // per instantiation
-  if (!attr_set) {
-    QB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes(SPLIT)));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;   // per instantiation and device
+  QB_CUDA(attr_once.ensure([&] { return cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes(SPLIT)); }));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(args.N / qb200::kChan, m_tiles, SPLIT);
   cfg.blockDim = dim3(Cfg::kNumThreads);
@@ -675,7 +730,7 @@ int launch_umma(const CUtensorMap& map, const qb200::GemmArgs& args, int m_tiles
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  const bool pdl = use_pdl() && g_skip_pdl_once.exchange(0, std::memory_order_relaxed) == 0;
+  const bool pdl = !take_relayout(stream) && use_pdl();
   cfg.numAttrs = pdl ? 2 : 1;
   QB_CUDA(cudaLaunchKernelEx(&cfg, kfn, map, args));
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -695,23 +750,40 @@ int dispatch_split(int split, const CUtensorMap& map, const qb200::GemmArgs& arg
   return fail(QB200_EINVAL, "unsupported split %d for tok %d", split, TOK);
 }
 
+// Which ring configuration a launch gets (Variant<TOK, VAR> in w4a16_umma.cuh); measured, tools/tune.py.
+int pick_variant(int tok, int split, int ctas, int K) {
+  const int stages = ((K / 64 + split - 1) / split + 1) / 2;   // 128-k stages per CTA
+  if (tok <= 32) return stages <= 4 ? 1 : 0;
+  if (tok == 64) return ctas <= device_sm_count() ? 1 : 0;
+  return 0;
+}
+
 template <int TOK>
 int dispatch_variant(int split, const CUtensorMap& map, const qb200::GemmArgs& args, int m_tiles, cudaStream_t st) {
+  int var = pick_variant(TOK, split, (args.N / qb200::kChan) * m_tiles * split, args.K);
 #ifdef QB200_VARIANTS
-  if (g_variant.load(std::memory_order_relaxed) == 1) return dispatch_split<TOK, 1>(split, map, args, m_tiles, st);
+  const int forced = g_variant.load(std::memory_order_relaxed);   // -1 = planner's choice
+  if (forced >= 0) var = forced;
+  switch (var) {
+    case 2: return dispatch_split<TOK, 2>(split, map, args, m_tiles, st);
+    case 3: return dispatch_split<TOK, 3>(split, map, args, m_tiles, st);
+  }
 #endif
+  if (var == 1) return dispatch_split<TOK, 1>(split, map, args, m_tiles, st);
   return dispatch_split<TOK, 0>(split, map, args, m_tiles, st);
 }
 
 int check_device() {
-  static int ok = -1;
-  if (ok < 0) {
-    int dev = 0, major = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return fail(QB200_ECUDA, "no CUDA device");
+  static std::atomic<signed char> ok[kMaxDevices];   // 0 = unknown, 1 = sm_100, -1 = something else
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(QB200_ECUDA, "no CUDA device");
+  signed char v = (dev >= 0 && dev < kMaxDevices) ? ok[dev].load(std::memory_order_relaxed) : 0;
+  if (v == 0) {
     cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
-    ok = (major == 10) ? 1 : 0;
+    v = (major == 10) ? 1 : -1;
+    if (dev >= 0 && dev < kMaxDevices) ok[dev].store(v, std::memory_order_relaxed);
   }
-  if (!ok) return fail(QB200_ECUDA, "quick_b200 requires an sm_100a (B200) device; no fallback path exists");
+  if (v != 1) return fail(QB200_ECUDA, "quick_b200 requires an sm_100a (B200) device; no fallback path exists");
   return QB200_OK;
 }
 
@@ -729,7 +801,7 @@ void plan(int M, int K, int N, int split_hint, unsigned flags, int* tok_out, int
     *split_out = 1;
     return;
   }
-  const int tok = M <= 8 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 256 ? 128 : 256;
+  const int tok = M <= 16 ? 16 : M <= 64 ? 64 : M <= 256 ? 128 : 256;   // 32-token tiles never won a measurement
   const int tiles = (N / 128) * ((M + tok - 1) / tok);
   const int KB = K / 64;
   const int sms = device_sm_count();
@@ -737,10 +809,11 @@ void plan(int M, int K, int N, int split_hint, unsigned flags, int* tok_out, int
   int split = 1;
   if (tok <= 64) {
     // Co-resident tiles (two CTAs per SM): pick the split with the smallest modelled time
-    //   waves(tiles*split over 2*SMs slots) x (stages per CTA x ~600 cycles of MMA-issuer time + fixed cost),
-    // fixed = setup + epilogue (~2500 cycles) + ~600 per extra cluster rank for the split-K exchange.  Constants
+    //   waves(tiles*split over 2*SMs slots) x (stages per CTA x ~600 cycles per stage + fixed cost),
+    // fixed = setup + epilogue (~2500 cycles) + ~300 per extra cluster rank for the split-K exchange.  Constants
     // from the in-kernel traces (profiles/README.md); the model reproduces the measured optimum for N = 4096
-    // (split 4 ~ 8) and moves the wide projections of a 7B layer (qkv: 96 tiles, down: 86 stages) off split 1 / 4.
+    // (split 8 for 16-token tiles, 4 for 64) and for the wide / deep projections of a 7B layer (qkv, gate|up: 2;
+    // down: 8).
     const int slots = 2 * sms;
     long best = -1;
     for (int s = 1; s <= max_split; s *= 2) {
@@ -749,7 +822,7 @@ void plan(int M, int K, int N, int split_hint, unsigned flags, int* tok_out, int
       // a partly filled last wave costs less than a full one but more than its share: midpoint of both (x2)
       const long ctas = static_cast<long>(tiles) * s;
       const long waves2 = (ctas + slots - 1) / slots * slots + (ctas > slots ? ctas : slots);   // (ceil + continuous) * slots
-      const long cost = waves2 * (stages * 600L + 2500L + 600L * (s - 1));
+      const long cost = waves2 * (stages * 600L + 2500L + 300L * (s - 1));
       if (best < 0 || cost < best) { best = cost; split = s; }
     }
   } else {
@@ -776,7 +849,7 @@ extern "C" {
 const char* qb200_version(void) { return "quick_b200 0.1 (sm_100a tcgen05/TMEM/TMA W4A16)"; }
 const char* qb200_last_error(void) { return g_last_error.c_str(); }
 unsigned long long qb200_launch_count(void) { return g_launches.load(); }
-void qb200_debug_set_variant(int variant) { g_variant.store(variant); }
+void qb200_debug_set_variant(int variant) { g_variant.store(variant); }   // -1 = planner's choice
 void qb200_debug_set_trace(void* device_buffer) {
   g_trace = reinterpret_cast<long long*>(device_buffer);
   // the same buffer (host-mapped if it should survive a trap) receives the timed-out-wait report
@@ -808,7 +881,7 @@ int qb200_relayout_from_quick(const int32_t* qweight, const int32_t* qzeros, con
   relayout_sz_kernel<<<static_cast<unsigned>((nsz + 255) / 256), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const uint32_t*>(qzeros), reinterpret_cast<const __half*>(scales), sz, K / G, N);
   g_launches.fetch_add(2, std::memory_order_relaxed);
-  g_skip_pdl_once.store(1, std::memory_order_relaxed);   // wq/sz are being written: the next GEMM launches fully serialised
+  note_relayout(as_stream(stream));   // wq/sz are being written: the next GEMM on this stream launches fully serialised
   QB_CUDA(cudaGetLastError());
   return QB200_OK;
 }
@@ -855,7 +928,7 @@ int qb200_relayout_from_awq_gemm(const int32_t* gemm_qweight, const int32_t* gem
   gemm_to_b200_sz_kernel<<<static_cast<unsigned>((nsz + 255) / 256), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const uint32_t*>(gemm_qzeros), reinterpret_cast<const __half*>(gemm_scales), sz, K / G, N);
   g_launches.fetch_add(2, std::memory_order_relaxed);
-  g_skip_pdl_once.store(1, std::memory_order_relaxed);   // wq/sz are being written: the next GEMM launches fully serialised
+  note_relayout(as_stream(stream));   // wq/sz are being written: the next GEMM on this stream launches fully serialised
   QB_CUDA(cudaGetLastError());
   return QB200_OK;
 }
@@ -1025,7 +1098,12 @@ int qb200_peer_barrier(unsigned* epoch_counter, unsigned* const* flag_arrays, in
     if (flag_arrays[p] == nullptr) return fail(QB200_EINVAL, "peer_barrier: null flag array %d", p);
     f.p[p] = flag_arrays[p];
   }
-  peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(epoch_counter, f, rank, n_peers);
+  static const unsigned long long timeout_ns = [] {
+    const char* e = getenv("QB200_PEER_TIMEOUT_S");
+    const double sec = e ? atof(e) : 120.0;
+    return sec <= 0 ? 0ull : static_cast<unsigned long long>(sec * 1e9);
+  }();
+  peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(epoch_counter, f, rank, n_peers, timeout_ns);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   QB_CUDA(cudaGetLastError());
   return QB200_OK;
@@ -1075,15 +1153,12 @@ int qb200_attn_decode(const void* qkv, const void* cos_table, const void* sin_ta
       {attn_decode_kernel<64, 1>, attn_decode_kernel<64, 2>, attn_decode_kernel<64, 4>, attn_decode_kernel<64, 8>},
       {attn_decode_kernel<128, 1>, attn_decode_kernel<128, 2>, attn_decode_kernel<128, 4>, attn_decode_kernel<128, 8>},
       {attn_decode_kernel<256, 1>, attn_decode_kernel<256, 2>, attn_decode_kernel<256, 4>, attn_decode_kernel<256, 8>}};
-  static bool attr_set[12] = {};
+  static PerDeviceOnce attr_once[12];
   const int grp = nh / nkv;
   const int hi = hd == 64 ? 0 : hd == 128 ? 1 : 2, gi = grp == 1 ? 0 : grp == 2 ? 1 : grp == 4 ? 2 : 3;
   const AttnFn kfn = table[hi][gi];
   const int ki = hi * 4 + gi;
-  if (!attr_set[ki]) {
-    QB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set[ki] = true;
-  }
+  QB_CUDA(attr_once[ki].ensure([&] { return cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(nkv, B);
   cfg.blockDim = dim3(kAttnThreads);

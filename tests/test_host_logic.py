@@ -106,7 +106,8 @@ def test_gemm_plan_fills_the_machine(built):
         assert tok in (16, 32, 64, 128, 256) and split in (1, 2, 4, 8) and ctas >= 32
         assert ctas == (4096 // 128) * -(-M // tok) * split
         if M <= 512:
-            assert 100 <= ctas <= 148 + 148 // 4, "one ordered GEMM should fill the 148 SMs"
+            # one ordered GEMM fills the 148 SMs; small tiles are sized for two co-resident CTAs per SM
+            assert 100 <= ctas <= (2 * 148 if tok <= 64 else 148 + 148 // 4)
         # independent launches overlap each other: never split K, largest token tile
         itok, isplit, ictas = ops.plan(M, 4096, 4096, 128, independent=True)
         assert isplit == 1 and itok >= min(M, 256) and ictas == (4096 // 128) * -(-M // itok)

@@ -12,7 +12,7 @@ import torch
 from oracle import quick_oracle as qo
 from quick_b200 import _lib, ops
 
-variants = [int(v) for v in os.environ.get("VARS", "0").split(",")]
+variants = [int(v) for v in os.environ.get("VARS", "-1").split(",")]
 lib = _lib.load()
 cases = {}
 

@@ -18,6 +18,7 @@ x = torch.randn(M, K, device=dev).half()
 from quick_b200 import _lib
 rep = torch.zeros(4096, dtype=torch.int64).pin_memory()
 _lib.load().qb200_debug_set_trace(rep.data_ptr())
+_lib.load().qb200_debug_set_variant(int(os.environ.get('VAR', '-1')))
 
 def print_report():
     r = rep.tolist()

@@ -8,7 +8,7 @@ tok, split, M, K, N = map(int, sys.argv[1:6]); G = 128
 INDEP = os.environ.get("INDEP", "0") == "1"
 dev = "cuda"; NL = 12
 lib = _lib.load()
-lib.qb200_debug_set_variant(int(os.environ.get("VAR", "0")))
+lib.qb200_debug_set_variant(int(os.environ.get("VAR", "-1")))
 sets = [(torch.randint(-2**31, 2**31 - 1, (K * N // 8,), device=dev, dtype=torch.int32),
          torch.full((K // G * N,), 0x64082000, device=dev, dtype=torch.int32)) for _ in range(NL)]
 x = torch.randn(M, K, device=dev).half()
