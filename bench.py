@@ -34,8 +34,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# keep stdout to the one JSON line: NCCL prints its version banner to stdout at NCCL_DEBUG >= VERSION
-os.environ["NCCL_DEBUG"] = os.environ.get("QB200_NCCL_DEBUG", "NONE")
+# NCCL_DEBUG is left as the caller set it (the driver reads the communicator's rank count from it); the JSON line is
+# the LAST line this script prints on stdout.
 
 import torch
 
@@ -46,6 +46,11 @@ NSETS = 40
 METRIC = "W4A16 GEMM TOPS vs M (K=N=4096 g128)"
 WORKLOAD = ("single-GEMM sweep M in {1,8,16,64,128,256,512} K=N=4096 g=128, 40 rotating weight sets "
             "(360 MB > L2: cold weights), 280 GEMMs per step")
+
+
+# identical in both arms (the driver compares the dicts)
+CONFIG = {"workload": WORKLOAD, "K": K, "N": N, "G": G, "M_sweep": MS, "weight_sets": NSETS,
+          "l2_policy": "inputs larger than L2 (360 MB of packed weights rotate through 40 sets: every GEMM streams its weights from HBM)"}
 
 
 def flops(M):
@@ -64,6 +69,26 @@ def peaks():
         return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
                 "source": "MEASURED_PEAKS.json"}
     return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def ncu_traffic(M):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the GEMM at this M from the committed ncu summary."""
+    for name in ("r2_ncu_full.json", "r1c_ncu_full.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(p):
+            continue
+        try:
+            d = json.load(open(p))
+            for key, recs in d.items():
+                if key.replace("indep", "").find(f"M{M}.") >= 0 and "indep" not in key and recs:
+                    r = recs[0]
+                    rd = float(str(r.get("dram__bytes_read.sum", "0")).split()[0]); u = str(r.get("dram__bytes_read.sum", "")).split()[-1]
+                    wr = float(str(r.get("dram__bytes_write.sum", "0")).split()[0]); uw = str(r.get("dram__bytes_write.sum", "")).split()[-1]
+                    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                    return int(rd * scale.get(u, 1) + wr * scale.get(uw, 1)), f"profiles/{name} ({key}: ncu --set full, per launch; not measured in this run)"
+        except Exception:
+            continue
+    return None, "no ncu summary for this M under profiles/"
 
 
 class ClockSampler:
@@ -116,13 +141,15 @@ def rand_b200_weights(seed, dev):
 
 
 def rand_quick_weights(seed, dev):
-    """Random QUICK-layout tensors (what the reference kernel consumes): pack random q/z/s on the GPU."""
-    from quick_b200 import ops
+    """Random QUICK-layout tensors (what the reference kernel consumes) with plain torch ops — no library of this repo
+    is involved, so the reference arm's process never loads libquick_b200.so.  Any nibble pattern is a valid qweight;
+    zeros and scales carry the duplication the format requires (reference quick.py:129-130,141-150)."""
     g = torch.Generator(device=dev); g.manual_seed(seed)
-    q = torch.randint(0, 16, (K, N), device=dev, generator=g, dtype=torch.int32)
-    z = torch.randint(0, 16, (K // G, N), device=dev, generator=g, dtype=torch.int32)
+    qweight = torch.randint(-2 ** 31, 2 ** 31 - 1, (K // 4, N // 2), device=dev, dtype=torch.int32, generator=g)
+    z4 = torch.randint(0, 2 ** 16, (K // G, N // 4), device=dev, dtype=torch.int32, generator=g)
+    qzeros = z4 | (z4 << 16)
     s = (torch.rand(K // G, N, device=dev, generator=g) * 0.01 + 0.002).half()
-    return ops.pack_quick(q, z, s, G)
+    return qweight, qzeros, s.repeat_interleave(2, dim=1).contiguous()
 
 
 def dist_setup(n_gpus):
@@ -175,32 +202,175 @@ def cpu_baseline(sample_sets=1):
             "seconds": dt}
 
 
-def model_tokens(world, rank):
-    """Second half of BASELINE.json's metric: Llama-2-7B AWQ w4 g128 tokens/s (random-init weights of that
-    architecture, prefill = decode = 128, the reference's examples/benchmark.py methodology) through the minimal
-    runner; with N > 1 ranks every linear is column-parallel with one NCCL all-gather (tensor parallel).
-    Reported beside the GEMM sweep, never mixed into `value`; failures are reported, not raised."""
-    try:
-        import copy
-        from quick_b200.awq.models.llama_like import PRESETS, LlamaLikeQuickModel, benchmark_generation
-        cfg = copy.deepcopy(PRESETS["llama-2-7b"])
-        cfg.max_seq_len = 256
-        for n_out in (cfg.hidden_size, 3 * cfg.hidden_size, 2 * cfg.intermediate_size):
-            if n_out % (128 * world) != 0:
-                return {"unsupported": f"N={n_out} does not split into {world} column shards of 128-channel tiles"}
+def model_tokens(world, rank, full=True):
+    """Second half of BASELINE.json's metric (configs 3-5): tokens/s of random-init models of the Llama-2-7B, Mistral-7B
+    and Llama-2-70B architectures (AWQ w4 g128, prefill = decode = 128, the reference's examples/benchmark.py
+    methodology: batch / median decode step, ctx*batch / prefill time) through the fused runner.  With N > 1 ranks the
+    runner is tensor-parallel (column-parallel linears, gathered over NVLink peer memory).  Reported beside the GEMM
+    sweep, never mixed into `value`; a failing leg is reported, not raised."""
+    import copy
+    import gc
+    from quick_b200.awq.models.llama_like import PRESETS, LlamaLikeQuickModel, benchmark_generation
+    plan = [("llama-2-7b", (1, 8, 32, 64)), ("mistral-7b", (1, 8, 32, 64)), ("llama-2-70b", (1, 8))] if world == 1 else \
+           [("llama-2-7b", (1, 64)), ("llama-2-70b", (1, 8))]
+    if not full:
+        plan = plan[:1]
+    out = []
+    for name, batches in plan:
+        leg = {"model": f"{name} shapes, random-init, w4 g128", "prefill": 128, "decode": 128, "tensor_parallel": world,
+               "cuda_graph_decode": True, "rows": []}
+        try:
+            cfg = copy.deepcopy(PRESETS[name])
+            cfg.max_seq_len = 256
+            for bs in batches:
+                torch.manual_seed(1234)
+                m = LlamaLikeQuickModel(cfg, bs)
+                m.release_quick_buffers(drop=True)       # one copy of every weight on the device (B200 layout)
+                r = benchmark_generation(m, 128, 128)
+                leg["rows"].append({"batch": bs, "decode_tokens_per_s": round(r["decode_tokens_per_s"], 1),
+                                    "prefill_tokens_per_s": round(r["prefill_tokens_per_s"], 1),
+                                    "decode_ms_per_step": round(r["decode_ms_per_step"], 3),
+                                    "decode_hbm_frac": round(m.weight_bytes() / (r["decode_ms_per_step"] * 1e-3) / (peaks()["hbm_gbs"] * 1e9), 4)})
+                del m
+                gc.collect(); torch.cuda.empty_cache()
+        except Exception as e:  # the GEMM sweep is the contract; a model leg must never take the JSON line down
+            leg["error"] = f"{type(e).__name__}: {e}"[:300]
+            gc.collect(); torch.cuda.empty_cache()
+        out.append(leg)
+    return out
+
+
+def plugin_sweep(dev, rank, args):
+    """The M sweep through the two reference-facing entry points, eager and stream-ordered exactly like the reference
+    arm's calls: `quick_kernels.gemm_forward_cuda_quick(x, qweight, scales, qzeros, split_k)` (the drop-in pybind symbol,
+    QUICK-layout tensors; the B200 copy is cached per weight storage) and `WQLinear_QUICK.forward`."""
+    import quick_kernels
+    from quick_b200.awq.modules.linear.quick import WQLinear_QUICK
+    nsets = NSETS
+    packed = [rand_quick_weights(7000 + 100 * rank + i, dev) for i in range(nsets)]
+    mods = []
+    for qw, qz, sc in packed:
+        m = WQLinear_QUICK(4, G, K, N, False, dev)
+        m.qweight, m.qzeros, m.scales = qw, qz, sc
+        mods.append(m)
+    xs = {M: torch.randn(M, K, device=dev).half() for M in MS}
+    out = {}
+    for label, call in (("gemm_forward_cuda_quick", lambda M, i: quick_kernels.gemm_forward_cuda_quick(xs[M], packed[i][0], packed[i][2], packed[i][1], 8)),
+                        ("WQLinear_QUICK.forward", lambda M, i: mods[i](xs[M]))):
+        for M in MS:
+            for i in range(nsets):
+                call(M, i)                       # warm-up: builds / caches the B200 copies
+        torch.cuda.synchronize()
+        steps = max(3, args.steps // 2)
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(MS) + 1)] for _ in range(steps)]
+        for k in range(steps):
+            for j, M in enumerate(MS):
+                evs[k][j].record()
+                for i in range(nsets):
+                    call(M, i)
+            evs[k][len(MS)].record()
+        torch.cuda.synchronize()
+        ms = sum(evs[k][0].elapsed_time(evs[k][-1]) for k in range(steps)) / steps
         rows = []
-        for bs in (1, 64):
-            torch.manual_seed(1234)
-            m = LlamaLikeQuickModel(cfg, bs)
-            r = benchmark_generation(m, 128, 128)
-            rows.append({"batch": bs, "decode_tokens_per_s": round(r["decode_tokens_per_s"], 1),
-                         "prefill_tokens_per_s": round(r["prefill_tokens_per_s"], 1), "decode_ms_per_step": round(r["decode_ms_per_step"], 3)})
-            del m
-            torch.cuda.empty_cache()
-        return {"model": "llama-2-7b shapes, random-init, w4 g128", "prefill": 128, "decode": 128, "tensor_parallel": world,
-                "cuda_graph_decode": True, "rows": rows}
-    except Exception as e:  # the GEMM sweep is the contract; the model leg must never take the JSON line down
-        return {"error": f"{type(e).__name__}: {e}"[:300]}
+        for j, M in enumerate(MS):
+            us = sum(evs[k][j].elapsed_time(evs[k][j + 1]) for k in range(steps)) / steps / nsets * 1e3
+            rows.append({"M": M, "us": round(us, 3), "TOPS": round(flops(M) / us / 1e6, 2)})
+        out[label] = {"value": round(sum(flops(M) for M in MS) * nsets / (ms * 1e-3) / 1e12, 3), "unit": "TOPS", "ms_per_step": round(ms, 4),
+                      "sweep": rows, "launch": "eager, one call per GEMM on the current stream (host launch cost included)"}
+    # the reference arm's end-to-end protocol, call for call: x.cuda() -> linear -> .cpu(), one GEMM at a time, no overlap
+    hx = {M: torch.randn(M, K).half().pin_memory() for M in MS}
+    nh = 16
+
+    def e2e_sync_step():
+        for M in MS:
+            for i in range(nh):
+                y = mods[i](hx[M].cuda(non_blocking=True)).cpu()
+        return y
+
+    e2e_sync_step(); torch.cuda.synchronize()
+    reps = max(2, args.steps // 4)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        e2e_sync_step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out["e2e_sync"] = {"value": round(sum(flops(M) for M in MS) * nh * reps / dt / 1e12, 3), "unit": "TOPS",
+                       "protocol": "per GEMM: pinned x.cuda() -> WQLinear_QUICK.forward -> .cpu() (synchronous, the reference arm's e2e protocol "
+                                   "call for call; the headline `e2e` overlaps 16 streams through the C-ABI host-buffer call)"}
+    del mods, packed
+    torch.cuda.empty_cache()
+    return out
+
+
+def tp_block(world, rank, dev, args):
+    """N > 1: the north_star's multi-GPU split — ONE column-parallel linear (K = 4096 -> N = 4096 x world, every rank
+    owns 4096 output columns) whose (M, N/R) slabs are gathered on every rank: the GEMM epilogue stores its slab into
+    all ranks' full-width buffers over NVLink (NVSwitch multicast when available) and the ranks meet on device-side
+    flags — no NCCL call on the data path.  Checked bit-for-bit against kernel + NCCL all_gather_into_tensor, then
+    timed per M (CUDA-graph replay, max over ranks) next to that NCCL baseline."""
+    import torch.distributed as dist
+    from quick_b200 import ops
+    from quick_b200.parallel import PeerGatherWorkspace
+    n_tot = N * world
+    res = {"linear": f"K={K} -> N={n_tot} column-parallel over {world} ranks, gathered output (M, {n_tot}) on every rank"}
+    try:
+        sets = [rand_b200_weights(9000 + 1000 * rank + i, dev) for i in range(NSETS)]
+        ws = [PeerGatherWorkspace(max(MS), n_tot), PeerGatherWorkspace(max(MS), n_tot)]   # alternate: consecutive uses of one
+        res["multicast"] = ws[0].multicast_ptr is not None                                # workspace are separated by the other's meeting
+        ok = True
+        for M in (1, 64, 300):
+            x = torch.randn(M, K, device=dev, generator=torch.Generator(device=dev).manual_seed(M)).half()
+            dist.broadcast(x, 0)
+            fused = ws[0].gemm(x, sets[0][0], sets[0][1], N, G).clone()
+            local = ops.gemm(x, sets[0][0], sets[0][1], N, G)
+            gathered = torch.empty((world * M, N), dtype=torch.float16, device=dev)
+            dist.all_gather_into_tensor(gathered, local.contiguous())
+            want = gathered.view(world, M, N).permute(1, 0, 2).reshape(M, n_tot)
+            ok = ok and bool(torch.equal(fused, want))
+            ws[1].gemm(x, sets[0][0], sets[0][1], N, G)          # keeps the alternation invariant
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        res["parity_fused_vs_nccl_bit_identical"] = bool(flag.item())
+        xs = {M: torch.randn(M, K, device=dev).half() for M in MS}
+        rows = []
+        for M in MS:
+            def fused_group():
+                for i in range(NSETS):
+                    ws[i & 1].gemm(xs[M], sets[i][0], sets[i][1], N, G)
+            gath = torch.empty((world * M, N), dtype=torch.float16, device=dev)
+
+            def nccl_group():
+                for i in range(NSETS):
+                    dist.all_gather_into_tensor(gath, ops.gemm(xs[M], sets[i][0], sets[i][1], N, G))
+            row = {"M": M}
+            for label, fn in (("fused", fused_group), ("nccl", nccl_group)):
+                try:
+                    fn(); torch.cuda.synchronize()
+                    side = torch.cuda.Stream(); g = torch.cuda.CUDAGraph()
+                    with torch.cuda.stream(side):
+                        with torch.cuda.graph(g, stream=side):
+                            fn()
+                    g.replay(); barrier(world)
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    reps = 5
+                    a.record()
+                    for _ in range(reps):
+                        g.replay()
+                    b.record(); torch.cuda.synchronize()
+                    us = max_over_ranks(a.elapsed_time(b) / reps / NSETS * 1e3, world)
+                    row[f"{label}_us"] = round(us, 3)
+                    row[f"{label}_TOPS"] = round(2.0 * M * K * n_tot / us / 1e6, 2)
+                    del g
+                except Exception as e:
+                    row[f"{label}_error"] = f"{type(e).__name__}: {e}"[:160]
+            # NVLink roofline of the gather: every rank receives (R-1)/R of the output at the measured peer-copy rate
+            link_us = 2.0 * M * n_tot * (world - 1) / world / 770e9 * 1e6
+            row["nvlink_us_at_770GBs"] = round(link_us, 3)
+            rows.append(row)
+        res["sweep"] = rows
+    except Exception as e:
+        res["error"] = f"{type(e).__name__}: {e}"[:300]
+    return res
 
 
 def run_mine(args):
@@ -303,10 +473,11 @@ def run_mine(args):
         roof = {"bound": "tensor", "achieved": dom["TOPS"], "peak": pk["tf_sustained"], "unit": "TFLOP/s"}
     else:
         roof = {"bound": "hbm", "achieved": dom["GBs"], "peak": pk["hbm_gbs"], "unit": "GB/s"}
-    # DRAM bytes per launch of the same kernel from `ncu --set full` (profiles/r1b_ncu_full.json): no re-reads
-    ncu_traffic = {1: 8948480, 256: 11040512, 512: 13138432}
-    roof.update({"frac": round(roof["achieved"] / roof["peak"], 4), "traffic": ncu_traffic.get(dom["M"]), "kernel": "w4a16_umma_kernel",
-                 "algorithmic_bytes": int(alg_bytes(dom["M"])),
+    # DRAM bytes per launch of the dominant kernel: not observable from inside the run — taken from the committed
+    # `ncu --set full` summary of this same command (profiles/r2_ncu_full.json, per launch) and labelled as such
+    traffic, traffic_src = ncu_traffic(dom["M"])
+    roof.update({"frac": round(roof["achieved"] / roof["peak"], 4), "traffic": traffic, "traffic_source": traffic_src,
+                 "kernel": "w4a16_umma_kernel", "algorithmic_bytes": int(alg_bytes(dom["M"])),
                  "at_M": dom["M"], "share_of_step": round(dom["us"] / sum(r["us"] for r in sweep), 3),
                  "peak_source": pk["source"] + (" (sustained bf16 cuBLAS)" if roof["bound"] == "tensor" else " (copy)")})
     m1 = sweep[0]
@@ -350,19 +521,28 @@ def run_mine(args):
         for h in handles:
             h.close()
 
-    model = model_tokens(world, rank) if args.model else None
+    # ---- the same sweep through the reference-facing plugin surface, eager (no graph), timed as called ----
+    plugin = None
+    if args.plugin:
+        plugin = plugin_sweep(dev, rank, args)
+    tp = tp_block(world, rank, dev, args) if (world > 1 and args.tp) else None
+    model = model_tokens(world, rank, full=args.full_models) if args.model else None
     cpu = cpu_baseline() if (rank == 0 and world == 1 and args.cpu_baseline) else None
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 3), "unit": "TOPS", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "K": K, "N": N, "G": G, "M_sweep": MS, "weight_sets": NSETS,
-                           "l2_policy": "inputs larger than L2 (360 MB of packed weights rotate)",
-                           "launch": "CUDA-graph replay of the 40 GEMMs per M; events between the M groups; headline = ordered "
-                                     "launches (each GEMM waits for its predecessor before loading activations)",
-                           "parallelism": f"{world} x independent column shards of 4096 outputs (no collective)"},
+                "config": dict(CONFIG),
+                "how": {"launch": "CUDA-graph replay of the 40 GEMMs per M through quick_b200.ops.gemm (C-ABI qb200_gemm_w4a16_ex); events "
+                                  "between the M groups; headline = ordered launches (each GEMM waits for its predecessor before "
+                                  "loading activations).  The reference arm is eager pybind calls: its kernel launches on the legacy "
+                                  "stream and cannot be captured; it is GPU-bound (ncu: 16 + 7 us of kernels per M = 1 call), see "
+                                  "`plugin` for this repo's eager numbers through the same pybind symbol",
+                        "parallelism": f"{world} x independent column shards of 4096 outputs (no collective in `value`; the "
+                                       "column-parallel linear WITH its all-gather is the `tp` block)"},
                 "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof, "roofline_m1": roof_m1,
-                "sweep": sweep, "independent": independent, "llama2_7b_tokens_per_s": model, "cpu_baseline": cpu}
+                "sweep": sweep, "independent": independent, "plugin": plugin, "tp": tp, "model_tokens_per_s": model,
+                "llama2_7b_tokens_per_s": (model[0] if model else None), "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
@@ -378,7 +558,7 @@ def run_reference(args):
     cpu = cpu_baseline()
     base = {"metric": METRIC, "unit": "TOPS", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOAD, "K": K, "N": N, "G": G, "M_sweep": MS, "weight_sets": NSETS}}
+            "config": dict(CONFIG)}
     if ref is None:
         # no reference binary: the oracle port on the host cores stands in (bounded sample)
         base.update({"value": round(cpu["value"], 4), "ms_per_step": round(cpu["seconds"] * 1e3 * NSETS, 2), "cpu_baseline": cpu,
@@ -448,7 +628,10 @@ def main():
     ap.add_argument("--impl", default="quick_b200", choices=["quick_b200", "reference"])
     ap.add_argument("--no-e2e", dest="e2e", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
-    ap.add_argument("--no-model", dest="model", action="store_false", help="skip the Llama-2-7B tokens/s leg")
+    ap.add_argument("--no-model", dest="model", action="store_false", help="skip the tokens/s legs")
+    ap.add_argument("--quick-models", dest="full_models", action="store_false", help="tokens/s of Llama-2-7B only (default: 7B, Mistral-7B, 70B)")
+    ap.add_argument("--no-plugin", dest="plugin", action="store_false", help="skip the eager sweep through the pybind symbol / WQLinear_QUICK")
+    ap.add_argument("--no-tp", dest="tp", action="store_false", help="N > 1: skip the column-parallel linear + all-gather block")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

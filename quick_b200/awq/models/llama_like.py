@@ -413,6 +413,16 @@ class LlamaLikeQuickModel(nn.Module):
         if B != self.batch:
             raise ValueError(f"batch {B} != the KV-cache batch {self.batch} this model was built with (batch_size=…)")
         start = self.start_pos if (T == 1 and use_cache) else 0
+        if T == 1 and start + 1 > self.cfg.max_seq_len:
+            # the reference's policy when decoding runs past the cache (fused_utils.py:26-28, cache.py:37-50): roll the
+            # oldest min(100, cache length) positions out, zero the freed tail, continue at the reduced position
+            n = min(100, self.cfg.max_seq_len)
+            for blk in self.blocks:
+                for c in (blk.cache_k, blk.cache_v):
+                    if n < self.cfg.max_seq_len:
+                        c.copy_(torch.roll(c, shifts=-n, dims=2))
+                    c[:, :, -n:].zero_()
+            start -= n
         if start + T > self.cfg.max_seq_len:
             raise ValueError(f"position {start} + {T} tokens exceed the cache length {self.cfg.max_seq_len} (max_new_tokens=…)")
         if T == 1:
@@ -421,6 +431,16 @@ class LlamaLikeQuickModel(nn.Module):
             logits = self(ids, torch.arange(start, start + T, device=dev), all_logits=True)
         self.start_pos = start + T
         return CausalLMOutputWithPast(logits=logits)
+
+    def release_quick_buffers(self, drop=False):
+        """Inference-only: every decoder linear keeps its B200-layout copy on the GPU and moves the QUICK-layout
+        checkpoint tensors to host memory (WQLinear_QUICK.release_quick_buffers; drop=True discards them:
+        random-init benchmark models) — the device then holds each weight once instead of twice.  Not for runs that
+        route through the reference kernel (ref_mod)."""
+        for blk in self.blocks:
+            for m in (blk.qkv_proj, blk.o_proj, blk.gate_up_proj, blk.down_proj):
+                m.release_quick_buffers(drop=drop)
+        return self
 
     def weight_bytes(self):
         n = 0
@@ -517,6 +537,8 @@ def fuse_hf_model(model, batch_size: int = 1, max_seq_len: Optional[int] = None)
                 delattr(mod, n)          # the fused copies replace them: free the memory layer by layer
     runner = LlamaLikeQuickModel(cfg, batch_size, dev, parts={"embed": model.model.embed_tokens, "blocks": blocks,
                                                               "norm": model.model.norm.weight, "lm_head": model.lm_head})
+    if dev.type == "cuda" and _os.environ.get("QB200_KEEP_QUICK_BUFFERS", "0") != "1":
+        runner.release_quick_buffers()      # the device holds every weight once (B200 layout); checkpoint tensors go to the host
     model.model = runner
     model.qb200_fused = True
 

@@ -20,24 +20,6 @@ from quick_kernels import gemm_forward_cuda_quick  # noqa: F401  (re-exported, s
 from ....layout import pack_quick
 
 
-def make_divisible(c, divisor):
-    return (c + divisor - 1) // divisor
-
-
-def calculate_zeros_width(in_features, group_size=128, pack_num=8):
-    if group_size >= 128:
-        size_multiplier = 1
-    elif group_size == 64:
-        size_multiplier = 2
-    elif group_size == 32:
-        size_multiplier = 4
-    else:
-        raise NotImplementedError
-    base_width = make_divisible(in_features // group_size, pack_num)
-    base_width = make_divisible(base_width, size_multiplier) * size_multiplier
-    return base_width
-
-
 class WQLinear_QUICK(nn.Module):
     def __init__(self, w_bit, group_size, in_features, out_features, bias, dev, k_split_1=2, k_split_2=8):
         super().__init__()
@@ -60,7 +42,9 @@ class WQLinear_QUICK(nn.Module):
         else:
             self.bias = None
         self._b200 = None       # (wq, sz) in the B200 layout — derived, never saved
-        self._b200_key = None
+        self._b200_src = None   # the packed tensors it was derived from (strong references: their storage cannot be
+                                # freed and re-used at the same address while the copy is cached) and their versions
+        self._b200_frozen = False
 
     @classmethod
     def from_linear(cls, linear, w_bit, group_size, init_only=False, scales=None, zeros=None, k_split_1=2, k_split_2=8):
@@ -107,11 +91,48 @@ class WQLinear_QUICK(nn.Module):
         return m
 
     def _prepacked(self):
-        key = tuple((t.data_ptr(), 0 if t.is_inference() else t._version) for t in (self.qweight, self.qzeros, self.scales))
-        if self._b200 is None or self._b200_key != key:
+        """(wq, sz): the B200-layout copy the kernel streams, rebuilt when a packed buffer is replaced or modified
+        in place (ordinary tensors: version counter; inference tensors have none and count as immutable)."""
+        if self._b200_frozen:
+            return self._b200
+        src = (self.qweight, self.qzeros, self.scales)
+        ver = tuple(0 if t.is_inference() else t._version for t in src)
+        cur = self._b200_src
+        if self._b200 is None or cur is None or any(a is not b for a, b in zip(cur[0], src)) or cur[1] != ver:
             wq, sz = quick_kernels.prepack_quick(self.qweight, self.scales, self.qzeros, self.in_features)
-            self._b200, self._b200_key = (wq, sz), key
+            self._b200, self._b200_src = (wq, sz), (src, ver)
         return self._b200
+
+    def release_quick_buffers(self, drop=False):
+        """Inference-only deployments: keep the B200 copy on the GPU and move the QUICK-layout buffers (qweight /
+        qzeros / scales — the checkpoint format, no longer read by the kernel) to host memory, halving the weight
+        footprint on the device.  ``state_dict`` / ``save_quantized`` keep working from the host copies;
+        ``restore_quick_buffers`` (or loading a state dict) brings them back.  drop=True discards them instead
+        (throw-away random-init benchmark models: nothing to save)."""
+        if not self.qweight.is_cuda:
+            return self
+        self._prepacked()
+        self._b200_device = self.qweight.device
+        for name in ("qweight", "qzeros", "scales"):
+            t = getattr(self, name)
+            setattr(self, name, torch.empty((0,) * t.dim(), dtype=t.dtype) if drop else t.to("cpu"))
+        self._b200_src = None
+        self._b200_frozen = True
+        return self
+
+    def restore_quick_buffers(self):
+        if self._b200_frozen:
+            dev = self._b200_device
+            for name in ("qweight", "qzeros", "scales"):
+                setattr(self, name, getattr(self, name).to(dev))
+            self._b200_frozen = False
+        return self
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        if self._b200_frozen:           # new packed tensors arrived: the frozen copy is stale
+            self.restore_quick_buffers()
+        self._b200 = self._b200_src = None
 
     @torch.no_grad()
     def forward(self, x, residual=None):

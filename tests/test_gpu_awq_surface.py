@@ -141,3 +141,80 @@ def test_quantize_save_load_forward_generate(tmp_path, built):
     from_gemm = AutoAWQForCausalLM.from_quantized(gdir, fuse_layers=False)
     sd2 = from_gemm.model.state_dict()
     assert all(torch.equal(sd0[k], sd2[k]) for k in sd0)
+
+
+def _save_tokenizer(path, vocab_size=512):
+    """A local word-level tokenizer (no hub access): what AutoTokenizer.from_pretrained(model_path) finds."""
+    from tokenizers import Tokenizer, models, pre_tokenizers
+    from transformers import PreTrainedTokenizerFast
+    tok = Tokenizer(models.WordLevel({f"t{i}": i for i in range(vocab_size)}, unk_token="t0"))
+    tok.pre_tokenizer = pre_tokenizers.Whitespace()
+    PreTrainedTokenizerFast(tokenizer_object=tok, unk_token="t0", pad_token="t1").save_pretrained(path)
+
+
+def test_reference_benchmark_flow_through_the_quick_namespace(tmp_path, built):
+    """The reference's own benchmark (examples/benchmark.py) against a random-init AWQ-QUICK checkpoint, through the
+    reference's import path.  When the reference tree is present the UNMODIFIED script is executed (runpy, its own
+    argument parser); on the GPU box, where /root/reference does not exist, the same call sequence is replayed line by
+    line (benchmark.py:38-67 generate_torch, :91-150 run_round): `from quick.awq import AutoAWQForCausalLM`,
+    `from_quantized(model_path, quant_file, max_new_tokens=…, batch_size=…, safetensors=…)`, `warmup(model)`,
+    `model(inputs, use_cache=True)` with the cache position carried by the model, `out[0][:, -1].max(1)[1]`,
+    `model.quant_config.version`."""
+    import runpy
+    import sys
+
+    import numpy as np
+    from quick.awq import AutoAWQForCausalLM                      # the reference's import lines (benchmark.py:6-7)
+    from quick.awq.models.base import BaseAWQForCausalLM
+    from transformers import AutoTokenizer
+
+    fp_path = _tiny_hf(tmp_path)
+    model = AutoAWQForCausalLM.from_pretrained(fp_path, device_map="cuda")
+    calib = torch.randint(0, 512, (4, 32), generator=torch.Generator().manual_seed(1))
+    model.quantize(None, quant_config={"zero_point": True, "q_group_size": 128, "w_bit": 4, "version": "QUICK"}, calib_data=calib)
+    quant_path = str(tmp_path / "quick")
+    model.save_quantized(quant_path)
+    _save_tokenizer(quant_path)
+    del model
+
+    ref_script = "/root/reference/examples/benchmark.py"
+    if os.path.exists(ref_script):
+        argv = sys.argv
+        sys.argv = [ref_script, "--model_path", quant_path, "--batch_size", "2"]
+        try:
+            runpy.run_path(ref_script, run_name="__main__")       # rounds beyond the cache length end the script's loop
+        except (ValueError, RuntimeError) as e:                   # (the reference sweeps contexts up to 4096)
+            assert "exceed" in str(e) or "position" in str(e), e
+        finally:
+            sys.argv = argv
+
+    tokenizer = AutoTokenizer.from_pretrained(quant_path, trust_remote_code=True)
+    batch_size, context, n_generate = 2, 16, 32      # cache = max_new_tokens = 32: decoding runs past it and rolls, like the reference
+    input_ids = torch.randint(0, tokenizer.vocab_size, (batch_size, context)).cuda()
+    model = AutoAWQForCausalLM.from_quantized(quant_path, "", max_new_tokens=n_generate, batch_size=batch_size, safetensors=True)
+    assert isinstance(model, BaseAWQForCausalLM)
+    warm_up = torch.randn((512, 512)).to(next(model.parameters()).device)       # warmup(model), benchmark.py:34-36
+    torch.mm(warm_up, warm_up)
+    context_time, generate_time = 0, []
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tokens = []
+    with torch.inference_mode():
+        for i in range(n_generate):
+            start.record()
+            inputs = torch.as_tensor(input_ids if i == 0 else token, device=next(model.parameters()).device)
+            out = model(inputs, use_cache=True)
+            end.record()
+            torch.cuda.synchronize()
+            token = out[0][:, -1].max(1)[1].unsqueeze(1)
+            tokens.append(token)
+            if i == 0:
+                context_time += start.elapsed_time(end) * 1e-3
+            else:
+                generate_time.append(start.elapsed_time(end) * 1e-3)
+    prefill_tps = input_ids.shape[1] / context_time * batch_size
+    decode_tps = 1 / np.median(generate_time) * batch_size
+    assert prefill_tps > 0 and decode_tps > 0 and model.quant_config.version == "QUICK"
+    assert model.model.model.cfg.max_seq_len == 32 and model.model.model.start_pos <= 32     # the cache rolled (fused_utils.py:26-28)
+    # the stateful loop produced a real greedy continuation: same tokens as generate() from the same prompt
+    gen = model.generate(input_ids, max_new_tokens=8)
+    assert torch.equal(gen[:, context:context + 8], torch.cat(tokens[:8], dim=1))

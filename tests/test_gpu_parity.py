@@ -113,6 +113,15 @@ CASES = [
     (4096, 11008, 128, (1, 64)),                                # Llama-2-7B gate/up
     (11008, 4096, 128, (1, 32, 300)),                           # Llama-2-7B down (K = 172 k-blocks, odd splits)
     (8192, 1280, 128, (5,)),                                    # Llama-2-70B qkv shard on 8 ranks
+    # full-size shapes of BASELINE configs 4 / 5 and the other group sizes at the headline size
+    (14336, 4096, 128, (1, 64)),                                # Mistral-7B down
+    (4096, 28672, 128, (1, 16)),                                # Mistral-7B gate|up
+    (8192, 10240, 128, (1, 8)),                                 # Llama-2-70B q|k|v
+    (28672, 8192, 128, (1, 8)),                                 # Llama-2-70B down
+    (8192, 3584, 128, (1, 64, 200)),                            # Llama-2-70B gate (or up) shard on 8 ranks
+    (28672, 1024, 128, (1, 33)),                                # Llama-2-70B down shard on 8 ranks
+    (4096, 4096, 64, (1, 16, 256)),
+    (4096, 4096, 32, (1, 16, 256)),
 ]
 
 
@@ -336,9 +345,11 @@ def test_against_unmodified_reference_kernel(ops):
     if ref is None:
         pytest.skip("oracle/_ref/quick_kernels_ref.so not built (needs /root/reference at build time)")
     import quick_kernels
-    for (K, N, G, sk) in [(512, 512, 128, 8), (4096, 4096, 128, 8), (4096, 11008, 128, 2), (256, 768, 64, 2)]:
+    shapes = [(512, 512, 128, 8), (4096, 4096, 128, 8), (4096, 11008, 128, 2), (256, 768, 64, 2),
+              (14336, 4096, 128, 8), (4096, 28672, 128, 2), (8192, 3584, 128, 2), (28672, 1024, 128, 8), (4096, 4096, 32, 8)]
+    for (K, N, G, sk) in shapes:
         q, z, s, qw, qz, sc, W16 = make_gpu_case(ops, K, N, G)
-        for M in (1, 8, 16, 17, 64, 100, 256):
+        for M in ((1, 8, 16, 17, 64, 100, 256, 512) if K * N <= 4096 * 11008 else (1, 64, 512)):
             A = torch.from_numpy(qo.make_activations(M, K, seed=M)).cuda()
             r = ref.gemm_forward_cuda_quick(A, qw, sc, qz, sk).reshape(M, N)
             mine = quick_kernels.gemm_forward_cuda_quick(A, qw, sc, qz, sk).reshape(M, N)
