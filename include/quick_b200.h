@@ -120,6 +120,46 @@ int qb200_gemm_w4a16_allgather(const void* A_fp16, const uint32_t* wq, const uin
  * zero-initialised uint32 in peer-mapped memory.  Traps after ~2 s instead of hanging if a peer never arrives. */
 int qb200_peer_barrier(unsigned* epoch_counter, unsigned* const* flag_arrays, int rank, int n_peers, void* stream);
 
+/* ---- Tensor parallelism without barrier kernels: the hand-over rides in the producing and the consuming kernels. ----
+ * A "gathered buffer" is a [rows][ld] fp16 buffer that exists on every rank (peer-mapped, e.g. torch symmetric memory);
+ * every rank's producer stores its column slab into ALL copies.  Per gathered buffer and rank there is a local epoch
+ * counter (zero-initialised uint32 in ordinary device memory) and a flag array of n_peers zero-initialised uint32 in
+ * peer-mapped memory.
+ *   qb200_peer_signal  given to the kernel that FILLS the buffer: one of its threads bumps *epoch (after the kernel's own
+ *                      stream predecessor has completed).  The fill itself is plain peer / multicast stores.
+ *   qb200_peer_wait    given to the FIRST kernel that reads the buffer after a fill, on every rank: once its own stream
+ *                      predecessor — hence this rank's producer grid, hence the delivery of this rank's slab — has
+ *                      completed, it writes *epoch into slot [rank] of every rank's flag array (st.release.sys) and polls its
+ *                      own array until every rank has announced that epoch (traps after QB200_PEER_TIMEOUT_S, default 120 s,
+ *                      0 = never).  Later readers on the same stream need no wait.
+ * Rules: on every rank the same sequence of fills per buffer (SPMD); every fill is followed by a waiting reader; the readers
+ * of fill i on a rank precede that rank's producer of fill i+1 in stream order; and between two fills of one buffer every
+ * rank runs the producer of some other gathered buffer that it launches after its readers of the first fill (a decoder
+ * layer alternates four buffers), so no rank's slab can overwrite rows a slower rank is still reading.  The epoch lives on
+ * the device: CUDA-graph replays work.  The reference has no multi-GPU path for this operator. */
+typedef struct { const unsigned* epoch; unsigned* const* flag_arrays; int rank; int n_peers; } qb200_peer_wait;
+typedef struct { unsigned* epoch; } qb200_peer_signal;
+
+/* The GEMM of a tensor-parallel layer.  n_peers = 0: local output C_local [M][N] (e.g. head-sharded q|k|v, gate|up);
+ * n_peers >= 1: column-parallel with the gather fused into the epilogue exactly like qb200_gemm_w4a16_allgather (C_peers,
+ * C_multicast_or_null, ld_c, col0; C_local ignored).  wait (or NULL): A lives in a gathered buffer; signal (or NULL): C is a
+ * gathered buffer.  Weights keep streaming while the wait polls: the hand-over costs no kernel of its own. */
+int qb200_gemm_w4a16_tp(const void* A_fp16, const uint32_t* wq, const uint32_t* sz, const void* bias_fp16_or_null,
+                        const void* residual_fp16_or_null, void* C_local_fp16, void* const* C_peers, void* C_multicast_or_null,
+                        int n_peers, int ld_c, int col0, int M, int K, int N, int G, int tok, int split, unsigned flags,
+                        const qb200_peer_wait* wait, const qb200_peer_signal* signal, void* stream);
+/* qb200_rmsnorm on rows of a gathered buffer (wait may be NULL). */
+int qb200_rmsnorm_tp(const void* x_fp16, const void* weight_fp16, void* y_fp16, int rows, int H, float eps,
+                     const qb200_peer_wait* wait, void* stream);
+/* silu(g) * u of this rank's gate|up slab [rows][2 I], written into every rank's [rows][ld] activation buffer at column
+ * col0 (the gathered input of the column-parallel down projection) and published. */
+int qb200_silu_mul_tp(const void* gate_up_fp16, long long rows, int I, void* const* act_peers, void* act_multicast_or_null,
+                      int n_peers, int ld, int col0, const qb200_peer_signal* signal, void* stream);
+/* src [rows][n_local] -> every rank's [rows][ld] buffer at column col0, published (this rank's attention heads -> the
+ * gathered input of the column-parallel output projection). */
+int qb200_scatter_cols(const void* src_fp16, long long rows, int n_local, void* const* dst_peers, void* dst_multicast_or_null,
+                       int n_peers, int ld, int col0, const qb200_peer_signal* signal, void* stream);
+
 /* Reports the configuration qb200_gemm_w4a16 would pick. */
 int qb200_gemm_plan(int M, int K, int N, int G, int split_k_hint, int* tok, int* split, int* ctas);
 /* Same for a given set of launch flags (the independent plan never splits K). */

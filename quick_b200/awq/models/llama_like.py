@@ -102,6 +102,13 @@ def _tp_rank() -> int:
     return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
 
 
+def _from_packed(like: WQLinear_QUICK, packed, n_out: int, bias=None) -> WQLinear_QUICK:
+    out = WQLinear_QUICK(like.w_bit, like.group_size, packed[0].shape[0] * 4, n_out, False, "meta", like.k_split_1, like.k_split_2)
+    out.qweight, out.qzeros, out.scales = packed
+    out.bias = bias
+    return out
+
+
 def shard_quick_linear(m: WQLinear_QUICK, rank: int, world: int) -> WQLinear_QUICK:
     """The column-parallel shard `rank` of `world` of a packed linear: output columns [rank·N/world, (rank+1)·N/world)
     as a WQLinear_QUICK of its own (layout.shard_columns: the inverse of QUICK_cat; N/world must stay a multiple of
@@ -110,45 +117,101 @@ def shard_quick_linear(m: WQLinear_QUICK, rank: int, world: int) -> WQLinear_QUI
     if m.out_features % (128 * world) != 0:
         raise ValueError(f"N={m.out_features} does not split into {world} shards of 128-column tiles")
     n_local = m.out_features // world
-    out = WQLinear_QUICK(m.w_bit, m.group_size, m.in_features, n_local, False, "meta", m.k_split_1, m.k_split_2)
-    out.qweight, out.qzeros, out.scales = shard_columns(m.qweight, m.qzeros, m.scales, rank, world)
-    out.bias = None if m.bias is None else m.bias[rank * n_local:(rank + 1) * n_local].clone()
-    return out
+    bias = None if m.bias is None else m.bias[rank * n_local:(rank + 1) * n_local].clone()
+    return _from_packed(m, shard_columns(m.qweight, m.qzeros, m.scales, rank, world), n_local, bias)
 
 
-def _gather_columns(local: torch.Tensor) -> torch.Tensor:
-    """Tensor-parallel linears (BASELINE config 5): every rank holds N/R output columns of each
-    weight and computes its (.., N/R) slab with the same kernel; ONE all-gather (NCCL over NVLink) rebuilds the
-    full width.  Same reassembly as quick_b200.parallel.ColumnParallelQuickLinear."""
-    import torch.distributed as dist
-    R = dist.get_world_size()
-    lead, n_local = local.shape[:-1], local.shape[-1]
-    flat = local.reshape(-1, n_local).contiguous()
-    gathered = torch.empty((R * flat.shape[0], n_local), dtype=flat.dtype, device=flat.device)
-    dist.all_gather_into_tensor(gathered, flat)
-    return gathered.view(R, flat.shape[0], n_local).permute(1, 0, 2).reshape(lead + (R * n_local,))
+def tp_shard_qkv(m: WQLinear_QUICK, nh: int, nkv: int, hd: int, rank: int, world: int) -> WQLinear_QUICK:
+    """Head-parallel shard of a fused q‖k‖v projection: rank r keeps [q heads of r | k heads of r | v heads of r], so
+    attention is local to the rank and q‖k‖v needs no gather at all ('qkv -> attention is head-local')."""
+    from ...layout import quick_cat, slice_columns
+    if nh % world or nkv % world:
+        raise ValueError(f"{nh} query / {nkv} key-value heads do not split over {world} ranks")
+    nh_l, nkv_l = nh // world, nkv // world
+    runs = [(rank * nh_l * hd, nh_l * hd), (nh * hd + rank * nkv_l * hd, nkv_l * hd), ((nh + nkv) * hd + rank * nkv_l * hd, nkv_l * hd)]
+    if any(w % 128 or s0 % 128 for s0, w in runs):
+        raise ValueError(f"heads per rank x head_dim ({nh_l}x{hd}, {nkv_l}x{hd}) must be multiples of the 128-column tile")
+    parts = [slice_columns(m.qweight, m.qzeros, m.scales, s0, s0 + w) for s0, w in runs]
+    packed = tuple(quick_cat([p[i] for p in parts], opt).contiguous() for i, opt in enumerate(("qweight", "qzeros", "scales")))
+    bias = None if m.bias is None else torch.cat([m.bias[s0:s0 + w] for s0, w in runs]).clone()
+    return _from_packed(m, packed, sum(w for _, w in runs), bias)
 
 
-# Tensor-parallel exchange: "peer" = fused GEMM + all-gather over peer memory (quick_b200.parallel.PeerGatherWorkspace),
-# "nccl" = kernel + one all_gather_into_tensor + re-layout copy (the baseline).  QB200_TP_MODE selects.
+def tp_pad_intermediate(I: int, world: int) -> int:
+    """The MLP width a tensor-parallel model runs with: the next multiple of 128 x world (zero-weight channels: exact)."""
+    step = 128 * world
+    return (I + step - 1) // step * step
+
+
+def tp_shard_gate_up(m: WQLinear_QUICK, I: int, rank: int, world: int) -> WQLinear_QUICK:
+    """Rank r's [gate columns of r | up columns of r] of a fused gate‖up projection (both halves padded with zero-weight
+    channels to a multiple of 128 x world first): SiLU(gate)·up is then local to the rank, and only the activation —
+    half as wide as gate‖up — is gathered for the down projection."""
+    from ...layout import pad_columns, quick_cat, slice_columns
+    Ip = tp_pad_intermediate(I, world)
+    I_l = Ip // world
+    halves = []
+    for h in range(2):
+        part = slice_columns(m.qweight, m.qzeros, m.scales, h * I, (h + 1) * I) if I % 128 == 0 else None
+        if part is None:
+            raise ValueError(f"intermediate size {I} is not a multiple of the 128-column tile")
+        part = pad_columns(*part, Ip)
+        halves.append(slice_columns(*part, rank * I_l, (rank + 1) * I_l))
+    packed = tuple(quick_cat([p[i] for p in halves], opt).contiguous() for i, opt in enumerate(("qweight", "qzeros", "scales")))
+    bias = None
+    if m.bias is not None:
+        pad = torch.zeros(Ip - I, dtype=m.bias.dtype, device=m.bias.device)
+        bias = torch.cat([torch.cat([m.bias[h * I:(h + 1) * I], pad])[rank * I_l:(rank + 1) * I_l] for h in range(2)]).clone()
+    return _from_packed(m, packed, 2 * I_l, bias)
+
+
+def tp_shard_down(m: WQLinear_QUICK, I: int, rank: int, world: int) -> WQLinear_QUICK:
+    """Column-parallel shard of the down projection whose input channels are padded like tp_shard_gate_up pads them."""
+    from ...layout import pad_rows
+    Ip = tp_pad_intermediate(I, world)
+    padded = _from_packed(m, pad_rows(m.qweight, m.qzeros, m.scales, Ip, m.group_size), m.out_features, m.bias)
+    return shard_quick_linear(padded, rank, world)
+
+
+# Tensor-parallel exchange: "peer" = every producer stores its column slab into all ranks' buffers over NVLink and the
+# hand-over rides in the kernels themselves (quick_b200.parallel.GatheredBuffer, include/quick_b200.h qb200_peer_*);
+# "nccl" = the same dataflow with torch.distributed all-gathers (the baseline, and what runs on CPU / gloo).
 import os as _os
 TP_MODE = _os.environ.get("QB200_TP_MODE", "peer")
+
+
+class TensorParallel:
+    """Per-model tensor-parallel state: rank / world and, in peer mode, the four gathered buffers a decoder layer
+    alternates — attention output, hidden state after the attention block (B), MLP activation, hidden state after the
+    MLP (A).  Between two fills of one buffer every rank fills the three others, which is what makes reuse safe
+    (include/quick_b200.h)."""
+
+    def __init__(self, cfg, batch: int, dev):
+        import torch.distributed as dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.mode = TP_MODE if torch.device(dev).type == "cuda" else "nccl"
+        self.I_pad = tp_pad_intermediate(cfg.intermediate_size, self.world)
+        if self.mode == "peer":
+            from ...parallel import GatheredBuffer
+            rows = batch * cfg.max_seq_len
+            self.attn = GatheredBuffer(rows, cfg.num_heads * cfg.head_dim)
+            self.hid_b = GatheredBuffer(rows, cfg.hidden_size)
+            self.act = GatheredBuffer(rows, self.I_pad)
+            self.hid_a = GatheredBuffer(rows, cfg.hidden_size)
+
+    def all_gather_cols(self, local: torch.Tensor) -> torch.Tensor:
+        """(M, n/R) slabs of every rank -> (M, n) in rank order: ONE all-gather (NCCL over NVLink, or gloo)."""
+        import torch.distributed as dist
+        flat = local.contiguous()
+        gathered = torch.empty((self.world * flat.shape[0], flat.shape[1]), dtype=flat.dtype, device=flat.device)
+        dist.all_gather_into_tensor(gathered, flat)
+        return gathered.view(self.world, flat.shape[0], flat.shape[1]).permute(1, 0, 2).reshape(flat.shape[0], -1)
 
 
 def _linear(m: WQLinear_QUICK, x, ref_mod=None, residual=None):
     """Route through the B200 kernel, or (baseline runs only) through the unmodified reference kernel.
     residual: returns residual + linear(x) (fused into the GEMM epilogue)."""
     if ref_mod is None:
-        ws = getattr(m, "peer_ws", None)
-        if ws is not None:
-            wq, sz = m._prepacked()
-            x2d = x.reshape(-1, x.shape[-1])
-            res2d = None if residual is None else residual.reshape(-1, ws.n_total)
-            y = ws.gemm(x2d, wq, sz, m.out_features, m.group_size, bias=m.bias, residual=res2d)
-            return y.reshape(x.shape[:-1] + (ws.n_total,))
-        if getattr(m, "tp_sharded", False):
-            y = _gather_columns(m(x))
-            return y if residual is None else residual + y
         return m(x, residual if FUSED_GLUE else None) if (residual is None or FUSED_GLUE) else residual + m(x)
     split = m.k_split_1 if m.out_features > m.in_features else m.k_split_2      # quick.py:161-164
     out = ref_mod.gemm_forward_cuda_quick(x.reshape(-1, x.shape[-1]), m.qweight, m.scales, m.qzeros, split)
@@ -157,65 +220,60 @@ def _linear(m: WQLinear_QUICK, x, ref_mod=None, residual=None):
 
 
 class Block(nn.Module):
-    def __init__(self, cfg: LlamaLikeConfig, dev, gen, batch: int, peer_ws=None, parts=None):
+    def __init__(self, cfg: LlamaLikeConfig, dev, gen, batch: int, tp: Optional["TensorParallel"] = None, parts=None):
         """parts: {"qkv_proj", "o_proj", "gate_up_proj", "down_proj": WQLinear_QUICK, "norm_1", "norm_2": fp16 weight}
-        taken from a loaded checkpoint (fuse_hf_model); without it the weights are random-init."""
+        taken from a loaded checkpoint (fuse_hf_model); without it the weights are random-init.
+        tp: tensor-parallel state (None on one GPU).  Under tensor parallelism this rank holds: q‖k‖v of ITS heads
+        (attention and the KV cache are head-sharded, nothing is gathered), N/R output columns of o_proj and down_proj
+        (column-parallel, slabs gathered), and [gate | up] of ITS slice of the MLP width (SiLU·up is local, the
+        activation is gathered for down_proj)."""
         super().__init__()
-        self.cfg = cfg
+        self.cfg, self.tp = cfg, tp
+        R = tp.world if tp is not None else 1
+        rank = tp.rank if tp is not None else 0
         hd, nh, nkv = cfg.head_dim, cfg.num_heads, cfg.num_kv_heads
-        self.norm_1 = RMSNorm(cfg.hidden_size, cfg.rms_eps, dev)
-        self.norm_2 = RMSNorm(cfg.hidden_size, cfg.rms_eps, dev)
+        H, I = cfg.hidden_size, cfg.intermediate_size
+        if nh % R or nkv % R:
+            raise ValueError(f"{nh} query / {nkv} key-value heads do not split over {R} ranks")
+        self.nh_l, self.nkv_l = nh // R, nkv // R
+        self.I_l = (tp.I_pad if tp is not None else I) // R
+        self.norm_1 = RMSNorm(H, cfg.rms_eps, dev)
+        self.norm_2 = RMSNorm(H, cfg.rms_eps, dev)
         if parts is not None:
-            R = tp_world()
             self.norm_1.weight.data = parts["norm_1"].detach().to(dev, torch.float16).contiguous()
             self.norm_2.weight.data = parts["norm_2"].detach().to(dev, torch.float16).contiguous()
-            expect = {"qkv_proj": (cfg.hidden_size, (nh + 2 * nkv) * hd), "o_proj": (nh * hd, cfg.hidden_size),
-                      "gate_up_proj": (cfg.hidden_size, 2 * cfg.intermediate_size),
-                      "down_proj": (cfg.intermediate_size, cfg.hidden_size)}
+            expect = {"qkv_proj": (H, (nh + 2 * nkv) * hd), "o_proj": (nh * hd, H), "gate_up_proj": (H, 2 * I), "down_proj": (I, H)}
             for name, (k, n) in expect.items():
                 m = parts[name]
                 if (m.in_features, m.out_features) != (k, n):
                     raise ValueError(f"{name}: ({m.in_features} -> {m.out_features}) does not match the config ({k} -> {n})")
-                if R > 1:       # tensor parallel: this rank keeps its N/R output columns (SURVEY §8e), the rest is freed
-                    m = shard_quick_linear(m, _tp_rank(), R)
-                    if TP_MODE == "peer":
-                        m.peer_ws = peer_ws(n)
+                if R > 1:       # this rank's shard; the full tensors are freed by the caller
+                    m = {"qkv_proj": lambda: tp_shard_qkv(m, nh, nkv, hd, rank, R), "o_proj": lambda: shard_quick_linear(m, rank, R),
+                         "gate_up_proj": lambda: tp_shard_gate_up(m, I, rank, R), "down_proj": lambda: tp_shard_down(m, I, rank, R)}[name]()
                 m.tp_sharded = R > 1
                 setattr(self, name, m)
-            self.register_buffer("cache_k", torch.zeros(batch, nkv, cfg.max_seq_len, hd, dtype=torch.float16, device=dev), persistent=False)
-            self.register_buffer("cache_v", torch.zeros(batch, nkv, cfg.max_seq_len, hd, dtype=torch.float16, device=dev), persistent=False)
-            return
-        # Under torch.distributed every linear is column-parallel: this rank's module holds N/R output columns
-        # (random-init, so the shard is generated directly instead of slicing a full weight with
-        # layout.shard_columns) and _linear() all-gathers the slabs.  N/R must stay a multiple of 128.
-        R = tp_world()
+        else:
+            # random-init: the rank's shard is generated directly (N/R must stay a multiple of the 128-column tile)
+            def lin(in_f, out_f):
+                assert out_f % 128 == 0, f"N={out_f} is not a multiple of the 128-column tile"
+                m = random_quick_linear(in_f, out_f, cfg.group_size, dev, gen)
+                m.tp_sharded = R > 1
+                return m
 
-        def lin(in_f, out_f):
-            assert out_f % (128 * R) == 0, f"N={out_f} does not split into {R} shards of 128-column tiles"
-            m = random_quick_linear(in_f, out_f // R, cfg.group_size, dev, gen)
-            m.tp_sharded = R > 1
-            if R > 1 and TP_MODE == "peer":
-                m.peer_ws = peer_ws(out_f)       # one workspace per projection width, shared by all layers
-            return m
+            self.qkv_proj = lin(H, (self.nh_l + 2 * self.nkv_l) * hd)
+            self.o_proj = lin(nh * hd, H // R)
+            self.gate_up_proj = lin(H, 2 * self.I_l)
+            self.down_proj = lin(self.I_l * R, H // R)
+        self.register_buffer("cache_k", torch.zeros(batch, self.nkv_l, cfg.max_seq_len, hd, dtype=torch.float16, device=dev), persistent=False)
+        self.register_buffer("cache_v", torch.zeros(batch, self.nkv_l, cfg.max_seq_len, hd, dtype=torch.float16, device=dev), persistent=False)
 
-        self.qkv_proj = lin(cfg.hidden_size, (nh + 2 * nkv) * hd)
-        self.o_proj = lin(cfg.hidden_size, cfg.hidden_size)
-        self.gate_up_proj = lin(cfg.hidden_size, 2 * cfg.intermediate_size)
-        self.down_proj = lin(cfg.intermediate_size, cfg.hidden_size)
-        self.register_buffer("cache_k", torch.zeros(batch, nkv, cfg.max_seq_len, hd, dtype=torch.float16, device=dev), persistent=False)
-        self.register_buffer("cache_v", torch.zeros(batch, nkv, cfg.max_seq_len, hd, dtype=torch.float16, device=dev), persistent=False)
-
-    def forward(self, x, cos, sin, pos_idx, attn_mask, ref_mod=None, rope=None):
-        cfg = self.cfg
-        B, T, _ = x.shape
-        hd, nh, nkv = cfg.head_dim, cfg.num_heads, cfg.num_kv_heads
-        qkv = _linear(self.qkv_proj, self.norm_1(x), ref_mod)
-        if T == 1 and attn_mask is None:
+    def _attention(self, qkv, cos, sin, pos_idx, attn_mask, rope, fused_decode):
+        """qkv (B, T, (nh_l + 2 nkv_l) hd) of this rank's heads -> attention output (B, T, nh_l hd); updates the cache."""
+        B, T, _ = qkv.shape
+        hd, nh, nkv = self.cfg.head_dim, self.nh_l, self.nkv_l
+        if fused_decode:
             # decode step on the fused path (the model decided: see LlamaLikeQuickModel._fused_decode_ok)
-            o = quick_kernels.attn_decode(qkv, rope[0], rope[1], pos_idx, self.cache_k, self.cache_v, nh, nkv)
-            x = _linear(self.o_proj, o, ref_mod, residual=x)
-            gu = _linear(self.gate_up_proj, self.norm_2(x), ref_mod)
-            return _linear(self.down_proj, quick_kernels.silu_mul(gu), ref_mod, residual=x)
+            return quick_kernels.attn_decode(qkv, rope[0], rope[1], pos_idx, self.cache_k, self.cache_v, nh, nkv)
         if FUSED_GLUE and qkv.is_cuda:
             # rotary embedding of q and k + KV-cache update in one kernel (rope tables are indexed by position)
             q = quick_kernels.rope_kv_update(qkv, rope[0], rope[1], pos_idx, self.cache_k, self.cache_v, nh, nkv)
@@ -228,14 +286,69 @@ class Block(nn.Module):
             self.cache_k.index_copy_(2, pos_idx, k)
             self.cache_v.index_copy_(2, pos_idx, v)
         o = F.scaled_dot_product_attention(q, self.cache_k, self.cache_v, attn_mask=attn_mask, enable_gqa=(nkv != nh))
-        x = _linear(self.o_proj, o.transpose(1, 2).reshape(B, T, nh * hd), ref_mod, residual=x)
+        return o.transpose(1, 2).reshape(B, T, nh * hd)
+
+    def forward(self, x, cos, sin, pos_idx, attn_mask, ref_mod=None, rope=None, x_src=None):
+        """Returns (hidden state, the gathered buffer it lives in or None)."""
+        if self.tp is not None:
+            return self.forward_tp(x, x_src, cos, sin, pos_idx, attn_mask, rope)
+        cfg = self.cfg
+        B, T, _ = x.shape
+        fused_decode = T == 1 and attn_mask is None
+        qkv = _linear(self.qkv_proj, self.norm_1(x), ref_mod)
+        o = self._attention(qkv, cos, sin, pos_idx, attn_mask, rope, fused_decode)
+        x = _linear(self.o_proj, o, ref_mod, residual=x)
         gu = _linear(self.gate_up_proj, self.norm_2(x), ref_mod)
         if FUSED_GLUE and gu.is_cuda:
             act = quick_kernels.silu_mul(gu)
         else:
             g, u = gu.split(cfg.intermediate_size, dim=-1)
             act = F.silu(g) * u
-        return _linear(self.down_proj, act, ref_mod, residual=x)
+        return _linear(self.down_proj, act, ref_mod, residual=x), None
+
+    def forward_tp(self, x, x_src, cos, sin, pos_idx, attn_mask, rope):
+        """One decoder layer on this rank's shards.  Peer mode: 9 kernels, none of them a barrier — the two column-parallel
+        GEMMs store their slabs into every rank's hidden-state buffer, the attention output and the MLP activation are
+        scattered the same way, and each consumer (RMSNorm rows, GEMM activations) meets the producers in its own
+        prologue.  NCCL mode: the same dataflow with four all-gathers."""
+        tp, cfg = self.tp, self.cfg
+        B, T, H = x.shape
+        M = B * T
+        hd = cfg.head_dim
+        fused_decode = T == 1 and attn_mask is None
+        x2d = x.reshape(M, H)
+        col_h = tp.rank * (H // tp.world)
+        if tp.mode == "peer":
+            from ... import ops
+            xn = ops.rmsnorm_tp(x2d, self.norm_1.weight, self.norm_1.eps, wait=x_src)
+            wq, sz = self.qkv_proj._prepacked()
+            qkv = ops.gemm_tp(xn, wq, sz, self.qkv_proj.out_features, self.qkv_proj.group_size, bias=self.qkv_proj.bias)
+            o = self._attention(qkv.view(B, T, -1), cos, sin, pos_idx, attn_mask, rope, fused_decode)
+            ops.scatter_cols(o.reshape(M, self.nh_l * hd).contiguous(), tp.attn, tp.rank * self.nh_l * hd)
+            wq, sz = self.o_proj._prepacked()
+            ops.gemm_tp(tp.attn.rows(M), wq, sz, self.o_proj.out_features, self.o_proj.group_size, bias=self.o_proj.bias,
+                        residual=x2d, dst=tp.hid_b, col0=col_h, wait=tp.attn)
+            x2 = tp.hid_b.rows(M)
+            xn2 = ops.rmsnorm_tp(x2, self.norm_2.weight, self.norm_2.eps, wait=tp.hid_b)
+            wq, sz = self.gate_up_proj._prepacked()
+            gu = ops.gemm_tp(xn2, wq, sz, self.gate_up_proj.out_features, self.gate_up_proj.group_size, bias=self.gate_up_proj.bias)
+            ops.silu_mul_tp(gu, tp.act, tp.rank * self.I_l)
+            wq, sz = self.down_proj._prepacked()
+            ops.gemm_tp(tp.act.rows(M), wq, sz, self.down_proj.out_features, self.down_proj.group_size, bias=self.down_proj.bias,
+                        residual=x2, dst=tp.hid_a, col0=col_h, wait=tp.act)
+            return tp.hid_a.rows(M).view(B, T, H), tp.hid_a
+        qkv = self.qkv_proj(self.norm_1(x2d))
+        o = self._attention(qkv.view(B, T, -1), cos, sin, pos_idx, attn_mask, rope, fused_decode)
+        o_full = tp.all_gather_cols(o.reshape(M, self.nh_l * hd))
+        x2 = x2d + tp.all_gather_cols(self.o_proj(o_full))
+        gu = self.gate_up_proj(self.norm_2(x2))
+        if FUSED_GLUE and gu.is_cuda:
+            act = quick_kernels.silu_mul(gu)
+        else:
+            g, u = gu.split(self.I_l, dim=-1)
+            act = F.silu(g) * u
+        out = x2 + tp.all_gather_cols(self.down_proj(tp.all_gather_cols(act)))
+        return out.view(B, T, H), None
 
 
 def _rope(t, cos, sin):
@@ -256,22 +369,14 @@ class LlamaLikeQuickModel(nn.Module):
         rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
         gen = torch.Generator(device=dev); gen.manual_seed(seed + 1000 * rank)   # every rank draws its own column slabs
         self.embed = parts["embed"] if parts is not None else nn.Embedding(cfg.vocab_size, cfg.hidden_size, device=dev, dtype=torch.float16)
-        # tensor parallel, peer mode: one symmetric full-width output buffer per projection width (rows = the largest
-        # token count a forward can carry), shared by all layers — consecutive uses are separated by other barriers
-        self._peer_ws = {}
-
-        def peer_ws(n_total):
-            if n_total not in self._peer_ws:
-                from ...parallel import PeerGatherWorkspace
-                self._peer_ws[n_total] = PeerGatherWorkspace(batch * cfg.max_seq_len, n_total)
-            return self._peer_ws[n_total]
-
+        # tensor parallel (a process group exists): head-sharded attention, column-parallel o / down, local SiLU·up
+        self.tp = TensorParallel(cfg, batch, dev) if tp_world() > 1 else None
         if parts is None:
-            self.blocks = nn.ModuleList([Block(cfg, dev, gen, batch, peer_ws) for _ in range(cfg.num_layers)])
+            self.blocks = nn.ModuleList([Block(cfg, dev, gen, batch, self.tp) for _ in range(cfg.num_layers)])
             self.norm = RMSNorm(cfg.hidden_size, cfg.rms_eps, dev)
             self.lm_head = nn.Linear(cfg.hidden_size, cfg.vocab_size, bias=False, device=dev, dtype=torch.float16)
         else:
-            self.blocks = nn.ModuleList([Block(cfg, dev, gen, batch, peer_ws, parts=p) for p in parts["blocks"]])
+            self.blocks = nn.ModuleList([Block(cfg, dev, gen, batch, self.tp, parts=p) for p in parts["blocks"]])
             self.norm = RMSNorm(cfg.hidden_size, cfg.rms_eps, dev)
             self.norm.weight.data = parts["norm"].detach().to(dev, torch.float16).contiguous()
             self.lm_head = parts["lm_head"]
@@ -288,12 +393,12 @@ class LlamaLikeQuickModel(nn.Module):
         rope_kv_update + SDPA path."""
         cfg = self.cfg
         if not (ATTN_DECODE and FUSED_GLUE and x.is_cuda and x.shape[1] == 1 and x.shape[0] == self.batch
-                and self.batch <= ATTN_DECODE_MAX_BATCH and cfg.max_seq_len <= ATTN_DECODE_MAX_CACHE
-                and tp_world() == 1):     # not yet validated on several GPUs
+                and self.batch <= ATTN_DECODE_MAX_BATCH and cfg.max_seq_len <= ATTN_DECODE_MAX_CACHE):
             return False
         if self._attn_decode_supported is None:
-            self._attn_decode_supported = bool(quick_kernels.attn_decode_supported(cfg.num_heads, cfg.num_kv_heads, cfg.head_dim,
-                                                                                    cfg.max_seq_len))
+            R = self.tp.world if self.tp is not None else 1      # tensor parallel: this rank's heads only
+            self._attn_decode_supported = bool(quick_kernels.attn_decode_supported(cfg.num_heads // R, cfg.num_kv_heads // R,
+                                                                                    cfg.head_dim, cfg.max_seq_len))
         return self._attn_decode_supported
 
     @torch.no_grad()
@@ -310,8 +415,15 @@ class LlamaLikeQuickModel(nn.Module):
             # causal mask over the static cache: key j visible to query at position p iff j <= p
             keys = torch.arange(cfg.max_seq_len, device=x.device)
             attn_mask = keys[None, :] <= pos_idx[:, None]
+        src = None        # tensor parallel, peer mode: the gathered buffer the hidden state lives in
         for blk in self.blocks:
-            x = blk(x, cos, sin, pos_idx, attn_mask, self.ref_mod, (self.rope_cos, self.rope_sin))
+            x, src = blk(x, cos, sin, pos_idx, attn_mask, self.ref_mod, (self.rope_cos, self.rope_sin), src)
+        if src is not None:
+            # the final norm is the consumer of the last gathered hidden state: it meets the ranks inside the kernel, so
+            # it runs on all rows (no torch op may touch gathered rows before a wait) and the last position is sliced after
+            from ... import ops
+            x = ops.rmsnorm_tp(x.reshape(-1, x.shape[-1]), self.norm.weight, self.norm.eps, wait=src).view(x.shape)
+            return self.lm_head(x if all_logits else x[:, -1:, :])
         return self.lm_head(self.norm(x if all_logits else x[:, -1:, :]))
 
     # ---- generation on the static cache (what the reference gets from HF generate over its fused blocks,

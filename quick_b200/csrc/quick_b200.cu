@@ -1,6 +1,7 @@
 // quick_b200 — C-ABI implementation (see include/quick_b200.h for the contract and the reference
 // interfaces each entry point replaces).  sm_100a only; there is no CPU or non-tcgen05 fallback on
 // the hot path: if the device is not compute capability 10.x the GEMM entry points return QB200_ECUDA.
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -288,11 +289,16 @@ __global__ void gemm_simt_kernel(const __half* __restrict__ A, const uint32_t* _
 // ------------------------------------------------------------------------------------------------
 
 // y = fp16( fp16( x * rsqrt(mean(x^2) + eps) ) * w ), statistics in fp32.  One CTA per row.
-__global__ void rmsnorm_kernel(const __half* __restrict__ x, const __half* __restrict__ w, __half* __restrict__ y, int H, float eps) {
+__global__ void rmsnorm_kernel(const __half* __restrict__ x, const __half* __restrict__ w, __half* __restrict__ y, int H, float eps,
+                               const qb200::PeerWait wait) {
   // programmatic dependent launch: let the next kernel (usually a GEMM: barrier init, TMEM, weight prefetch) start
   // now; our own input comes from the previous kernel, so wait for it before the first load
   qb200::pdl_launch_dependents();
   qb200::pdl_wait_prior_grid();
+  if (wait.epoch != nullptr) {          // tensor parallel: x is a gathered buffer, meet the ranks that fill it
+    if (threadIdx.x < 32) qb200::peer_wait_warp(wait, blockIdx.x == 0);
+    __syncthreads();
+  }
   const __half* xr = x + static_cast<size_t>(blockIdx.x) * H;
   __half* yr = y + static_cast<size_t>(blockIdx.x) * H;
   float ss = 0.f;
@@ -554,6 +560,58 @@ __global__ void silu_mul_kernel(const __half* __restrict__ gu, __half* __restric
   *reinterpret_cast<uint4*>(act + idx) = o;
 }
 
+// Destination of a column slab that every rank needs (tensor parallel): the [rows][ld] buffers of all ranks at column
+// col0 — ONE multimem.st per 16-byte chunk through the NVSwitch multicast mapping when there is one, else a loop of
+// peer stores.
+struct PeerDst {
+  __half* peer[8];
+  __half* mc;
+  int n, ld, col0;
+};
+__device__ __forceinline__ void store16_all(const PeerDst& d, size_t off, uint4 v) {
+  if (d.mc != nullptr) qb200::multimem_st_v4(d.mc + off, v);
+  else for (int p = 0; p < d.n; ++p) *reinterpret_cast<uint4*>(d.peer[p] + off) = v;
+}
+// act[rows][I] = silu(g) * u of this rank's gate|up slab [rows][2 I], written to every rank's [rows][ld] activation
+// buffer at column col0 (the input of the column-parallel down projection), then published.
+__global__ void silu_mul_scatter_kernel(const __half* __restrict__ gu, size_t M, int I, const PeerDst dst, const qb200::PeerSignal sig) {
+  qb200::pdl_launch_dependents();
+  qb200::pdl_wait_prior_grid();
+  if (blockIdx.x == 0 && threadIdx.x == 0) qb200::peer_begin_fill(sig);
+  const size_t total = M * static_cast<size_t>(I);
+  for (size_t idx = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x * 8) {
+    const size_t m = idx / I;
+    const int i = static_cast<int>(idx % I);
+    const uint4 g = *reinterpret_cast<const uint4*>(gu + m * 2 * I + i);
+    const uint4 u = *reinterpret_cast<const uint4*>(gu + m * 2 * I + I + i);
+    const __half2* gh = reinterpret_cast<const __half2*>(&g);
+    const __half2* uh = reinterpret_cast<const __half2*>(&u);
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(gh[j]);
+      oh[j] = __hmul2(__floats2half2_rn(f.x / (1.f + expf(-f.x)), f.y / (1.f + expf(-f.y))), uh[j]);
+    }
+    store16_all(dst, m * dst.ld + dst.col0 + i, o);
+  }
+}
+// src[rows][n_local] -> every rank's [rows][ld] buffer at column col0, then published (the attention output of this
+// rank's heads, input of the column-parallel output projection).
+__global__ void scatter_cols_kernel(const __half* __restrict__ src, size_t M, int n_local, const PeerDst dst, const qb200::PeerSignal sig) {
+  qb200::pdl_launch_dependents();
+  qb200::pdl_wait_prior_grid();
+  if (blockIdx.x == 0 && threadIdx.x == 0) qb200::peer_begin_fill(sig);
+  const size_t total = M * static_cast<size_t>(n_local);
+  for (size_t idx = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x * 8) {
+    const size_t m = idx / n_local;
+    const int i = static_cast<int>(idx % n_local);
+    store16_all(dst, m * dst.ld + dst.col0 + i, *reinterpret_cast<const uint4*>(src + idx));
+  }
+}
+
 // Cross-GPU hand-over for the fused all-gather: every rank bumps its own epoch counter, publishes the epoch in its slot
 // of every peer's flag array (peer-mapped memory) and waits until all peers have published the same epoch in ITS array.
 // Launched right behind the GEMM on the same stream: the GEMM's peer stores are complete (kernel boundary) before the
@@ -678,6 +736,43 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStre
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+unsigned long long peer_timeout_ns() {   // QB200_PEER_TIMEOUT_S (default 120 s, 0 = never): a lost rank traps instead of hanging
+  static const unsigned long long v = [] {
+    const char* e = getenv("QB200_PEER_TIMEOUT_S");
+    const double sec = e ? atof(e) : 120.0;
+    return sec <= 0 ? 0ull : static_cast<unsigned long long>(sec * 1e9);
+  }();
+  return v;
+}
+qb200::PeerWait make_wait(const qb200_peer_wait* w) {
+  qb200::PeerWait r{};
+  if (w != nullptr && w->epoch != nullptr) {
+    r.epoch = w->epoch; r.flags = w->flag_arrays[w->rank]; r.rank = w->rank; r.n = w->n_peers; r.timeout_ns = peer_timeout_ns();
+    // 2 (default): device-scope acquire fence after the last poll — the rows being read are in THIS device's memory (L2 is
+    // where the peers' stores land, and they were released at system scope by the announcing ranks); 0: system-scope fence,
+    // the conservative form, 2.3 us (M = 1) to 7 us (64 reader CTAs) slower per hand-over on 2 GPUs (profiles/README.md)
+    static const int mode = [] { const char* e = getenv("QB200_TP_WAITMODE"); return e ? atoi(e) : 2; }();
+    r.mode = mode;
+    for (int p = 0; p < 8; ++p) r.peer_flags[p] = p < w->n_peers ? w->flag_arrays[p] : nullptr;
+  }
+  return r;
+}
+qb200::PeerSignal make_signal(const qb200_peer_signal* s) {
+  qb200::PeerSignal r{};
+  if (s != nullptr && s->epoch != nullptr) r.epoch = s->epoch;
+  return r;
+}
+int check_peer_args(const qb200_peer_wait* w, const qb200_peer_signal* s) {
+  (void)s;
+  if (w != nullptr && w->epoch != nullptr) {
+    if (w->flag_arrays == nullptr || w->n_peers < 1 || w->n_peers > 8 || w->rank < 0 || w->rank >= w->n_peers)
+      return fail(QB200_EINVAL, "peer wait: flag arrays, rank and n_peers (1..8) required");
+    for (int p = 0; p < w->n_peers; ++p)
+      if (w->flag_arrays[p] == nullptr) return fail(QB200_EINVAL, "peer wait: null flag array %d", p);
+  }
+  return QB200_OK;
 }
 
 std::atomic<int> g_variant{-1};        // tile-configuration variant forced by qb200_debug_set_variant (QB200_VARIANTS builds); -1 = planner
@@ -838,7 +933,7 @@ void plan(int M, int K, int N, int split_hint, unsigned flags, int* tok_out, int
 namespace {
 int gemm_impl(const void* A, const uint32_t* wq, const uint32_t* sz, const void* bias, const void* residual, void* C,
               void* const* C_peers, int n_peers, int ld_c, int col0, int M, int K, int N, int G, int tok, int split,
-              unsigned flags, void* stream);
+              unsigned flags, void* stream, const qb200_peer_wait* wait = nullptr, const qb200_peer_signal* signal = nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -985,15 +1080,35 @@ int qb200_gemm_w4a16_allgather(const void* A, const uint32_t* wq, const uint32_t
   return gemm_impl(A, wq, sz, bias, residual, C_multicast, C_peers, n_peers, ld_c, col0, M, K, N, G, tok, split, flags, stream);
 }
 
+int qb200_gemm_w4a16_tp(const void* A, const uint32_t* wq, const uint32_t* sz, const void* bias, const void* residual,
+                        void* C_local, void* const* C_peers, void* C_multicast, int n_peers, int ld_c, int col0, int M, int K,
+                        int N, int G, int tok, int split, unsigned flags, const qb200_peer_wait* wait,
+                        const qb200_peer_signal* signal, void* stream) {
+  if (n_peers == 0) {   // local output (row stride N), possibly reading a gathered buffer
+    if (C_local == nullptr) return fail(QB200_EINVAL, "tp gemm: C_local required when n_peers = 0");
+    return gemm_impl(A, wq, sz, bias, residual, C_local, nullptr, 0, N, 0, M, K, N, G, tok, split, flags, stream, wait, signal);
+  }
+  if (n_peers < 1 || n_peers > 8 || C_peers == nullptr) return fail(QB200_EINVAL, "tp gemm: 1..8 peer buffers required");
+  if (ld_c < col0 + N || col0 < 0 || (ld_c % 8) != 0 || (col0 % 8) != 0) return fail(QB200_EINVAL, "tp gemm: bad ld_c / col0");
+  for (int p = 0; p < n_peers; ++p)
+    if (C_peers[p] == nullptr || (reinterpret_cast<uintptr_t>(C_peers[p]) & 15)) return fail(QB200_EINVAL, "tp gemm: peer buffer %d is null or unaligned", p);
+  if (C_multicast != nullptr && (reinterpret_cast<uintptr_t>(C_multicast) & 15)) return fail(QB200_EINVAL, "tp gemm: multicast pointer unaligned");
+  return gemm_impl(A, wq, sz, bias, residual, C_multicast, C_peers, n_peers, ld_c, col0, M, K, N, G, tok, split, flags, stream, wait, signal);
+}
+
 }  // extern "C" (reopened below)
 
 namespace {
 int gemm_impl(const void* A, const uint32_t* wq, const uint32_t* sz, const void* bias, const void* residual, void* C,
               void* const* C_peers, int n_peers, int ld_c, int col0, int M, int K, int N, int G, int tok, int split,
-              unsigned flags, void* stream) {
+              unsigned flags, void* stream, const qb200_peer_wait* wait, const qb200_peer_signal* signal) {
   int rc = qb200_check_shape(M, K, N, G);
   if (rc) return rc;
-  if (M == 0) return QB200_OK;
+  if (M == 0) return (wait || signal) ? fail(QB200_EINVAL, "tensor-parallel GEMM with M = 0") : QB200_OK;
+  rc = check_peer_args(wait, signal);
+  if (rc) return rc;
+  if ((flags & QB200_GEMM_INDEPENDENT) && ((wait != nullptr && wait->epoch != nullptr) || (signal != nullptr && signal->epoch != nullptr)))
+    return fail(QB200_EINVAL, "an independent launch cannot take part in a peer hand-over (it does not wait for its own predecessor)");
   rc = check_device();
   if (rc) return rc;
   if (flags & ~QB200_GEMM_INDEPENDENT) return fail(QB200_EINVAL, "unknown flags 0x%x", flags);
@@ -1035,6 +1150,8 @@ int gemm_impl(const void* A, const uint32_t* wq, const uint32_t* sz, const void*
   args.G = G;
   args.kb_per_split = kbps;
   args.flags = flags;
+  args.wait = make_wait(wait);
+  args.signal = make_signal(signal);
   args.launch_id = static_cast<unsigned>(g_launches.load(std::memory_order_relaxed));
   args.trace = g_trace;
   cudaStream_t st = as_stream(stream);
@@ -1109,16 +1226,22 @@ int qb200_peer_barrier(unsigned* epoch_counter, unsigned* const* flag_arrays, in
   return QB200_OK;
 }
 
-int qb200_rmsnorm(const void* x, const void* weight, void* y, int rows, int H, float eps, void* stream) {
+int qb200_rmsnorm_tp(const void* x, const void* weight, void* y, int rows, int H, float eps, const qb200_peer_wait* wait,
+                     void* stream) {
+  { const int prc = check_peer_args(wait, nullptr); if (prc) return prc; }
   if (rows < 0 || H <= 0 || H % 8 != 0) return fail(QB200_EINVAL, "rmsnorm: H must be a positive multiple of 8");
   if (rows == 0) return QB200_OK;
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(y)) & 15)
     return fail(QB200_EINVAL, "rmsnorm: pointers must be 16-byte aligned");
   const int threads = H >= 4096 ? 512 : H >= 1024 ? 128 : 64;
   QB_CUDA(launch_pdl(rmsnorm_kernel, dim3(rows), dim3(threads), as_stream(stream), reinterpret_cast<const __half*>(x),
-                     reinterpret_cast<const __half*>(weight), reinterpret_cast<__half*>(y), H, eps));
+                     reinterpret_cast<const __half*>(weight), reinterpret_cast<__half*>(y), H, eps, make_wait(wait)));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return QB200_OK;
+}
+
+int qb200_rmsnorm(const void* x, const void* weight, void* y, int rows, int H, float eps, void* stream) {
+  return qb200_rmsnorm_tp(x, weight, y, rows, H, eps, nullptr, stream);
 }
 
 int qb200_rope_kv_update(const void* qkv, const void* cos_table, const void* sin_table, const long long* pos, void* q_out,
@@ -1183,6 +1306,58 @@ int qb200_silu_mul(const void* gate_up, void* act, long long rows, int I, void* 
   const size_t vecs = static_cast<size_t>(rows) * I / 8;
   QB_CUDA(launch_pdl(silu_mul_kernel, dim3(static_cast<unsigned>((vecs + 255) / 256)), dim3(256), as_stream(stream),
                      reinterpret_cast<const __half*>(gate_up), reinterpret_cast<__half*>(act), static_cast<size_t>(rows), I));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return QB200_OK;
+}
+
+
+}  // extern "C"
+namespace {
+int make_peer_dst(PeerDst* d, void* const* peers, void* mc, int n_peers, int ld, int col0, int width) {
+  if (n_peers < 1 || n_peers > 8 || peers == nullptr) return fail(QB200_EINVAL, "1..8 peer buffers required");
+  if (ld < col0 + width || col0 < 0 || (ld % 8) != 0 || (col0 % 8) != 0 || (width % 8) != 0) return fail(QB200_EINVAL, "bad ld / col0 / width");
+  for (int p = 0; p < 8; ++p) {
+    d->peer[p] = p < n_peers ? reinterpret_cast<__half*>(peers[p]) : nullptr;
+    if (p < n_peers && (peers[p] == nullptr || (reinterpret_cast<uintptr_t>(peers[p]) & 15))) return fail(QB200_EINVAL, "peer buffer %d is null or unaligned", p);
+  }
+  if (mc != nullptr && (reinterpret_cast<uintptr_t>(mc) & 15)) return fail(QB200_EINVAL, "multicast pointer unaligned");
+  d->mc = reinterpret_cast<__half*>(mc);
+  d->n = n_peers; d->ld = ld; d->col0 = col0;
+  return QB200_OK;
+}
+}  // namespace
+extern "C" {
+
+int qb200_silu_mul_tp(const void* gate_up, long long rows, int I, void* const* act_peers, void* act_multicast, int n_peers, int ld,
+                      int col0, const qb200_peer_signal* signal, void* stream) {
+  if (rows <= 0 || I <= 0 || I % 8 != 0) return fail(QB200_EINVAL, "silu_mul_tp: rows > 0 and I a positive multiple of 8 required");
+  if (reinterpret_cast<uintptr_t>(gate_up) & 15) return fail(QB200_EINVAL, "silu_mul_tp: pointers must be 16-byte aligned");
+  int rc = check_peer_args(nullptr, signal);
+  if (rc) return rc;
+  PeerDst d;
+  rc = make_peer_dst(&d, act_peers, act_multicast, n_peers, ld, col0, I);
+  if (rc) return rc;
+  const size_t vecs = static_cast<size_t>(rows) * I / 8;
+  const unsigned blocks = static_cast<unsigned>(std::min<size_t>((vecs + 255) / 256, 2 * static_cast<size_t>(device_sm_count())));
+  QB_CUDA(launch_pdl(silu_mul_scatter_kernel, dim3(blocks), dim3(256), as_stream(stream), reinterpret_cast<const __half*>(gate_up),
+                     static_cast<size_t>(rows), I, d, make_signal(signal)));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return QB200_OK;
+}
+
+int qb200_scatter_cols(const void* src, long long rows, int n_local, void* const* dst_peers, void* dst_multicast, int n_peers, int ld,
+                       int col0, const qb200_peer_signal* signal, void* stream) {
+  if (rows <= 0 || n_local <= 0) return fail(QB200_EINVAL, "scatter_cols: rows and n_local must be positive");
+  if (reinterpret_cast<uintptr_t>(src) & 15) return fail(QB200_EINVAL, "scatter_cols: pointers must be 16-byte aligned");
+  int rc = check_peer_args(nullptr, signal);
+  if (rc) return rc;
+  PeerDst d;
+  rc = make_peer_dst(&d, dst_peers, dst_multicast, n_peers, ld, col0, n_local);
+  if (rc) return rc;
+  const size_t vecs = static_cast<size_t>(rows) * n_local / 8;
+  const unsigned blocks = static_cast<unsigned>(std::min<size_t>((vecs + 255) / 256, 2 * static_cast<size_t>(device_sm_count())));
+  QB_CUDA(launch_pdl(scatter_cols_kernel, dim3(blocks), dim3(256), as_stream(stream), reinterpret_cast<const __half*>(src),
+                     static_cast<size_t>(rows), n_local, d, make_signal(signal)));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return QB200_OK;
 }

@@ -425,6 +425,61 @@ struct TileCfg {
 
 constexpr unsigned kFlagIndependent = 1u;   // == QB200_GEMM_INDEPENDENT
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-parallel hand-over without a barrier kernel (include/quick_b200.h: qb200_peer_wait / qb200_peer_signal).
+// A gathered buffer (every rank's kernel stores its column slab into ALL ranks' copies over NVLink) has a local epoch
+// counter and, on every rank, one flag word per producing rank.
+//   producer kernel : plain peer / multicast stores, no fence; ONE thread bumps the local epoch after
+//                     griddepcontrol.wait (every reader of the previous fill has completed by then).
+//   consumer kernel : after ITS griddepcontrol.wait the local producer grid has completed, i.e. this rank's slab has
+//                     been delivered everywhere; one thread announces that (epoch -> slot [rank] of every rank's flag
+//                     array, st.release.sys) and every CTA polls its own flag array until all ranks have announced.
+// The producer needs no system-scope fence and no CTA counter (an earlier version fenced in every CTA and published
+// from the last one: 7-12 us per hand-over on 2 GPUs against 2-3 us for this form), the epoch lives on the device
+// (CUDA-graph replays hand out fresh epochs) and the wait rides in the consumer's prologue — a GEMM keeps prefetching
+// its weights meanwhile — instead of a barrier kernel per gather.
+// ------------------------------------------------------------------------------------------------
+struct PeerWait {
+  const unsigned* epoch;   // local epoch counter of the buffer about to be read (nullptr: nothing to wait for)
+  const unsigned* flags;   // this rank's flag array: flags[p] = last fill rank p has announced as delivered
+  unsigned* peer_flags[8]; // every rank's flag array (peer-mapped); slot [rank] is ours to write
+  int rank, n;
+  int mode;                // QB200_TP_WAITMODE: 2 = device-scope acquire fence after the last poll (default), 0 = system scope
+  unsigned long long timeout_ns;   // 0 = wait for ever
+};
+struct PeerSignal {
+  unsigned* epoch;         // local epoch counter of the buffer this kernel fills (nullptr: not a gathered buffer)
+};
+// Producer side: called by ONE thread of the launch, after griddepcontrol.wait.
+__device__ __forceinline__ void peer_begin_fill(const PeerSignal& s) {
+  if (s.epoch != nullptr) *reinterpret_cast<volatile unsigned*>(s.epoch) = *reinterpret_cast<volatile unsigned*>(s.epoch) + 1u;
+}
+// Consumer side: called by one converged warp per CTA after griddepcontrol.wait; `announce` is true in exactly one
+// warp of the launch.
+__device__ __forceinline__ void peer_wait_warp(const PeerWait& w, bool announce) {
+  if (w.epoch == nullptr) return;
+  const int lane = threadIdx.x & 31;
+  const unsigned e = *reinterpret_cast<const volatile unsigned*>(w.epoch);
+  if (lane < w.n) {
+    if (announce) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(w.peer_flags[lane] + w.rank), "r"(e) : "memory");
+    unsigned long long t0 = 0;
+    unsigned v, polls = 0;
+    do {   // relaxed polls (an acquire per poll would put a system-scope fence into the loop); one fence after the last
+      asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(w.flags + lane) : "memory");
+      if (w.timeout_ns != 0 && (++polls & 1023u) == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > w.timeout_ns) __trap();
+      }
+    } while (static_cast<int>(v - e) < 0);
+    if (w.mode == 0) asm volatile("fence.acq_rel.sys;" ::: "memory");
+    else if (w.mode == 2) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  }
+  __syncwarp();
+  asm volatile("fence.proxy.async;" ::: "memory");   // the gathered rows may be read by TMA (async proxy) next
+}
+
 struct GemmArgs {
   const uint32_t* wq;
   const uint32_t* sz;
@@ -440,6 +495,8 @@ struct GemmArgs {
   int M, K, N, G;
   int kb_per_split;   // k64 blocks per cluster rank
   unsigned flags;     // QB200_GEMM_* (include/quick_b200.h)
+  PeerWait wait;      // tensor parallel: A lives in a gathered buffer — meet its producers before the first load
+  PeerSignal signal;  // tensor parallel: C is a gathered buffer — publish once every CTA has stored its slab
   unsigned launch_id; // host-side launch counter (QB200_TRACE builds: row of the cross-launch timeline)
   long long* trace;   // debug (QB200_TRACE builds only): clock64 stamps of CTA (0,0,0)
 };
@@ -707,6 +764,10 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
     // with it, W(j+DS-D2), reuses the W slot of the same stage j-D2 — whose nibbles were read into registers
     // before its MMAs could even start.  So the single "MMAs of stage j-D2 complete" barrier releases both.
     if (!independent) pdl_wait_prior_grid();   // the activations come from the previous kernel
+    // tensor parallel: the activations may live in a gathered buffer (meet the ranks that fill it), and C may be one
+    const bool first_cta = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+    peer_wait_warp(args.wait, first_cta);
+    if (first_cta && lane == 0) peer_begin_fill(args.signal);
     if (lane == 0) QB_TL(1);
     if (lane == 0) QB_TLALL(1);
     for (int j = 0; j < nst; ++j) {

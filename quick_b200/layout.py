@@ -146,17 +146,56 @@ def quick_cat(tensors, options: str) -> torch.Tensor:
     return torch.cat([t.reshape(rows, -1) for t in tensors], dim=1).reshape(H, -1)
 
 
-def shard_columns(qweight, qzeros, scales, rank: int, world: int):
-    """Column-parallel (N) shard of a packed weight: the inverse slice of quick_cat."""
+def slice_columns(qweight, qzeros, scales, n0: int, n1: int):
+    """Output columns [n0, n1) of a packed weight as a packed weight of its own (n0, n1 multiples of the 128-column
+    tile): the inverse slice of quick_cat."""
     K, N = qweight.shape[0] * 4, qweight.shape[1] * 2
     NG = qzeros.shape[0]
-    if N % world != 0 or (N // world) % 128 != 0:
-        raise ValueError(f"N={N} cannot be split into {world} shards of 128-column tiles")
-    n0, n1 = rank * N // world, (rank + 1) * N // world
+    if not (0 <= n0 < n1 <= N) or n0 % 128 != 0 or n1 % 128 != 0:
+        raise ValueError(f"columns [{n0}, {n1}) of N={N} are not a run of 128-column tiles")
     qw = qweight.reshape(K // 8, N)[:, n0:n1].reshape(K // 4, -1).contiguous()
     sc = scales.reshape(4 * NG, N // 2)[:, n0 // 2:n1 // 2].reshape(NG, -1).contiguous()
     qz = qzeros.reshape(4 * NG, N // 16)[:, n0 // 16:n1 // 16].reshape(NG, -1).contiguous()
     return qw, qz, sc
+
+
+def shard_columns(qweight, qzeros, scales, rank: int, world: int):
+    """Column-parallel (N) shard `rank` of `world` equal shards of a packed weight."""
+    N = qweight.shape[1] * 2
+    if N % world != 0 or (N // world) % 128 != 0:
+        raise ValueError(f"N={N} cannot be split into {world} shards of 128-column tiles")
+    return slice_columns(qweight, qzeros, scales, rank * N // world, (rank + 1) * N // world)
+
+
+def pad_columns(qweight, qzeros, scales, n_new: int):
+    """Append zero-weight output columns up to N = n_new (a multiple of 128): q = z = 0 and s = 0, so the new
+    channels compute exactly 0.  Used to make a width divisible by 128 x the tensor-parallel degree."""
+    K, N = qweight.shape[0] * 4, qweight.shape[1] * 2
+    NG = qzeros.shape[0]
+    if n_new < N or n_new % 128 != 0:
+        raise ValueError(f"cannot pad N={N} to {n_new}")
+    if n_new == N:
+        return qweight, qzeros, scales
+    e = n_new - N
+    zw = torch.zeros((K // 4, e // 2), dtype=qweight.dtype, device=qweight.device)
+    zz = torch.zeros((NG, e // 4), dtype=qzeros.dtype, device=qzeros.device)
+    zs = torch.zeros((NG, 2 * e), dtype=scales.dtype, device=scales.device)
+    return (quick_cat([qweight, zw], "qweight").contiguous(), quick_cat([qzeros, zz], "qzeros").contiguous(),
+            quick_cat([scales, zs], "scales").contiguous())
+
+
+def pad_rows(qweight, qzeros, scales, k_new: int, G: int):
+    """Append zero-weight input channels up to K = k_new (a multiple of the group size): the QUICK layout is k-tile
+    major, so new k-tiles are new rows."""
+    K = qweight.shape[0] * 4
+    if k_new < K or k_new % G != 0 or k_new % 64 != 0:
+        raise ValueError(f"cannot pad K={K} to {k_new}")
+    if k_new == K:
+        return qweight, qzeros, scales
+    e = k_new - K
+    return (torch.cat([qweight, torch.zeros((e // 4, qweight.shape[1]), dtype=qweight.dtype, device=qweight.device)], 0).contiguous(),
+            torch.cat([qzeros, torch.zeros((e // G, qzeros.shape[1]), dtype=qzeros.dtype, device=qzeros.device)], 0).contiguous(),
+            torch.cat([scales, torch.zeros((e // G, scales.shape[1]), dtype=scales.dtype, device=scales.device)], 0).contiguous())
 
 
 def quantize_rtn(W: torch.Tensor, G: int):

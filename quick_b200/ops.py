@@ -157,6 +157,69 @@ def gemm_allgather(x: torch.Tensor, wq: torch.Tensor, sz: torch.Tensor, N: int, 
                                                   len(peer_ptrs), ld_c, col0, M, K, N, G, 0, 0, 1 if independent else 0, _stream_ptr()))
 
 
+def gemm_tp(x: torch.Tensor, wq: torch.Tensor, sz: torch.Tensor, N: int, G: int, bias=None, residual=None, out=None,
+            dst=None, col0: int = 0, wait=None) -> torch.Tensor | None:
+    """qb200_gemm_w4a16_tp.  dst = None: local output [M, N] (returned).  dst = GatheredBuffer: this rank's [M, N] slab
+    goes to column col0 of every rank's copy and the fill is published (returns None; read it through dst.rows(M) in a
+    kernel that is given dst.wait).  wait = the GatheredBuffer x lives in (its rows were filled by all ranks), or None.
+    residual: local [M, N] (dst None) or full-width [M, dst.width] tensor read at the slab's columns."""
+    _require_cuda(x, wq, sz, bias, residual)
+    lib = _lib.load()
+    assert x.dim() == 2 and x.dtype == torch.float16 and x.is_contiguous()
+    M, K = x.shape
+    w = C.byref(wait.wait) if wait is not None else None
+    with torch.cuda.device(x.device):
+        if dst is None:
+            if out is None:
+                out = torch.empty((M, N), dtype=torch.float16, device=x.device)
+            _lib.check(lib.qb200_gemm_w4a16_tp(_ptr(x), _ptr(wq), _ptr(sz), _ptr(bias), _ptr(residual), _ptr(out), None, None, 0, N, 0,
+                                               M, K, N, G, 0, 0, 0, w, None, _stream_ptr()))
+            return out
+        if M > dst.max_rows:
+            raise ValueError(f"M={M} exceeds the gathered buffer ({dst.max_rows} rows)")
+        if residual is not None:
+            assert residual.is_contiguous() and residual.dtype == torch.float16 and tuple(residual.shape) == (M, dst.width)
+        _lib.check(lib.qb200_gemm_w4a16_tp(_ptr(x), _ptr(wq), _ptr(sz), _ptr(bias), _ptr(residual), None, dst.buf_ptrs, dst.multicast_ptr,
+                                           dst.world, dst.width, col0, M, K, N, G, 0, 0, 0, w, C.byref(dst.signal), _stream_ptr()))
+    return None
+
+
+def rmsnorm_tp(x: torch.Tensor, weight: torch.Tensor, eps: float, wait=None) -> torch.Tensor:
+    """qb200_rmsnorm_tp: RMSNorm of rows that live in a gathered buffer (wait = that GatheredBuffer, or None)."""
+    _require_cuda(x, weight)
+    lib = _lib.load()
+    assert x.dtype == torch.float16 and x.is_contiguous()
+    H = x.shape[-1]
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.qb200_rmsnorm_tp(_ptr(x), _ptr(weight), _ptr(y), x.numel() // H, H, float(eps),
+                                        C.byref(wait.wait) if wait is not None else None, _stream_ptr()))
+    return y
+
+
+def silu_mul_tp(gate_up: torch.Tensor, dst, col0: int) -> None:
+    """qb200_silu_mul_tp: silu(g) * u of this rank's [rows, 2 I] slab -> column col0 of every rank's copy of dst, published."""
+    _require_cuda(gate_up)
+    lib = _lib.load()
+    assert gate_up.dtype == torch.float16 and gate_up.is_contiguous()
+    I = gate_up.shape[-1] // 2
+    rows = gate_up.numel() // (2 * I)
+    with torch.cuda.device(gate_up.device):
+        _lib.check(lib.qb200_silu_mul_tp(_ptr(gate_up), rows, I, dst.buf_ptrs, dst.multicast_ptr, dst.world, dst.width, col0,
+                                         C.byref(dst.signal), _stream_ptr()))
+
+
+def scatter_cols(src: torch.Tensor, dst, col0: int) -> None:
+    """qb200_scatter_cols: this rank's [rows, n_local] slab -> column col0 of every rank's copy of dst, published."""
+    _require_cuda(src)
+    lib = _lib.load()
+    assert src.dtype == torch.float16 and src.is_contiguous()
+    n_local = src.shape[-1]
+    with torch.cuda.device(src.device):
+        _lib.check(lib.qb200_scatter_cols(_ptr(src), src.numel() // n_local, n_local, dst.buf_ptrs, dst.multicast_ptr, dst.world,
+                                          dst.width, col0, C.byref(dst.signal), _stream_ptr()))
+
+
 def peer_barrier(epoch: torch.Tensor, flag_ptrs, rank: int) -> None:
     """qb200_peer_barrier on the current stream (epoch: 1-element int32 device tensor owned by the caller)."""
     lib = _lib.load()

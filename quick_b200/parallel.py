@@ -127,3 +127,50 @@ class PeerGatherWorkspace:
         is not separated from this one by another peer barrier (back-to-back calls on one workspace)."""
         from . import ops
         ops.peer_barrier(self.epoch, self.flag_ptrs, self.rank)
+
+
+class GatheredBuffer:
+    """A [max_rows, width] fp16 buffer that exists on every rank (torch symmetric memory: every rank's copy is mapped
+    into every process, plus the NVSwitch multicast mapping when the fabric has one) with the hand-over state of
+    include/quick_b200.h (qb200_peer_signal / qb200_peer_wait): a local epoch counter and a symmetric flag array.
+    Producers (a column-parallel GEMM epilogue, silu_mul_tp, scatter_cols) store this rank's column slab into ALL
+    copies; the first consumer of a fill (GEMM activations, RMSNorm rows) announces this rank's slab and meets the
+    other ranks inside its own prologue — no barrier kernel, no NCCL call, CUDA-graph capturable."""
+
+    def __init__(self, max_rows: int, width: int, group=None, device=None):
+        import ctypes as C
+        import os
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        if not (1 <= self.world <= 8):
+            raise ValueError("peer gather supports 1..8 ranks (one NVLink domain)")
+        device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.max_rows, self.width = max_rows, width
+        self.buf = symm_mem.empty((max_rows, width), dtype=torch.float16, device=device)
+        self.flags = symm_mem.empty(64, dtype=torch.int32, device=device)
+        self.flags.zero_()
+        hb = symm_mem.rendezvous(self.buf, self.group)
+        hf = symm_mem.rendezvous(self.flags, self.group)
+        self.buf_ptrs = (C.c_void_p * self.world)(*[int(p) for p in hb.buffer_ptrs])
+        self.flag_ptrs = (C.c_void_p * self.world)(*[int(p) for p in hf.buffer_ptrs])
+        self.multicast_ptr = None
+        if os.environ.get("QB200_TP_MULTICAST", "1") == "1" and self.world > 1:
+            try:
+                if hb.has_multicast_support:
+                    mp_ = int(hb.multicast_ptr)
+                    self.multicast_ptr = mp_ if mp_ != 0 else None
+            except Exception:
+                self.multicast_ptr = None
+        self.state = torch.zeros(1, dtype=torch.int32, device=device)      # the local epoch counter
+        self.wait = _lib.PeerWait(self.state.data_ptr(), self.flag_ptrs, self.rank, self.world)
+        self.signal = _lib.PeerSignal(self.state.data_ptr())
+        self._handles = (hb, hf)
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)          # every rank's flags are zero before anybody publishes
+
+    def rows(self, M: int) -> torch.Tensor:
+        if M > self.max_rows:
+            raise ValueError(f"M={M} exceeds the gathered buffer ({self.max_rows} rows)")
+        return self.buf[:M]

@@ -58,11 +58,14 @@ def _runner_gather_worker(rank, world, port, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from quick_b200.awq.models.llama_like import _gather_columns, tp_world
-    local = (torch.arange(2 * 3 * 4, dtype=torch.float32).reshape(2, 3, 4) + 100 * rank).half()
-    full = _gather_columns(local)
-    want = torch.cat([(torch.arange(24, dtype=torch.float32).reshape(2, 3, 4) + 100 * r).half() for r in range(world)], dim=-1)
-    ret[rank] = bool(tp_world() == world and full.shape == (2, 3, 4 * world) and torch.equal(full, want))
+    from quick_b200.awq.models.llama_like import PRESETS, TensorParallel, tp_pad_intermediate, tp_world
+    tp = TensorParallel(PRESETS["tiny"], 1, "cpu")          # CPU: the all-gather ("nccl") mode, no peer buffers
+    local = (torch.arange(6 * 4, dtype=torch.float32).reshape(6, 4) + 100 * rank).half()
+    full = tp.all_gather_cols(local)
+    want = torch.cat([(torch.arange(24, dtype=torch.float32).reshape(6, 4) + 100 * r).half() for r in range(world)], dim=-1)
+    ok = tp_world() == world and tp.mode == "nccl" and full.shape == (6, 4 * world) and torch.equal(full, want)
+    ok = ok and tp_pad_intermediate(11008, 8) == 11264 and tp_pad_intermediate(11008, 2) == 11008 and tp.I_pad == 1024
+    ret[rank] = bool(ok)
     dist.destroy_process_group()
 
 
