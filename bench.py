@@ -303,71 +303,105 @@ def plugin_sweep(dev, rank, args):
 
 
 def tp_block(world, rank, dev, args):
-    """N > 1: the north_star's multi-GPU split — ONE column-parallel linear (K = 4096 -> N = 4096 x world, every rank
-    owns 4096 output columns) whose (M, N/R) slabs are gathered on every rank: the GEMM epilogue stores its slab into
-    all ranks' full-width buffers over NVLink (NVSwitch multicast when available) and the ranks meet on device-side
-    flags — no NCCL call on the data path.  Checked bit-for-bit against kernel + NCCL all_gather_into_tensor, then
-    timed per M (CUDA-graph replay, max over ranks) next to that NCCL baseline."""
+    """N > 1: the north_star's multi-GPU split — the K = N = 4096 linear column-parallel over the ranks (every rank owns
+    4096 / world output columns) with its all-gather: the GEMM epilogue stores its slab into every rank's full-width
+    buffer over NVLink (NVSwitch multicast when available) and the NEXT kernel — here the next linear of a chain, whose
+    activations are the gathered rows — meets the ranks inside its own prologue (qb200_gemm_w4a16_tp; no NCCL call and no
+    barrier kernel on the data path).  Checked bit-for-bit against kernel + NCCL all_gather_into_tensor, then timed per M
+    as a dependent chain (CUDA-graph replay, max over ranks) next to the same chain with NCCL all-gathers and next to the
+    one-GPU chain of full 4096 x 4096 linears."""
     import torch.distributed as dist
     from quick_b200 import ops
-    from quick_b200.parallel import PeerGatherWorkspace
-    n_tot = N * world
-    res = {"linear": f"K={K} -> N={n_tot} column-parallel over {world} ranks, gathered output (M, {n_tot}) on every rank"}
+    from quick_b200.parallel import GatheredBuffer
+    n_l = N // world
+    res = {"linear": f"K={K} -> N={N} column-parallel over {world} ranks ({n_l} columns each), gathered (M, {N}) on every rank, "
+                     "consumed by the next linear of the chain"}
     try:
-        sets = [rand_b200_weights(9000 + 1000 * rank + i, dev) for i in range(NSETS)]
-        ws = [PeerGatherWorkspace(max(MS), n_tot), PeerGatherWorkspace(max(MS), n_tot)]   # alternate: consecutive uses of one
-        res["multicast"] = ws[0].multicast_ptr is not None                                # workspace are separated by the other's meeting
+        if n_l % 128 != 0:
+            raise ValueError(f"{N} columns do not split into {world} shards of 128-column tiles")
+        g = torch.Generator(device=dev)
+
+        def shard_weights(seed):
+            g.manual_seed(seed)
+            wq = torch.randint(-2 ** 31, 2 ** 31 - 1, (K * n_l // 8,), device=dev, dtype=torch.int32, generator=g)
+            s = (torch.rand(K // G * n_l, device=dev, generator=g) * 0.01 + 0.002).half().view(torch.int16).to(torch.int32) & 0xFFFF
+            z = torch.randint(0, 16, (K // G * n_l,), device=dev, generator=g, dtype=torch.int32)
+            return wq, (s | ((0x6400 + z) << 16)).to(torch.int32)
+
+        sets = [shard_weights(9000 + 1000 * rank + i) for i in range(NSETS)]
+        full_sets = [rand_b200_weights(9500 + i, dev) for i in range(8)]
+        bufs = [GatheredBuffer(max(MS), N), GatheredBuffer(max(MS), N)]     # alternate: the reuse rule of include/quick_b200.h
+        res["multicast"] = bufs[0].multicast_ptr is not None
+        ones = torch.ones(N, device=dev, dtype=torch.float16)
         ok = True
         for M in (1, 64, 300):
             x = torch.randn(M, K, device=dev, generator=torch.Generator(device=dev).manual_seed(M)).half()
             dist.broadcast(x, 0)
-            fused = ws[0].gemm(x, sets[0][0], sets[0][1], N, G).clone()
-            local = ops.gemm(x, sets[0][0], sets[0][1], N, G)
-            gathered = torch.empty((world * M, N), dtype=torch.float16, device=dev)
+            ops.gemm_tp(x, sets[0][0], sets[0][1], n_l, G, dst=bufs[0], col0=rank * n_l)
+            y = ops.rmsnorm_tp(bufs[0].rows(M), ones, 1e-5, wait=bufs[0])                   # a reader that meets the ranks in-kernel
+            ops.gemm_tp(bufs[0].rows(M), sets[1][0], sets[1][1], n_l, G, dst=bufs[1], col0=rank * n_l)   # a GEMM reading gathered rows
+            y2 = ops.rmsnorm_tp(bufs[1].rows(M), ones, 1e-5, wait=bufs[1])
+            local = ops.gemm(x, sets[0][0], sets[0][1], n_l, G)
+            gathered = torch.empty((world * M, n_l), dtype=torch.float16, device=dev)
             dist.all_gather_into_tensor(gathered, local.contiguous())
-            want = gathered.view(world, M, N).permute(1, 0, 2).reshape(M, n_tot)
-            ok = ok and bool(torch.equal(fused, want))
-            ws[1].gemm(x, sets[0][0], sets[0][1], N, G)          # keeps the alternation invariant
+            want = gathered.view(world, M, n_l).permute(1, 0, 2).reshape(M, N).clone()     # clone: at M = 1 the reshape is a view of `gathered`
+            local2 = ops.gemm(want, sets[1][0], sets[1][1], n_l, G)
+            dist.all_gather_into_tensor(gathered, local2.contiguous())
+            want2 = gathered.view(world, M, n_l).permute(1, 0, 2).reshape(M, N).clone()
+            ok = ok and bool(torch.equal(y, ops.rmsnorm_tp(want, ones, 1e-5))) and bool(torch.equal(y2, ops.rmsnorm_tp(want2, ones, 1e-5)))
         flag = torch.tensor([1 if ok else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         res["parity_fused_vs_nccl_bit_identical"] = bool(flag.item())
-        xs = {M: torch.randn(M, K, device=dev).half() for M in MS}
         rows = []
         for M in MS:
-            def fused_group():
-                for i in range(NSETS):
-                    ws[i & 1].gemm(xs[M], sets[i][0], sets[i][1], N, G)
-            gath = torch.empty((world * M, N), dtype=torch.float16, device=dev)
+            x0 = torch.randn(M, K, device=dev).half()
+            gath = torch.empty((world * M, n_l), dtype=torch.float16, device=dev)
 
-            def nccl_group():
+            def chain_fused():
+                x = x0
                 for i in range(NSETS):
-                    dist.all_gather_into_tensor(gath, ops.gemm(xs[M], sets[i][0], sets[i][1], N, G))
+                    b = bufs[i & 1]
+                    ops.gemm_tp(x, sets[i][0], sets[i][1], n_l, G, dst=b, col0=rank * n_l, wait=(bufs[(i - 1) & 1] if i else None))
+                    x = b.rows(M)
+                ops.rmsnorm_tp(x, ones, 1e-5, wait=bufs[(NSETS - 1) & 1])        # every fill needs a waiting reader
+
+            def chain_nccl():
+                x = x0
+                for i in range(NSETS):
+                    dist.all_gather_into_tensor(gath, ops.gemm(x, sets[i][0], sets[i][1], n_l, G))
+                    x = gath.view(world, M, n_l).permute(1, 0, 2).reshape(M, N).clone()
+
+            def chain_one_gpu():
+                x = x0
+                for i in range(NSETS):
+                    x = ops.gemm(x, full_sets[i % 8][0], full_sets[i % 8][1], N, G)
             row = {"M": M}
-            for label, fn in (("fused", fused_group), ("nccl", nccl_group)):
+            for label, fn in (("fused", chain_fused), ("nccl", chain_nccl), ("one_gpu", chain_one_gpu)):
                 try:
                     fn(); torch.cuda.synchronize()
-                    side = torch.cuda.Stream(); g = torch.cuda.CUDAGraph()
+                    side = torch.cuda.Stream(); gr = torch.cuda.CUDAGraph()
                     with torch.cuda.stream(side):
-                        with torch.cuda.graph(g, stream=side):
+                        with torch.cuda.graph(gr, stream=side):
                             fn()
-                    g.replay(); barrier(world)
+                    gr.replay(); barrier(world)
                     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     reps = 5
                     a.record()
                     for _ in range(reps):
-                        g.replay()
+                        gr.replay()
                     b.record(); torch.cuda.synchronize()
                     us = max_over_ranks(a.elapsed_time(b) / reps / NSETS * 1e3, world)
                     row[f"{label}_us"] = round(us, 3)
-                    row[f"{label}_TOPS"] = round(2.0 * M * K * n_tot / us / 1e6, 2)
-                    del g
+                    row[f"{label}_TOPS"] = round(flops(M) / us / 1e6, 2)
+                    del gr
                 except Exception as e:
                     row[f"{label}_error"] = f"{type(e).__name__}: {e}"[:160]
-            # NVLink roofline of the gather: every rank receives (R-1)/R of the output at the measured peer-copy rate
-            link_us = 2.0 * M * n_tot * (world - 1) / world / 770e9 * 1e6
-            row["nvlink_us_at_770GBs"] = round(link_us, 3)
+            # NVLink floor of the gather alone: every rank receives (R-1)/R of the (M, N) output at the measured peer-copy rate
+            row["nvlink_us_at_770GBs"] = round(2.0 * M * N * (world - 1) / world / 770e9 * 1e6, 3)
             rows.append(row)
         res["sweep"] = rows
+        res["note"] = ("dependent chain of 40 linears, weights rotate (cold); one_gpu = the same chain of full 4096 x 4096 linears on one "
+                       "GPU (ordered launches); the hand-over measured on 2 GPUs is ~3 us per linear (profiles/README.md)")
     except Exception as e:
         res["error"] = f"{type(e).__name__}: {e}"[:300]
     return res

@@ -461,7 +461,10 @@ __device__ __forceinline__ void peer_wait_warp(const PeerWait& w, bool announce)
   const int lane = threadIdx.x & 31;
   const unsigned e = *reinterpret_cast<const volatile unsigned*>(w.epoch);
   if (lane < w.n) {
-    if (announce) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(w.peer_flags[lane] + w.rank), "r"(e) : "memory");
+    if (announce) {
+      if (w.mode & 4) __threadfence_system();     // experiment: explicit system-scope fence before the announcement
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(w.peer_flags[lane] + w.rank), "r"(e) : "memory");
+    }
     unsigned long long t0 = 0;
     unsigned v, polls = 0;
     do {   // relaxed polls (an acquire per poll would put a system-scope fence into the loop); one fence after the last
@@ -473,8 +476,8 @@ __device__ __forceinline__ void peer_wait_warp(const PeerWait& w, bool announce)
         else if (now - t0 > w.timeout_ns) __trap();
       }
     } while (static_cast<int>(v - e) < 0);
-    if (w.mode == 0) asm volatile("fence.acq_rel.sys;" ::: "memory");
-    else if (w.mode == 2) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    if ((w.mode & 3) == 0) asm volatile("fence.acq_rel.sys;" ::: "memory");
+    else if ((w.mode & 3) == 2) asm volatile("fence.acq_rel.gpu;" ::: "memory");
   }
   __syncwarp();
   asm volatile("fence.proxy.async;" ::: "memory");   // the gathered rows may be read by TMA (async proxy) next
