@@ -135,6 +135,21 @@ for M in (1, 64):
             x = ops.rmsnorm_tp(x, nw, 1e-5)
     say(check="hand-over cost", M=M, us_per_pair_tp=time_graph(chain_tp, 16), us_per_pair_one_gpu=time_graph(chain_local, 16),
         us_per_pair_shard_no_handover=time_graph(chain_local_shard, 16))
+# ---- 1c. stress: thousands of hand-overs at the sizes where a late slab would show (tiny kernels), every chain verified ----
+for M in (1, 8):
+    bad = 0
+    for it in range(150):
+        x0 = torch.randn(M, H, device=dev, generator=torch.Generator(device=dev).manual_seed(1000 * M + it)).half()
+        x = x0
+        for i in range(16):       # GEMM fills a gathered buffer, the RMSNorm of its rows is the waiting reader (values stay bounded)
+            ops.gemm_tp(x, *wsets[(i + it) % 8], H // world, G, dst=bufs[i & 1], col0=rank * (H // world))
+            x = ops.rmsnorm_tp(bufs[i & 1].rows(M), nw, 1e-5, wait=bufs[i & 1])
+        got = x.clone()
+        x = x0
+        for i in range(16):
+            x = ops.rmsnorm_tp(gather_cols(ops.gemm(x, *wsets[(i + it) % 8], H // world, G)).contiguous(), nw, 1e-5)
+        bad += int(not torch.equal(got, x))
+    all_ok &= say(check="stress: 150 chains x 16 hand-overs, each verified against the NCCL chain", M=M, mismatching_chains=bad, ok=bad == 0)
 del bufs
 
 if os.environ.get('TP_ONLY_HANDOVER') == '1':
