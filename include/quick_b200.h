@@ -93,6 +93,12 @@ int qb200_gemm_w4a16_cfg(const void* A_fp16, const uint32_t* wq, const uint32_t*
  * of COMPLETION is preserved (a later ordinary launch still sees all results).  The reference has no such
  * mode: its launches serialise on the legacy default stream (gemm_cuda_quick.cu:1491-1513). */
 #define QB200_GEMM_INDEPENDENT 1u
+/* SwiGLU fused into the epilogue (reference modules/fused/mlp.py:52-76: silu(gate_proj(x)) * up_proj(x)): the weight is
+ * the gate|up pair with its OUTPUT CHANNELS INTERLEAVED (channel 2i = gate_i, 2i+1 = up_i; quick_b200.ops.interleave_pairs
+ * prepares it once from the [gate | up] concatenation), C is [M][N/2] (row stride N/2, or ld_c for gathered buffers, col0 in
+ * units of output columns) and C[m][i] = fp16(silu(fp16(gate_i)) ) * fp16(up_i) — the rounding of the unfused GEMM +
+ * qb200_silu_mul pair, so the results are bit-identical to it.  No residual. */
+#define QB200_GEMM_SILU_MUL 2u
 int qb200_gemm_w4a16_ex(const void* A_fp16, const uint32_t* wq, const uint32_t* sz, const void* bias_fp16_or_null,
                         void* C_fp16, int M, int K, int N, int G, int tok, int split, unsigned flags, void* stream);
 
@@ -197,6 +203,9 @@ int qb200_attn_decode(const void* qkv_fp16, const void* cos_table_fp16, const vo
                       void* stream);
 /* act[rows][I] = silu(g) * u for gate_up rows [g | u] of width 2I. */
 int qb200_silu_mul(const void* gate_up_fp16, void* act_fp16, long long rows, int I, void* stream);
+/* Same for rows with interleaved columns (g_0, u_0, g_1, u_1, ...): the output of a QB200_GEMM_SILU_MUL weight run without
+ * the flag (large token tiles, where the fused epilogue's math would idle the tensor pipe). */
+int qb200_silu_mul_interleaved(const void* gate_up_fp16, void* act_fp16, long long rows, int I, void* stream);
 
 /* ---- HOST-buffer handle API (the end-to-end path: H2D, GEMM, D2H inside the call) ---- */
 typedef struct qb200_linear qb200_linear;

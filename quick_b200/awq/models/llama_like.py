@@ -35,6 +35,8 @@ ATTN_DECODE_MAX_BATCH = int(_os0.environ.get("QB200_ATTN_DECODE_MAX_BATCH", "16"
 # One CTA streams the whole cache of its (kv head, sequence): measured at a cache of 192 positions only; long caches
 # want the positions split over several CTAs (flash-decoding), which SDPA does -> keep it for caches beyond this.
 ATTN_DECODE_MAX_CACHE = int(_os0.environ.get("QB200_ATTN_DECODE_MAX_CACHE", "1024"))
+# SiLU(gate)·up inside the gate|up GEMM's epilogue (QB200_GEMM_SILU_MUL) instead of a separate qb200_silu_mul kernel.
+FUSED_SILU = _os0.environ.get("QB200_FUSED_SILU", "1") != "0"
 
 
 @dataclass
@@ -298,16 +300,20 @@ class Block(nn.Module):
         qkv = _linear(self.qkv_proj, self.norm_1(x), ref_mod)
         o = self._attention(qkv, cos, sin, pos_idx, attn_mask, rope, fused_decode)
         x = _linear(self.o_proj, o, ref_mod, residual=x)
-        gu = _linear(self.gate_up_proj, self.norm_2(x), ref_mod)
-        if FUSED_GLUE and gu.is_cuda:
-            act = quick_kernels.silu_mul(gu)
+        if FUSED_GLUE and FUSED_SILU and x.is_cuda and ref_mod is None:
+            # SiLU(gate)·up inside the gate|up GEMM's epilogue (gate / up channels interleaved once, at first use)
+            act = self.gate_up_proj.enable_silu_mul().forward_silu_mul(self.norm_2(x))
         else:
-            g, u = gu.split(cfg.intermediate_size, dim=-1)
-            act = F.silu(g) * u
+            gu = _linear(self.gate_up_proj, self.norm_2(x), ref_mod)
+            if FUSED_GLUE and gu.is_cuda:
+                act = quick_kernels.silu_mul(gu)
+            else:
+                g, u = gu.split(cfg.intermediate_size, dim=-1)
+                act = F.silu(g) * u
         return _linear(self.down_proj, act, ref_mod, residual=x), None
 
     def forward_tp(self, x, x_src, cos, sin, pos_idx, attn_mask, rope):
-        """One decoder layer on this rank's shards.  Peer mode: 9 kernels, none of them a barrier — the two column-parallel
+        """One decoder layer on this rank's shards.  Peer mode: 8 kernels, none of them a barrier — the two column-parallel
         GEMMs store their slabs into every rank's hidden-state buffer, the attention output and the MLP activation are
         scattered the same way, and each consumer (RMSNorm rows, GEMM activations) meets the producers in its own
         prologue.  NCCL mode: the same dataflow with four all-gathers."""
@@ -330,9 +336,10 @@ class Block(nn.Module):
                         residual=x2d, dst=tp.hid_b, col0=col_h, wait=tp.attn)
             x2 = tp.hid_b.rows(M)
             xn2 = ops.rmsnorm_tp(x2, self.norm_2.weight, self.norm_2.eps, wait=tp.hid_b)
-            wq, sz = self.gate_up_proj._prepacked()
-            gu = ops.gemm_tp(xn2, wq, sz, self.gate_up_proj.out_features, self.gate_up_proj.group_size, bias=self.gate_up_proj.bias)
-            ops.silu_mul_tp(gu, tp.act, tp.rank * self.I_l)
+            gup = self.gate_up_proj.enable_silu_mul()      # [gate_r | up_r] -> interleaved channels, once
+            wq, sz = gup._b200
+            # SiLU(gate)·up in the epilogue, this rank's slice of the activation stored straight into every rank's buffer
+            ops.gemm_tp(xn2, wq, sz, gup.out_features, gup.group_size, bias=gup._pair_bias, dst=tp.act, col0=tp.rank * self.I_l, silu_mul=True)
             wq, sz = self.down_proj._prepacked()
             ops.gemm_tp(tp.act.rows(M), wq, sz, self.down_proj.out_features, self.down_proj.group_size, bias=self.down_proj.bias,
                         residual=x2, dst=tp.hid_a, col0=col_h, wait=tp.act)

@@ -21,6 +21,8 @@ from ....layout import pack_quick
 
 
 class WQLinear_QUICK(nn.Module):
+    SILU_FUSED_MAX_ROWS = 256     # forward_silu_mul: rows up to which SiLU·up runs inside the GEMM epilogue
+
     def __init__(self, w_bit, group_size, in_features, out_features, bias, dev, k_split_1=2, k_split_2=8):
         super().__init__()
         if w_bit not in [4]:
@@ -45,6 +47,7 @@ class WQLinear_QUICK(nn.Module):
         self._b200_src = None   # the packed tensors it was derived from (strong references: their storage cannot be
                                 # freed and re-used at the same address while the copy is cached) and their versions
         self._b200_frozen = False
+        self.gated_pairs = False    # True: the B200 copy has interleaved gate / up channels (enable_silu_mul)
 
     @classmethod
     def from_linear(cls, linear, w_bit, group_size, init_only=False, scales=None, zeros=None, k_split_1=2, k_split_2=8):
@@ -103,6 +106,35 @@ class WQLinear_QUICK(nn.Module):
             self._b200, self._b200_src = (wq, sz), (src, ver)
         return self._b200
 
+    def enable_silu_mul(self):
+        """This module is a fused gate|up projection ([gate | up] along N): switch its B200 copy to interleaved output
+        channels so that ``forward_silu_mul`` computes silu(gate(x)) * up(x) in the GEMM epilogue (QB200_GEMM_SILU_MUL,
+        the reference's QuantFusedMLP.our_llama_mlp, modules/fused/mlp.py:52-76, in one launch).  The plain ``forward``
+        is no longer available on this module afterwards."""
+        if getattr(self, "gated_pairs", False):
+            return self
+        from .... import ops
+        wq, sz = self._prepacked()
+        wq, sz, bias = ops.interleave_pairs(wq, sz, self.in_features, self.out_features, self.group_size, self.bias)
+        self._b200, self._pair_bias, self.gated_pairs, self._b200_frozen = (wq, sz), bias, True, True
+        return self
+
+    @torch.no_grad()
+    def forward_silu_mul(self, x):
+        """silu(gate(x)) * up(x) -> (..., out_features / 2), bit-identical to forward + qb200_silu_mul."""
+        assert getattr(self, "gated_pairs", False), "call enable_silu_mul() first"
+        wq, sz = self._b200
+        x2d = x.reshape(-1, x.shape[-1])
+        if x2d.shape[0] > self.SILU_FUSED_MAX_ROWS:
+            # large token tiles: the epilogue's SiLU math would idle the tensor pipe (prefill -4 % measured on 7B shapes);
+            # run the GEMM plain (its output columns are the interleaved pairs) and one elementwise kernel behind it
+            from .... import ops
+            out = ops.silu_mul_interleaved(quick_kernels.gemm_forward_b200(x2d, wq, sz, self._pair_bias, self.out_features, self.group_size,
+                                                                            False, None, False))
+        else:
+            out = quick_kernels.gemm_forward_b200(x2d, wq, sz, self._pair_bias, self.out_features, self.group_size, False, None, True)
+        return out.reshape(x.shape[:-1] + (self.out_features // 2,))
+
     def release_quick_buffers(self, drop=False):
         """Inference-only deployments: keep the B200 copy on the GPU and move the QUICK-layout buffers (qweight /
         qzeros / scales — the checkpoint format, no longer read by the kernel) to host memory, halving the weight
@@ -121,7 +153,7 @@ class WQLinear_QUICK(nn.Module):
         return self
 
     def restore_quick_buffers(self):
-        if self._b200_frozen:
+        if self._b200_frozen and getattr(self, "_b200_device", None) is not None:
             dev = self._b200_device
             for name in ("qweight", "qzeros", "scales"):
                 setattr(self, name, getattr(self, name).to(dev))
@@ -133,10 +165,13 @@ class WQLinear_QUICK(nn.Module):
         if self._b200_frozen:           # new packed tensors arrived: the frozen copy is stale
             self.restore_quick_buffers()
         self._b200 = self._b200_src = None
+        self._b200_frozen = self.gated_pairs = False
 
     @torch.no_grad()
     def forward(self, x, residual=None):
         """residual (same shape as the output): returns residual + linear(x), the add fused into the GEMM epilogue."""
+        if getattr(self, "gated_pairs", False):
+            raise RuntimeError("this gate|up module has interleaved output channels (enable_silu_mul): use forward_silu_mul")
         out_shape = x.shape[:-1] + (self.out_features,)
         wq, sz = self._prepacked()
         res2d = None if residual is None else residual.reshape(-1, self.out_features)

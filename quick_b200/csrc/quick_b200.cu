@@ -560,6 +560,28 @@ __global__ void silu_mul_kernel(const __half* __restrict__ gu, __half* __restric
   *reinterpret_cast<uint4*>(act + idx) = o;
 }
 
+// Same for a gate|up GEMM output whose columns are interleaved (g_0, u_0, g_1, u_1, ...): what a QB200_GEMM_SILU_MUL weight
+// produces when it is run WITHOUT the fused epilogue (large token tiles, where the epilogue math would idle the tensor pipe).
+__global__ void silu_mul_pairs_kernel(const __half* __restrict__ gu, __half* __restrict__ act, size_t total) {
+  qb200::pdl_launch_dependents();
+  qb200::pdl_wait_prior_grid();
+  const size_t idx = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;   // 8 outputs = 16 inputs
+  if (idx >= total) return;
+  const uint4 a = *reinterpret_cast<const uint4*>(gu + 2 * idx);
+  const uint4 b = *reinterpret_cast<const uint4*>(gu + 2 * idx + 8);
+  const __half2* ah = reinterpret_cast<const __half2*>(&a);
+  const __half2* bh = reinterpret_cast<const __half2*>(&b);
+  uint4 o;
+  __half* oh = reinterpret_cast<__half*>(&o);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const __half2 p = j < 4 ? ah[j] : bh[j - 4];
+    const float g = __low2float(p);
+    oh[j] = __hmul(__float2half_rn(g / (1.f + expf(-g))), __high2half(p));
+  }
+  *reinterpret_cast<uint4*>(act + idx) = o;
+}
+
 // Destination of a column slab that every rank needs (tensor parallel): the [rows][ld] buffers of all ranks at column
 // col0 — ONE multimem.st per 16-byte chunk through the NVSwitch multicast mapping when there is one, else a loop of
 // peer stores.
@@ -1089,7 +1111,8 @@ int qb200_gemm_w4a16_tp(const void* A, const uint32_t* wq, const uint32_t* sz, c
     return gemm_impl(A, wq, sz, bias, residual, C_local, nullptr, 0, N, 0, M, K, N, G, tok, split, flags, stream, wait, signal);
   }
   if (n_peers < 1 || n_peers > 8 || C_peers == nullptr) return fail(QB200_EINVAL, "tp gemm: 1..8 peer buffers required");
-  if (ld_c < col0 + N || col0 < 0 || (ld_c % 8) != 0 || (col0 % 8) != 0) return fail(QB200_EINVAL, "tp gemm: bad ld_c / col0");
+  const int n_out = (flags & QB200_GEMM_SILU_MUL) ? N / 2 : N;
+  if (ld_c < col0 + n_out || col0 < 0 || (ld_c % 8) != 0 || (col0 % 8) != 0) return fail(QB200_EINVAL, "tp gemm: bad ld_c / col0");
   for (int p = 0; p < n_peers; ++p)
     if (C_peers[p] == nullptr || (reinterpret_cast<uintptr_t>(C_peers[p]) & 15)) return fail(QB200_EINVAL, "tp gemm: peer buffer %d is null or unaligned", p);
   if (C_multicast != nullptr && (reinterpret_cast<uintptr_t>(C_multicast) & 15)) return fail(QB200_EINVAL, "tp gemm: multicast pointer unaligned");
@@ -1111,7 +1134,12 @@ int gemm_impl(const void* A, const uint32_t* wq, const uint32_t* sz, const void*
     return fail(QB200_EINVAL, "an independent launch cannot take part in a peer hand-over (it does not wait for its own predecessor)");
   rc = check_device();
   if (rc) return rc;
-  if (flags & ~QB200_GEMM_INDEPENDENT) return fail(QB200_EINVAL, "unknown flags 0x%x", flags);
+  if (flags & ~(QB200_GEMM_INDEPENDENT | QB200_GEMM_SILU_MUL)) return fail(QB200_EINVAL, "unknown flags 0x%x", flags);
+  if (flags & QB200_GEMM_SILU_MUL) {
+    if (residual != nullptr) return fail(QB200_EINVAL, "QB200_GEMM_SILU_MUL takes no residual");
+    if (n_peers == 0) ld_c = N / 2;          // local output [M][N/2]
+    if ((reinterpret_cast<uintptr_t>(C) & 15) && n_peers == 0) return fail(QB200_EINVAL, "C must be 16-byte aligned");
+  }
   if (tok == 0 || split == 0) {
     int t, s;
     plan(M, K, N, 0, flags, &t, &s);
@@ -1310,6 +1338,17 @@ int qb200_silu_mul(const void* gate_up, void* act, long long rows, int I, void* 
   return QB200_OK;
 }
 
+
+int qb200_silu_mul_interleaved(const void* gate_up, void* act, long long rows, int I, void* stream) {
+  if (rows < 0 || I <= 0 || I % 8 != 0) return fail(QB200_EINVAL, "silu_mul_interleaved: I must be a positive multiple of 8");
+  if (rows == 0) return QB200_OK;
+  if ((reinterpret_cast<uintptr_t>(gate_up) | reinterpret_cast<uintptr_t>(act)) & 15) return fail(QB200_EINVAL, "silu_mul_interleaved: pointers must be 16-byte aligned");
+  const size_t total = static_cast<size_t>(rows) * I;
+  QB_CUDA(launch_pdl(silu_mul_pairs_kernel, dim3(static_cast<unsigned>((total / 8 + 255) / 256)), dim3(256), as_stream(stream),
+                     reinterpret_cast<const __half*>(gate_up), reinterpret_cast<__half*>(act), total));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return QB200_OK;
+}
 
 }  // extern "C"
 namespace {

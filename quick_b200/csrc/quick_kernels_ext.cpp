@@ -144,7 +144,7 @@ std::vector<torch::Tensor> prepack_quick(torch::Tensor kernel, torch::Tensor sca
 // are not produced by a kernel that may still be running (e.g. sibling projections of one activation tensor).
 torch::Tensor gemm_forward_b200(torch::Tensor in_feats, torch::Tensor wq, torch::Tensor sz,
                                 c10::optional<torch::Tensor> bias, int64_t N, int64_t G, bool independent,
-                                c10::optional<torch::Tensor> residual) {
+                                c10::optional<torch::Tensor> residual, bool silu_mul) {
   TORCH_CHECK(in_feats.dim() == 2 && in_feats.is_cuda(), "in_feats must be a 2-D CUDA tensor (there is no CPU path)");
   const at::cuda::OptionalCUDAGuard device_guard(device_of(in_feats));
   torch::Tensor x = in_feats.contiguous();
@@ -167,12 +167,14 @@ torch::Tensor gemm_forward_b200(torch::Tensor in_feats, torch::Tensor wq, torch:
     TORCH_CHECK(r.numel() == static_cast<int64_t>(M) * N && r.scalar_type() == torch::kHalf && r.is_cuda(), "residual must be CUDA fp16 [M, N]");
     res_ptr = r.data_ptr<at::Half>();
   }
-  torch::Tensor out = torch::empty({M, N}, x.options());
+  // silu_mul: the weight is a gate|up pair with interleaved output channels; out = silu(gate) * up, [M, N/2]
+  TORCH_CHECK(!(silu_mul && res_ptr != nullptr), "silu_mul takes no residual");
+  torch::Tensor out = torch::empty({M, silu_mul ? N / 2 : N}, x.options());
   auto stream = at::cuda::getCurrentCUDAStream();
   check(qb200_gemm_w4a16_fused(x.data_ptr<at::Half>(), reinterpret_cast<const uint32_t*>(wq.data_ptr<int>()),
                                reinterpret_cast<const uint32_t*>(sz.data_ptr<int>()), bias_ptr, res_ptr, out.data_ptr<at::Half>(), M, K,
                                static_cast<int>(N), static_cast<int>(G), /*tok*/ 0, /*split*/ 0,
-                               independent ? QB200_GEMM_INDEPENDENT : 0u, stream.stream()));
+                               (independent ? QB200_GEMM_INDEPENDENT : 0u) | (silu_mul ? QB200_GEMM_SILU_MUL : 0u), stream.stream()));
   return out;
 }
 
@@ -257,7 +259,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("prepack_quick", &prepack_quick, "QUICK layout -> B200 layout (wq, sz)");
   m.def("gemm_forward_b200", &gemm_forward_b200, "W4A16 GEMM on B200-layout weights (bias fused)", pybind11::arg("in_feats"),
         pybind11::arg("wq"), pybind11::arg("sz"), pybind11::arg("bias"), pybind11::arg("N"), pybind11::arg("G"),
-        pybind11::arg("independent") = false, pybind11::arg("residual") = pybind11::none());
+        pybind11::arg("independent") = false, pybind11::arg("residual") = pybind11::none(), pybind11::arg("silu_mul") = false);
   m.def("cache_stats", [] {
     std::lock_guard<std::mutex> lock(g_mu);
     return std::vector<int64_t>{static_cast<int64_t>(g_cache.size()), static_cast<int64_t>(g_hits), static_cast<int64_t>(g_misses)};

@@ -424,6 +424,20 @@ struct TileCfg {
 };
 
 constexpr unsigned kFlagIndependent = 1u;   // == QB200_GEMM_INDEPENDENT
+constexpr unsigned kFlagSiluMul = 2u;       // == QB200_GEMM_SILU_MUL
+
+// SwiGLU fused into the epilogue (reference modules/fused/mlp.py:52-76: gate and up projections, silu(gate) * up).
+// The weight's output channels are interleaved gate_0, up_0, gate_1, up_1, ... (prepared once at load), so in the
+// swap-A/B accumulator — one lane per channel — a gate channel and its up channel are NEIGHBOURING LANES of one warp:
+// one shuffle, no second pass over HBM.  Rounding is that of the unfused pair of kernels (fp16 GEMM outputs, SiLU in
+// fp32 rounded to fp16, fp16 product), so results are bit-identical to GEMM + qb200_silu_mul.  Valid in even lanes.
+__device__ __forceinline__ __half silu_mul_pair(float acc, int lane) {
+  const __half h = __float2half_rn(acc);
+  const __half other = __ushort_as_half(static_cast<unsigned short>(__shfl_xor_sync(0xffffffffu, static_cast<unsigned>(__half_as_ushort(h)), 1)));
+  const float g = __half2float(h);
+  (void)lane;
+  return __hmul(__float2half_rn(g / (1.f + expf(-g))), other);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Tensor-parallel hand-over without a barrier kernel (include/quick_b200.h: qb200_peer_wait / qb200_peer_signal).
@@ -642,6 +656,38 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Epilogue staging: this CTA's [rows tokens][128 channels] fp16 tile in shared memory (or [rows][64] products when
+// SiLU·up is fused), then 16-byte coalesced stores to C / every peer / the multicast mapping.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_out(uint32_t smem_out, int row, int ch, int lane, float acc, bool silu_mul) {
+  if (silu_mul) {
+    const __half h = silu_mul_pair(acc, lane);
+    if ((lane & 1) == 0) sts_u16(smem_out + static_cast<uint32_t>((row * (kChan / 2) + (ch >> 1)) * 2), __half_as_ushort(h));
+  } else {
+    sts_u16(smem_out + static_cast<uint32_t>((row * kChan + ch) * 2), __half_as_ushort(__float2half_rn(acc)));
+  }
+}
+// called by the 256 epilogue threads after the tile has been staged (and a barrier)
+__device__ __forceinline__ void store_tile(const GemmArgs& args, uint32_t smem_out, int rows, int m_base, int n0, bool silu_mul) {
+  const int tid = threadIdx.x;             // 0..255
+  const int cpr = silu_mul ? 8 : 16;       // 16-byte chunks per staged row (128 B of products, or 256 B)
+  const int chunk = tid % cpr;
+  const int nbase = silu_mul ? (n0 >> 1) : n0;
+#pragma unroll 1
+  for (int row = tid / cpr; row < rows; row += (kEpilogueWarps * 32) / cpr) {
+    const int m = m_base + row;
+    if (m < args.M) {
+      uint4 v = lds128(smem_out + static_cast<uint32_t>((row * cpr + chunk) * 16));
+      const size_t off = static_cast<size_t>(m) * args.ldc + args.col0 + nbase + chunk * 8;
+      if (args.residual != nullptr) v = hadd2x4(*reinterpret_cast<const uint4*>(args.residual + off), v);
+      if (args.n_peers == 0) *reinterpret_cast<uint4*>(args.C + off) = v;
+      else if (args.mcC != nullptr) multimem_st_v4(args.mcC + off, v);
+      else for (int p = 0; p < args.n_peers; ++p) *reinterpret_cast<uint4*>(args.peerC[p] + off) = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------
 template <int TOK, int SPLIT, int VAR = 0>
@@ -699,6 +745,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
   // the previous grid until the very end (one griddepcontrol.wait before exit keeps completion transitive:
   // "this kernel finished" still implies "everything launched before it finished").
   const bool independent = (args.flags & kFlagIndependent) != 0;
+  const bool silu_mul = (args.flags & kFlagSiluMul) != 0;    // SwiGLU fused into the epilogue (gate / up channels interleaved)
   const int nt = blockIdx.x;
   const int mt = blockIdx.y;
   const int rank = SPLIT > 1 ? static_cast<int>(cluster_ctarank()) : 0;
@@ -1020,6 +1067,21 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
           for (int i = 0; i < PIECE; ++i) {
             const int m = m_base + j0 + i;
             if (m < args.M) {
+              if (silu_mul) {
+                // lanes (2i, 2i+1) = (gate_i, up_i): even lanes hold the product, output column (n0 + ch) / 2
+                const __half h = silu_mul_pair(acc[i], lane);
+                const size_t off = static_cast<size_t>(m) * args.ldc + args.col0 + ((n0 + ch) >> 1);
+                if (args.n_peers == 0) {
+                  if ((lane & 1) == 0) args.C[off] = h;
+                } else if (args.mcC != nullptr) {
+                  const uint32_t mine = __half_as_ushort(h);
+                  const uint32_t next = __shfl_down_sync(0xffffffffu, mine, 2);
+                  if ((lane & 3) == 0) multimem_st_b32(args.mcC + off, mine | (next << 16));
+                } else if ((lane & 1) == 0) {
+                  for (int p = 0; p < args.n_peers; ++p) args.peerC[p][off] = h;
+                }
+                continue;
+              }
               const size_t off = static_cast<size_t>(m) * args.ldc + args.col0 + n0 + ch;
               __half h = __float2half_rn(acc[i]);
               if (args.residual != nullptr) h = __hadd(args.residual[off], h);
@@ -1038,25 +1100,12 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
         } else {
 #pragma unroll
           for (int i = 0; i < PIECE; ++i)
-            sts_u16(smem_out + static_cast<uint32_t>(((j0 + i) * kChan + ch) * 2), __half_as_ushort(__float2half_rn(acc[i])));
+            stage_out(smem_out, j0 + i, ch, lane, acc[i], silu_mul);
         }
       }
       if constexpr (!kDirectStore) {
         named_bar_sync(1, kEpilogueWarps * 32);
-        const int tid = threadIdx.x;             // 0..255
-        const int chunk = tid & 15;
-#pragma unroll 1
-        for (int row = tid >> 4; row < SLICE; row += (kEpilogueWarps * 32) / 16) {
-          const int m = m_base + row;
-          if (m < args.M) {
-            uint4 v = lds128(smem_out + static_cast<uint32_t>(row * kChan * 2 + chunk * 16));
-            const size_t off = static_cast<size_t>(m) * args.ldc + args.col0 + n0 + chunk * 8;
-            if (args.residual != nullptr) v = hadd2x4(*reinterpret_cast<const uint4*>(args.residual + off), v);
-            if (args.n_peers == 0) *reinterpret_cast<uint4*>(args.C + off) = v;
-            else if (args.mcC != nullptr) multimem_st_v4(args.mcC + off, v);
-            else for (int p = 0; p < args.n_peers; ++p) *reinterpret_cast<uint4*>(args.peerC[p] + off) = v;
-          }
-        }
+        store_tile(args, smem_out, SLICE, m_base, n0, silu_mul);
       }
       if (threadIdx.x == 0) QB_TRACE(3, 0, 3);
     }
@@ -1139,7 +1188,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
         }
 #pragma unroll
         for (int i = 0; i < PIECE; ++i)
-          sts_u16(smem_out + static_cast<uint32_t>(((j0 + i) * kChan + ch) * 2), __half_as_ushort(__float2half_rn(acc[i])));
+          stage_out(smem_out, j0 + i, ch, lane, acc[i], silu_mul);
       }
       if (threadIdx.x == 0) QB_TRACE(3, 2, 3);
       named_bar_sync(1, kEpilogueWarps * 32);
@@ -1147,20 +1196,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
       // lane's wait (its X loads fed the MMAs whose completion barrier these warps have observed), i.e. after the
       // previous grid has completed and flushed; in independent mode the caller has declared C unrelated.
       // coalesced 16-byte stores: 16 threads cover one 256-byte token row of the tile
-      const int tid = threadIdx.x;             // 0..255
-      const int chunk = tid & 15;
-#pragma unroll 1
-      for (int row = tid >> 4; row < SLICE; row += (kEpilogueWarps * 32) / 16) {
-        const int m = m_base + row;
-        if (m < args.M) {
-          uint4 v = lds128(smem_out + static_cast<uint32_t>(row * kChan * 2 + chunk * 16));
-          const size_t off = static_cast<size_t>(m) * args.ldc + args.col0 + n0 + chunk * 8;
-          if (args.residual != nullptr) v = hadd2x4(*reinterpret_cast<const uint4*>(args.residual + off), v);
-          if (args.n_peers == 0) *reinterpret_cast<uint4*>(args.C + off) = v;
-          else if (args.mcC != nullptr) multimem_st_v4(args.mcC + off, v);
-          else for (int p = 0; p < args.n_peers; ++p) *reinterpret_cast<uint4*>(args.peerC[p] + off) = v;
-        }
-      }
+      store_tile(args, smem_out, SLICE, m_base, n0, silu_mul);
       if (threadIdx.x == 0) QB_TRACE(3, 0, 3);
     }
     if constexpr (SPLIT > 1) cluster_wait();

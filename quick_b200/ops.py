@@ -157,8 +157,23 @@ def gemm_allgather(x: torch.Tensor, wq: torch.Tensor, sz: torch.Tensor, N: int, 
                                                   len(peer_ptrs), ld_c, col0, M, K, N, G, 0, 0, 1 if independent else 0, _stream_ptr()))
 
 
+def interleave_pairs(wq: torch.Tensor, sz: torch.Tensor, K: int, N: int, G: int, bias: torch.Tensor | None = None):
+    """B200-layout weight of a [first | second] concatenation (gate | up) -> the same weight with its output channels
+    interleaved (2i = first_i, 2i+1 = second_i): what QB200_GEMM_SILU_MUL expects.  Done once at load; N/2 must be a
+    multiple of 64 (every 128-channel tile then holds 64 complete pairs)."""
+    if N % 256 != 0:
+        raise ValueError("interleave_pairs: N/2 must be a multiple of the 128-column tile")
+    NT, KB, NG, I = N // 128, K // 64, K // G, N // 2
+    idx = torch.arange(N, device=wq.device)
+    src = (idx & 1) * I + (idx >> 1)                                     # new channel n' <- old column src[n']
+    w = wq.view(NT, KB, 2, 128, 4).permute(0, 3, 1, 2, 4).reshape(N, KB * 8)[src]
+    w = w.reshape(NT, 128, KB, 2, 4).permute(0, 2, 3, 1, 4).contiguous().view(-1)
+    z = sz.view(NT, NG, 128).permute(0, 2, 1).reshape(N, NG)[src].reshape(NT, 128, NG).permute(0, 2, 1).contiguous().view(-1)
+    return w, z, (None if bias is None else bias[src].contiguous())
+
+
 def gemm_tp(x: torch.Tensor, wq: torch.Tensor, sz: torch.Tensor, N: int, G: int, bias=None, residual=None, out=None,
-            dst=None, col0: int = 0, wait=None) -> torch.Tensor | None:
+            dst=None, col0: int = 0, wait=None, silu_mul: bool = False) -> torch.Tensor | None:
     """qb200_gemm_w4a16_tp.  dst = None: local output [M, N] (returned).  dst = GatheredBuffer: this rank's [M, N] slab
     goes to column col0 of every rank's copy and the fill is published (returns None; read it through dst.rows(M) in a
     kernel that is given dst.wait).  wait = the GatheredBuffer x lives in (its rows were filled by all ranks), or None.
@@ -168,19 +183,20 @@ def gemm_tp(x: torch.Tensor, wq: torch.Tensor, sz: torch.Tensor, N: int, G: int,
     assert x.dim() == 2 and x.dtype == torch.float16 and x.is_contiguous()
     M, K = x.shape
     w = C.byref(wait.wait) if wait is not None else None
+    fl = 2 if silu_mul else 0                  # QB200_GEMM_SILU_MUL: interleaved gate|up weight, output [M, N/2]
     with torch.cuda.device(x.device):
         if dst is None:
             if out is None:
-                out = torch.empty((M, N), dtype=torch.float16, device=x.device)
+                out = torch.empty((M, N // 2 if silu_mul else N), dtype=torch.float16, device=x.device)
             _lib.check(lib.qb200_gemm_w4a16_tp(_ptr(x), _ptr(wq), _ptr(sz), _ptr(bias), _ptr(residual), _ptr(out), None, None, 0, N, 0,
-                                               M, K, N, G, 0, 0, 0, w, None, _stream_ptr()))
+                                               M, K, N, G, 0, 0, fl, w, None, _stream_ptr()))
             return out
         if M > dst.max_rows:
             raise ValueError(f"M={M} exceeds the gathered buffer ({dst.max_rows} rows)")
         if residual is not None:
             assert residual.is_contiguous() and residual.dtype == torch.float16 and tuple(residual.shape) == (M, dst.width)
         _lib.check(lib.qb200_gemm_w4a16_tp(_ptr(x), _ptr(wq), _ptr(sz), _ptr(bias), _ptr(residual), None, dst.buf_ptrs, dst.multicast_ptr,
-                                           dst.world, dst.width, col0, M, K, N, G, 0, 0, 0, w, C.byref(dst.signal), _stream_ptr()))
+                                           dst.world, dst.width, col0, M, K, N, G, 0, 0, fl, w, C.byref(dst.signal), _stream_ptr()))
     return None
 
 
@@ -195,6 +211,18 @@ def rmsnorm_tp(x: torch.Tensor, weight: torch.Tensor, eps: float, wait=None) -> 
         _lib.check(lib.qb200_rmsnorm_tp(_ptr(x), _ptr(weight), _ptr(y), x.numel() // H, H, float(eps),
                                         C.byref(wait.wait) if wait is not None else None, _stream_ptr()))
     return y
+
+
+def silu_mul_interleaved(gate_up: torch.Tensor) -> torch.Tensor:
+    """qb200_silu_mul_interleaved: rows (g_0, u_0, g_1, u_1, ...) -> silu(g) * u, [..., I]."""
+    _require_cuda(gate_up)
+    lib = _lib.load()
+    assert gate_up.dtype == torch.float16 and gate_up.is_contiguous()
+    I = gate_up.shape[-1] // 2
+    act = torch.empty(gate_up.shape[:-1] + (I,), dtype=torch.float16, device=gate_up.device)
+    with torch.cuda.device(gate_up.device):
+        _lib.check(lib.qb200_silu_mul_interleaved(_ptr(gate_up), _ptr(act), gate_up.numel() // (2 * I), I, _stream_ptr()))
+    return act
 
 
 def silu_mul_tp(gate_up: torch.Tensor, dst, col0: int) -> None:

@@ -569,3 +569,37 @@ def test_attn_decode_matches_rope_cache_update_plus_sdpa(ops, nh, nkv, hd):
     with pytest.raises(Exception):
         quick_kernels.attn_decode(torch.zeros(1, 2, (nh + 2 * nkv) * hd, device="cuda", dtype=torch.float16), cos, sin,
                                   torch.tensor([0], device="cuda"), ck_new[:1], cv_new[:1], nh, nkv)
+
+
+@pytest.mark.parametrize("K,I,G", [(512, 256, 128), (4096, 11008, 128), (1024, 1408 - 128, 64)], ids=["small", "llama7b_gate_up", "g64"])
+def test_silu_mul_fused_into_the_gate_up_epilogue_is_bit_identical(ops, K, I, G):
+    """SURVEY §8 f4 / reference modules/fused/mlp.py:52-76: silu(gate(x)) * up(x) computed in the epilogue of the fused gate|up
+    GEMM (QB200_GEMM_SILU_MUL, interleaved output channels) == the unfused GEMM followed by qb200_silu_mul, bit for bit, for
+    every tile configuration the planner picks and for forced ones; also through WQLinear_QUICK.forward_silu_mul."""
+    import quick_kernels
+    from quick_b200.awq.modules.linear.quick import WQLinear_QUICK
+    N = 2 * I
+    q, z, s, qw, qz, sc, W16 = make_gpu_case(ops, K, N, G, seed=I)
+    wq, sz, *_ = ops.prepack(qw, qz, sc)
+    bias = (torch.randn(N, device="cuda") * 0.1).half()
+    wq_i, sz_i, bias_i = ops.interleave_pairs(wq, sz, K, N, G, bias)
+    # the interleaved weight is a column permutation of the original one
+    Wd = ops.dequantize(wq_i, sz_i, K, N, G)
+    assert torch.equal(Wd[:, 0::2], W16[:, :I]) and torch.equal(Wd[:, 1::2], W16[:, I:])
+    mod = WQLinear_QUICK(4, G, K, N, True, "cuda")
+    mod.qweight, mod.qzeros, mod.scales, mod.bias = qw, qz, sc, bias
+    for M in (1, 8, 16, 33, 64, 100, 130, 300, 512):
+        A = torch.from_numpy(qo.make_activations(M, K, seed=M)).cuda()
+        for use_bias in (False, True):
+            b, bi = (bias, bias_i) if use_bias else (None, None)
+            want = quick_kernels.silu_mul(ops.gemm(A, wq, sz, N, G, bias=b))
+            got = ops.gemm_tp(A, wq_i, sz_i, N, G, bias=bi, silu_mul=True)
+            assert got.shape == (M, I) and torch.equal(got, want), (M, use_bias)
+        assert torch.equal(mod.enable_silu_mul().forward_silu_mul(A), quick_kernels.silu_mul(ops.gemm(A, wq, sz, N, G, bias=bias)))
+    with pytest.raises(RuntimeError, match="forward_silu_mul"):
+        mod(A)
+    # against the fp64 definition as well (not only against our own unfused kernels)
+    A = torch.from_numpy(qo.make_activations(64, K, seed=3)).cuda()
+    y = A.double() @ W16.double()
+    g, u = y[:, :I].half().double(), y[:, I:].half().double()
+    assert_close(ops.gemm_tp(A, wq_i, sz_i, N, G, silu_mul=True), (g / (1 + torch.exp(-g))) * u, "fused SwiGLU vs fp64")
