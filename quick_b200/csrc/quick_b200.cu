@@ -826,10 +826,10 @@ bool take_relayout(cudaStream_t st) {   // true: a layout kernel precedes this l
   return g_relayout_overflow.exchange(0, std::memory_order_relaxed) != 0;
 }
 
-template <int TOK, int SPLIT, int VAR>
-int launch_umma(const CUtensorMap& map, const qb200::GemmArgs& args, int m_tiles, cudaStream_t stream) {
+template <int TOK, int SPLIT, int VAR, bool SILU>
+int launch_umma_impl(const CUtensorMap& map, const qb200::GemmArgs& args, int m_tiles, cudaStream_t stream) {
   using Cfg = qb200::TileCfg<TOK, VAR>;
-  auto kfn = qb200::w4a16_umma_kernel<TOK, SPLIT, VAR>;
+  auto kfn = qb200::w4a16_umma_kernel<TOK, SPLIT, VAR, SILU>;
   static PerDeviceOnce attr_once;   // per instantiation and device
   QB_CUDA(attr_once.ensure([&] { return cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem_bytes(SPLIT)); }));
   cudaLaunchConfig_t cfg{};
@@ -852,6 +852,15 @@ int launch_umma(const CUtensorMap& map, const qb200::GemmArgs& args, int m_tiles
   QB_CUDA(cudaLaunchKernelEx(&cfg, kfn, map, args));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return QB200_OK;
+}
+
+template <int TOK, int SPLIT, int VAR>
+int launch_umma(const CUtensorMap& map, const qb200::GemmArgs& args, int m_tiles, cudaStream_t stream) {
+  if (args.flags & qb200::kFlagSiluMul) {
+    if constexpr (VAR <= 1) return launch_umma_impl<TOK, SPLIT, VAR, true>(map, args, m_tiles, stream);   // experiment slots: no fused SwiGLU
+    else return fail(QB200_EINVAL, "QB200_GEMM_SILU_MUL is not instantiated for experiment variants");
+  }
+  return launch_umma_impl<TOK, SPLIT, VAR, false>(map, args, m_tiles, stream);
 }
 
 template <int TOK, int VAR>

@@ -25,6 +25,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace qb200 {
 
@@ -690,7 +691,7 @@ __device__ __forceinline__ void store_tile(const GemmArgs& args, uint32_t smem_o
 // ------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------
-template <int TOK, int SPLIT, int VAR = 0>
+template <int TOK, int SPLIT, int VAR = 0, bool SILU = false>
 __global__ void __launch_bounds__(TileCfg<TOK, VAR>::kNumThreads, TileCfg<TOK, VAR>::kMinBlocks)
 w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs args) {
   using Cfg = TileCfg<TOK, VAR>;
@@ -745,7 +746,9 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
   // the previous grid until the very end (one griddepcontrol.wait before exit keeps completion transitive:
   // "this kernel finished" still implies "everything launched before it finished").
   const bool independent = (args.flags & kFlagIndependent) != 0;
-  const bool silu_mul = (args.flags & kFlagSiluMul) != 0;    // SwiGLU fused into the epilogue (gate / up channels interleaved)
+  // SwiGLU fused into the epilogue (gate / up channels interleaved): a separate instantiation — as a run-time branch in
+  // the epilogue's inner loops it cost every GEMM 3 % (16-token tiles) to 10 % (256-token tiles)
+  constexpr bool silu_mul = SILU;
   const int nt = blockIdx.x;
   const int mt = blockIdx.y;
   const int rank = SPLIT > 1 ? static_cast<int>(cluster_ctarank()) : 0;
@@ -891,78 +894,99 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
     const int NG = args.K / args.G;
     const int g32 = args.G >> 5;                    // k32 blocks per group
     const uint32_t* szp = args.sz + static_cast<size_t>(nt) * NG * kChan + ch;
-    // group index of each of the 4 k32 blocks of the next stage, advanced incrementally (no divisions in the loop)
-    int kq = (kb0 + wg * kSubPerStage) * 2;
-    int grp = kq / g32, rem = kq % g32;
-    uint32_t szw[2 * kSubPerStage];
-    auto load_sz = [&]() {
-      int g = grp, r = rem;
+    constexpr int kQ = 2 * kSubPerStage;            // k32 blocks per stage
+    const int last_nsub = nkb - (nst - 1) * kSubPerStage;   // only the last stage can be partial
+    // One scale / zero word per stage when a whole stage lies inside one quantisation group (G a multiple of the stage
+    // length and the CTA's k range starting on a stage boundary: the common case, G = 128 with 128-k stages); otherwise
+    // one word per k32 block.  The loop is instantiated for both (the choice is uniform over the CTA): the common case
+    // saves three loads and nine constant-preparation instructions per stage and thread.
+    const bool one_group = (g32 % kQ == 0) && ((kb0 * 2) % kQ == 0);
+    auto run = [&](auto one_tag) {
+      constexpr bool kOne = decltype(one_tag)::value;
+      constexpr int kNZ = kOne ? 1 : kQ;            // scale / zero words per stage
+      // group index of the k32 blocks of the next stage, advanced incrementally (no divisions in the loop)
+      int kq = (kb0 + wg * kSubPerStage) * 2;
+      int grp = kq / g32, rem = kq % g32;
+      uint32_t szw[kNZ];
+      auto load_sz = [&]() {
+        int g = grp, r = rem;
 #pragma unroll
-      for (int q = 0; q < 2 * kSubPerStage; ++q) {
-        szw[q] = __ldg(szp + static_cast<size_t>(min(g, NG - 1)) * kChan);
-        if (++r >= g32) { r = 0; ++g; }
+        for (int q = 0; q < kNZ; ++q) {
+          szw[q] = __ldg(szp + static_cast<size_t>(min(g, NG - 1)) * kChan);
+          if (++r >= g32) { r = 0; ++g; }
+        }
+      };
+      if (wg < nst) load_sz();
+      int s = wg % DS;                              // W ring slot (same warpgroup every time: DS % NWG == 0)
+      uint32_t sph = 0;
+      int b = wg % NB;                              // ready / free barrier of the stage (it % NB), kept incrementally
+      uint32_t bph = 0;                             // (it / NB) & 1
+      for (int it = wg; it < nst; it += NWG) {
+        const int nsub = it == nst - 1 ? last_nsub : kSubPerStage;
+        mbar_wait(bar_wfull + 8 * s, sph, 3, it);
+        if (lane == 0 && quad == QB_TQ) QB_TRACE(2, it, 0);
+        const uint32_t wbase = smem_w + s * kWStage + ch * 16;
+        uint4 w[kQ];
+#pragma unroll
+        for (int p = 0; p < kSubPerStage; ++p) {
+          if (p < nsub) {
+            w[2 * p] = lds128(wbase + p * 4096);
+            w[2 * p + 1] = lds128(wbase + p * 4096 + 2048);
+          }
+        }
+        GroupConsts gc[kNZ];
+#pragma unroll
+        for (int q = 0; q < kNZ; ++q) gc[q] = make_group_consts(szw[q]);
+        // advance NWG stages and prefetch the next scale / zero words
+        rem += kQ * NWG;
+        while (rem >= g32) { rem -= g32; ++grp; }
+        if (it + NWG < nst) load_sz();
+        if (lane == 0 && quad == QB_TQ) QB_TRACE(4, it, 0);
+        // operand slot t = it % D2 is free once the MMAs of stage it - D2 have completed (barrier (it - D2) % NB)
+        int t, fb;
+        uint32_t fph;
+        if constexpr (NB == D2) { t = b; fb = b; fph = bph ^ 1u; }
+        else { t = b >= D2 ? b - D2 : b; fb = b >= D2 ? b - D2 : b + D2; fph = b >= D2 ? bph : bph ^ 1u; }
+        if (it >= D2) {
+          mbar_wait(bar_free + 8 * fb, fph, 4, it);
+          tc_fence_after();
+        }
+        if (lane == 0 && quad == QB_TQ) QB_TRACE(4, it, 1);
+        const uint32_t a_tmem = tmem_base + lane_addr + Cfg::kACol0 + t * kASlotCols;
+#pragma unroll
+        for (int sub = 0; sub < kSubPerStage; ++sub) {
+          if (sub < nsub) {
+            const GroupConsts& g0 = gc[kOne ? 0 : 2 * sub];
+            const GroupConsts& g1 = gc[kOne ? 0 : 2 * sub + 1];
+            uint32_t r[32];
+            dequant_word(w[2 * sub].x, g0, r + 0);
+            dequant_word(w[2 * sub].y, g0, r + 4);
+            dequant_word(w[2 * sub].z, g0, r + 8);
+            dequant_word(w[2 * sub].w, g0, r + 12);
+            dequant_word(w[2 * sub + 1].x, g1, r + 16);
+            dequant_word(w[2 * sub + 1].y, g1, r + 20);
+            dequant_word(w[2 * sub + 1].z, g1, r + 24);
+            dequant_word(w[2 * sub + 1].w, g1, r + 28);
+            tmem_st16(a_tmem + sub * 32, r);
+            tmem_st16(a_tmem + sub * 32 + 16, r + 16);
+            if (sub == 0 && lane == 0 && quad == QB_TQ) QB_TRACE(4, it, 2);
+          }
+        }
+        if (lane == 0 && quad == QB_TQ) QB_TRACE(2, it, 1);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0 && quad == QB_TQ) QB_TRACE(4, it, 3);
+        if (lane == 0) mbar_arrive(bar_ready + 8 * b);
+        if (lane == 0 && quad == QB_TQ) QB_TRACE(2, it, 2);
+        if (lane == 0 && quad != QB_TQ) QB_TRACE(5, it, 1 + (quad < QB_TQ ? quad : quad - 1));   // hand-off of the other quadrants
+        s += NWG;
+        if (s >= DS) { s -= DS; sph ^= 1; }
+        b += NWG;
+        if (b >= NB) { b -= NB; bph ^= 1u; }
       }
     };
-    if (wg < nst) load_sz();
-    int s = wg % DS, t = wg % D2;
-    uint32_t sph = 0;
-    for (int it = wg; it < nst; it += NWG) {
-      const int nsub = min(kSubPerStage, nkb - it * kSubPerStage);
-      mbar_wait(bar_wfull + 8 * s, sph, 3, it);
-      if (lane == 0 && quad == QB_TQ) QB_TRACE(2, it, 0);
-      const uint32_t wbase = smem_w + s * kWStage + ch * 16;
-      uint4 w[2 * kSubPerStage];
-#pragma unroll
-      for (int p = 0; p < kSubPerStage; ++p) {
-        if (p < nsub) {
-          w[2 * p] = lds128(wbase + p * 4096);
-          w[2 * p + 1] = lds128(wbase + p * 4096 + 2048);
-        }
-      }
-      GroupConsts gc[2 * kSubPerStage];
-#pragma unroll
-      for (int q = 0; q < 2 * kSubPerStage; ++q) gc[q] = make_group_consts(szw[q]);
-      // advance NWG stages (4 k32 blocks each) and prefetch the next scale/zero words
-      rem += 2 * kSubPerStage * NWG;
-      while (rem >= g32) { rem -= g32; ++grp; }
-      if (it + NWG < nst) load_sz();
-      if (lane == 0 && quad == QB_TQ) QB_TRACE(4, it, 0);
-      // operand slot t is free once the MMAs of stage it - D2 have completed
-      if (it >= D2) {
-        mbar_wait(bar_free + 8 * ((it - D2) % NB), static_cast<uint32_t>((it - D2) / NB) & 1u, 4, it);
-        tc_fence_after();
-      }
-      if (lane == 0 && quad == QB_TQ) QB_TRACE(4, it, 1);
-      const uint32_t a_tmem = tmem_base + lane_addr + Cfg::kACol0 + t * kASlotCols;
-#pragma unroll
-      for (int sub = 0; sub < kSubPerStage; ++sub) {
-        if (sub < nsub) {
-          uint32_t r[32];
-          dequant_word(w[2 * sub].x, gc[2 * sub], r + 0);
-          dequant_word(w[2 * sub].y, gc[2 * sub], r + 4);
-          dequant_word(w[2 * sub].z, gc[2 * sub], r + 8);
-          dequant_word(w[2 * sub].w, gc[2 * sub], r + 12);
-          dequant_word(w[2 * sub + 1].x, gc[2 * sub + 1], r + 16);
-          dequant_word(w[2 * sub + 1].y, gc[2 * sub + 1], r + 20);
-          dequant_word(w[2 * sub + 1].z, gc[2 * sub + 1], r + 24);
-          dequant_word(w[2 * sub + 1].w, gc[2 * sub + 1], r + 28);
-          tmem_st16(a_tmem + sub * 32, r);
-          tmem_st16(a_tmem + sub * 32 + 16, r + 16);
-          if (sub == 0 && lane == 0 && quad == QB_TQ) QB_TRACE(4, it, 2);
-        }
-      }
-      if (lane == 0 && quad == QB_TQ) QB_TRACE(2, it, 1);
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0 && quad == QB_TQ) QB_TRACE(4, it, 3);
-      if (lane == 0) mbar_arrive(bar_ready + 8 * (it % NB));
-      if (lane == 0 && quad == QB_TQ) QB_TRACE(2, it, 2);
-      if (lane == 0 && quad != QB_TQ) QB_TRACE(5, it, 1 + (quad < QB_TQ ? quad : quad - 1));   // hand-off of the other quadrants
-      s += NWG;
-      if (s >= DS) { s -= DS; sph ^= 1; }
-      t = (t + NWG) % D2;
-    }
+    if (one_group) run(std::true_type{}); else run(std::false_type{});
   }
 
   // ===================== epilogue =====================
