@@ -881,6 +881,7 @@ int pick_variant(int tok, int split, int ctas, int K) {
   const int stages = ((K / 64 + split - 1) / split + 1) / 2;   // 128-k stages per CTA
   if (tok <= 32) return stages <= 4 ? 1 : 0;
   if (tok == 64) return ctas <= device_sm_count() ? 1 : 0;
+  if (tok == 128) return stages >= 16 ? 1 : 0;
   return 0;
 }
 

@@ -345,6 +345,7 @@ struct Rings {
 // Two configurations per small tile, chosen by the launch planner (quick_b200.cu, pick_variant):
 //   VAR 0  three dequant warpgroups, one issuer  — many stages per CTA / co-resident CTAs that both stream
 //   VAR 1  two dequant warpgroups, two issuers   — short tiles (<= 4 stages) and lone 64-token CTAs
+//   128-token tiles: VAR 0 = (2 warpgroups, 4 operand slots, 2 issuers) for <= 8 stages, VAR 1 = (3, 3, 2) for longer ones
 // (measured with tools/tune.py on K = N = 4096 and the 7B layer shapes, profiles/r2_tune_*.json).  VAR 2..3 exist in
 // QB200_VARIANTS builds only (A/B slots for tools/tune.py, qb200_debug_set_variant).
 template <int TOK, int VAR> struct Variant;
@@ -355,7 +356,7 @@ template <> struct Variant<32, 1> : Rings<2, 6, 3, 2, 2> {};
 template <> struct Variant<64, 0> : Rings<3, 6, 3> {};
 template <> struct Variant<64, 1> : Rings<2, 6, 3, 2, 2> {};
 template <> struct Variant<128, 0> : Rings<2, 6, 4, 2, 2> {};
-template <> struct Variant<128, 1> : Rings<3, 6, 3> {};
+template <> struct Variant<128, 1> : Rings<3, 6, 3, 2, 2> {};
 template <> struct Variant<256, 0> : Rings<2, 4, 3> {};
 template <> struct Variant<256, 1> : Rings<2, 4, 2> {};
 #ifdef QB200_VARIANTS   // experiment slots (tools/tune.py)
@@ -363,10 +364,10 @@ template <> struct Variant<16, 2> : Rings<3, 9, 3> {};
 template <> struct Variant<16, 3> : Rings<3, 6, 3, 2, 2> {};
 template <> struct Variant<32, 2> : Rings<3, 9, 3> {};
 template <> struct Variant<32, 3> : Rings<3, 6, 3, 2, 2> {};
-template <> struct Variant<64, 2> : Rings<3, 9, 3> {};
-template <> struct Variant<64, 3> : Rings<2, 6, 2, 2, 2> {};
-template <> struct Variant<128, 2> : Rings<3, 6, 3, 2, 2> {};
-template <> struct Variant<128, 3> : Rings<2, 6, 3, 2, 2> {};
+template <> struct Variant<64, 2> : Rings<3, 6, 3, 2, 2> {};
+template <> struct Variant<64, 3> : Rings<4, 8, 4, 2, 2> {};
+template <> struct Variant<128, 2> : Rings<4, 8, 4, 2, 2> {};
+template <> struct Variant<128, 3> : Rings<3, 6, 3> {};
 template <> struct Variant<256, 2> : Rings<2, 4, 3> {};
 template <> struct Variant<256, 3> : Rings<2, 4, 3> {};
 #endif
@@ -813,9 +814,12 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
 
   if (warp == kProducerWarp) {
     // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
-    // One in-order loop over the X stages: X(j) reuses the operand slot of stage j-D2, and the W stage issued
-    // with it, W(j+DS-D2), reuses the W slot of the same stage j-D2 — whose nibbles were read into registers
-    // before its MMAs could even start.  So the single "MMAs of stage j-D2 complete" barrier releases both.
+    // One in-order loop over the X stages: X(j) reuses the operand slot of stage j-D2 and waits for that stage's
+    // MMAs ("free").  The W ring is not refilled here: a W slot is dead as soon as its dequant warpgroup has loaded
+    // it into registers, long before the stage's MMAs complete, so the warpgroup itself requests the slot's next
+    // stage (round-2 traces: riding on "free", weights were requested only DS - D2 stages ahead and 128-token tiles
+    // waited ~400 cycles per stage for them; polling a separate "loaded" barrier from this warp cost more than it
+    // gained because it delayed the X loads).
     if (!independent) pdl_wait_prior_grid();   // the activations come from the previous kernel
     // tensor parallel: the activations may live in a gathered buffer (meet the ranks that fill it), and C may be one
     const bool first_cta = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
@@ -835,8 +839,6 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
         for (int p = 0; p < kSubPerStage; ++p)
           if (p < nsub)
             tma_load_2d(smem_x + x * Cfg::kXStageBytes + p * Cfg::kXPanelBytes, &tmap_x, bar, (kb0 + j * kSubPerStage + p) * kBK, mt * TOK);
-        const int jw = j + (DS - D2);
-        if (j >= D2 && jw < nst) issue_w(jw);
         QB_TRACE(0, j, 1);
       }
       __syncwarp();
@@ -980,6 +982,13 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
         if (lane == 0) mbar_arrive(bar_ready + 8 * b);
         if (lane == 0 && quad == QB_TQ) QB_TRACE(2, it, 2);
         if (lane == 0 && quad != QB_TQ) QB_TRACE(5, it, 1 + (quad < QB_TQ ? quad : quad - 1));   // hand-off of the other quadrants
+        // Refill this W slot with the stage DS ahead: all four warps of the warpgroup have loaded it (named barrier
+        // per warpgroup), one of them — rotating, so no quadrant is always the late one — issues the bulk copy.
+        if (it + DS < nst) {
+          named_bar_sync(3 + (warp >> 2), 128);
+          if (quad == (it & 3) && elect_one()) issue_w(it + DS);
+          __syncwarp();
+        }
         s += NWG;
         if (s >= DS) { s -= DS; sph ^= 1; }
         b += NWG;
