@@ -201,6 +201,12 @@ int qb200_attn_decode_smem_bytes(int nh, int nkv, int hd, int S);
 int qb200_attn_decode(const void* qkv_fp16, const void* cos_table_fp16, const void* sin_table_fp16, const long long* pos,
                       void* out_fp16, void* cache_k_fp16, void* cache_v_fp16, int B, int nh, int nkv, int hd, int S, float scale,
                       void* stream);
+/* qb200_attn_decode of this rank's heads (tensor parallel: head-sharded attention) whose output goes straight into every
+ * rank's [B][ld] attention buffer at column col0 (a gathered buffer: the input of the column-parallel output projection);
+ * plain peer stores, `signal` as for the other producers.  nh / nkv are the LOCAL head counts. */
+int qb200_attn_decode_tp(const void* qkv_fp16, const void* cos_table_fp16, const void* sin_table_fp16, const long long* pos,
+                         void* cache_k_fp16, void* cache_v_fp16, int B, int nh, int nkv, int hd, int S, float scale,
+                         void* const* out_peers, int n_peers, int ld, int col0, const qb200_peer_signal* signal, void* stream);
 /* act[rows][I] = silu(g) * u for gate_up rows [g | u] of width 2I. */
 int qb200_silu_mul(const void* gate_up_fp16, void* act_fp16, long long rows, int I, void* stream);
 /* Same for rows with interleaved columns (g_0, u_0, g_1, u_1, ...): the output of a QB200_GEMM_SILU_MUL weight run without

@@ -17,7 +17,7 @@ SYMBOLS = [
     "qb200_dequantize", "qb200_gemm_w4a16",
     "qb200_gemm_w4a16_cfg", "qb200_gemm_w4a16_ex", "qb200_gemm_w4a16_fused", "qb200_attn_decode", "qb200_attn_decode_smem_bytes", "qb200_rmsnorm", "qb200_rope_kv_update",
     "qb200_silu_mul", "qb200_silu_mul_interleaved", "qb200_gemm_w4a16_allgather", "qb200_peer_barrier",
-    "qb200_gemm_w4a16_tp", "qb200_rmsnorm_tp", "qb200_silu_mul_tp", "qb200_scatter_cols", "qb200_gemm_plan", "qb200_gemm_plan_ex", "qb200_gemm_forward_quick", "qb200_gemm_w4a16_simt",
+    "qb200_gemm_w4a16_tp", "qb200_rmsnorm_tp", "qb200_silu_mul_tp", "qb200_scatter_cols", "qb200_attn_decode_tp", "qb200_gemm_plan", "qb200_gemm_plan_ex", "qb200_gemm_forward_quick", "qb200_gemm_w4a16_simt",
     "qb200_linear_create", "qb200_linear_forward_host", "qb200_linear_forward_host_async", "qb200_linear_synchronize",
     "qb200_linear_forward", "qb200_linear_destroy",
     "qb200_launch_count", "qb200_debug_set_trace", "qb200_debug_set_variant",
@@ -75,6 +75,8 @@ def load() -> C.CDLL:
                                         C.POINTER(PeerWait), C.POINTER(PeerSignal), vp]
     lib.qb200_rmsnorm_tp.argtypes = [vp, vp, vp, i32, i32, C.c_float, C.POINTER(PeerWait), vp]
     lib.qb200_silu_mul_tp.argtypes = [vp, C.c_longlong, i32, C.POINTER(vp), vp, i32, i32, i32, C.POINTER(PeerSignal), vp]
+    lib.qb200_attn_decode_tp.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, C.c_float, C.POINTER(vp), i32, i32, i32,
+                                         C.POINTER(PeerSignal), vp]
     lib.qb200_scatter_cols.argtypes = [vp, C.c_longlong, i32, C.POINTER(vp), vp, i32, i32, i32, C.POINTER(PeerSignal), vp]
     lib.qb200_rope_kv_update.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     lib.qb200_silu_mul.argtypes = [vp, vp, C.c_longlong, i32, vp]

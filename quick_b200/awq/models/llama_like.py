@@ -313,7 +313,7 @@ class Block(nn.Module):
         return _linear(self.down_proj, act, ref_mod, residual=x), None
 
     def forward_tp(self, x, x_src, cos, sin, pos_idx, attn_mask, rope):
-        """One decoder layer on this rank's shards.  Peer mode: 8 kernels, none of them a barrier — the two column-parallel
+        """One decoder layer on this rank's shards.  Peer mode: 8 kernels (7 for a decode step), none of them a barrier — the two column-parallel
         GEMMs store their slabs into every rank's hidden-state buffer, the attention output and the MLP activation are
         scattered the same way, and each consumer (RMSNorm rows, GEMM activations) meets the producers in its own
         prologue.  NCCL mode: the same dataflow with four all-gathers."""
@@ -329,8 +329,14 @@ class Block(nn.Module):
             xn = ops.rmsnorm_tp(x2d, self.norm_1.weight, self.norm_1.eps, wait=x_src)
             wq, sz = self.qkv_proj._prepacked()
             qkv = ops.gemm_tp(xn, wq, sz, self.qkv_proj.out_features, self.qkv_proj.group_size, bias=self.qkv_proj.bias)
-            o = self._attention(qkv.view(B, T, -1), cos, sin, pos_idx, attn_mask, rope, fused_decode)
-            ops.scatter_cols(o.reshape(M, self.nh_l * hd).contiguous(), tp.attn, tp.rank * self.nh_l * hd)
+            if fused_decode:
+                # decode step: rotary + KV-cache update + attention of the local heads, output stored straight into
+                # every rank's attention buffer (no separate scatter kernel)
+                ops.attn_decode_tp(qkv, rope[0], rope[1], pos_idx, self.cache_k, self.cache_v, self.nh_l, self.nkv_l, tp.attn,
+                                   tp.rank * self.nh_l * hd)
+            else:
+                o = self._attention(qkv.view(B, T, -1), cos, sin, pos_idx, attn_mask, rope, fused_decode)
+                ops.scatter_cols(o.reshape(M, self.nh_l * hd).contiguous(), tp.attn, tp.rank * self.nh_l * hd)
             wq, sz = self.o_proj._prepacked()
             ops.gemm_tp(tp.attn.rows(M), wq, sz, self.o_proj.out_features, self.o_proj.group_size, bias=self.o_proj.bias,
                         residual=x2d, dst=tp.hid_b, col0=col_h, wait=tp.attn)

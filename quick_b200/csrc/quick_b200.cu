@@ -366,56 +366,127 @@ __global__ void rope_kv_kernel(const __half* __restrict__ qkv, const __half* __r
 
 // Decode-step attention (ONE new token per sequence) fused with the rotary embedding and the KV-cache update — the job of
 // the reference's QuantAttentionFused decode branch (modules/fused/attn.py:187-245: awq_ext.single_query_attention over
-// its rolling cache).  One CTA per (kv head, sequence): it rotates its k and the g = nh / nkv query heads that share it
-// (same arithmetic as rope_kv_kernel), writes k / v into the static caches [B][nkv][S][hd] at position p = pos[0],
-// scores the p + 1 visible positions (the new one from shared memory), softmaxes in fp32 and accumulates P·V — no mask
-// tensor, no q / k / v round trip through HBM, one launch instead of rope + mask arithmetic + SDPA.
-//   out [B][1][nh * hd] fp16 (the layout o_proj consumes).  Shared memory: q_rot g·hd, k, v (fp16) | scores g·S (fp32) |
-//   P·V partials (256 / (hd/2)) · g · hd (fp32) | 1 / sum per head.
+// its rolling cache).  A CLUSTER of `nsplit` CTAs per (kv head, sequence) — flash-decoding inside a thread-block cluster:
+// CTA r of the cluster takes a contiguous range of the cached positions, a warp streams its positions' K and V rows in
+// ONE pass (online softmax, kBatch K rows + kBatch V rows in flight per lane, a lane owns hd/32 consecutive dims), the
+// eight warps merge in shared memory and the cluster's partial (max, sum, P·V) triples are merged by CTA 0 through
+// distributed shared memory.  No score buffer (any cache length), no mask tensor, no q / k / v round trip through HBM.
+// The g = nh / nkv query heads that share a kv head are processed together (each K / V row is read once).
+// CTA 0 also rotates k, writes k / v into the static caches [B][nkv][S][hd] at position p = pos[0] (same arithmetic as
+// rope_kv_kernel) and adds the new position from shared memory.
+//   out [B][1][nh * hd] fp16 (the layout o_proj consumes), or (tensor parallel) column col0 of every rank's buffer.
+// Before griddepcontrol.wait the CTAs prefetch their K / V rows into L2 (prefetch.global.L2: no data is consumed, so a
+// stale position can only cost bandwidth) — the HBM latency of the cache overlaps the tail of the q|k|v GEMM.
 constexpr int kAttnThreads = 256;
-constexpr int kAttnMaxGroup = 8;
-__host__ __device__ constexpr size_t attn_decode_smem(int g, int hd, int S) {
-  return static_cast<size_t>(g + 2) * hd * 2 + static_cast<size_t>(g) * S * 4 +
-         static_cast<size_t>(kAttnThreads / (hd / 2)) * g * hd * 4 + kAttnMaxGroup * 4;
+constexpr int kAttnWarps = kAttnThreads / 32;
+constexpr int kAttnMaxSplit = 8;
+__host__ __device__ constexpr size_t attn_decode_smem(int g, int hd) {
+  // q_rot g·hd, k, v (fp16) | per-warp (max, sum) | per-warp P·V | per-CTA (max, sum) x cluster | per-CTA P·V x cluster | mbarrier
+  return static_cast<size_t>(g + 2) * hd * 2 + static_cast<size_t>(kAttnWarps) * g * 8 + static_cast<size_t>(kAttnWarps) * g * hd * 4 +
+         static_cast<size_t>(kAttnMaxSplit) * g * 8 + static_cast<size_t>(kAttnMaxSplit) * g * hd * 4 + 16;
 }
 
+template <int VEC> struct AttnRow;      // VEC consecutive fp16 of a cache row, as loaded
+template <> struct AttnRow<2> { uint32_t v; };
+template <> struct AttnRow<4> { uint2 v; };
+template <> struct AttnRow<8> { uint4 v; };
 template <int VEC>
-__device__ __forceinline__ void attn_load_row(const __half* p, float (&f)[VEC]) {   // VEC consecutive fp16 -> fp32
-  __align__(16) __half h[VEC];
-  if constexpr (VEC == 2) *reinterpret_cast<uint32_t*>(h) = *reinterpret_cast<const uint32_t*>(p);
-  else if constexpr (VEC == 4) *reinterpret_cast<uint2*>(h) = *reinterpret_cast<const uint2*>(p);
-  else *reinterpret_cast<uint4*>(h) = *reinterpret_cast<const uint4*>(p);
+__device__ __forceinline__ void attn_unpack(const AttnRow<VEC>& r, float (&f)[VEC]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&r.v);
 #pragma unroll
-  for (int u = 0; u < VEC; ++u) f[u] = __half2float(h[u]);
+  for (int u = 0; u < VEC / 2; ++u) {
+    const float2 t = __half22float2(h[u]);
+    f[2 * u] = t.x; f[2 * u + 1] = t.y;
+  }
 }
 
+// Destination of a column slab that every rank needs (tensor parallel): the [rows][ld] buffers of all ranks at column
+// col0 — ONE multimem.st per 16-byte chunk through the NVSwitch multicast mapping when there is one, else a loop of
+// peer stores.
+struct PeerDst {
+  __half* peer[8];
+  __half* mc;
+  int n, ld, col0;
+};
+__device__ __forceinline__ void store16_all(const PeerDst& d, size_t off, uint4 v) {
+  if (d.mc != nullptr) qb200::multimem_st_v4(d.mc + off, v);
+  else for (int p = 0; p < d.n; ++p) *reinterpret_cast<uint4*>(d.peer[p] + off) = v;
+}
 template <int HD, int G>
 __global__ void __launch_bounds__(kAttnThreads)
 attn_decode_kernel(const __half* __restrict__ qkv, const __half* __restrict__ cosb, const __half* __restrict__ sinb,
                    const long long* __restrict__ pos, __half* __restrict__ out, __half* __restrict__ cache_k,
-                   __half* __restrict__ cache_v, int nh, int nkv, int S, float scale) {
-  qb200::pdl_launch_dependents();
-  qb200::pdl_wait_prior_grid();
-  extern __shared__ __align__(16) uint8_t attn_smem[];
+                   __half* __restrict__ cache_v, int nh, int nkv, int S, float scale, int nsplit, const PeerDst dst,
+                   const qb200::PeerSignal sig) {
   constexpr int hd = HD, g = G;
   constexpr int VEC = HD / 32;                           // halves of a row owned by one lane (2, 4 or 8)
-  constexpr int kWarps = kAttnThreads / 32;
-  constexpr int kBatch = 4;                              // cache rows a warp has in flight
+  constexpr int kBatch = (G * VEC >= 32) ? 2 : 4;        // cache positions per batch (K and V rows each); two batches in flight
   const int kvh = blockIdx.x, b = blockIdx.y;
+  const int rank = blockIdx.z;                           // == %cluster_ctarank: the cluster spans the z dimension
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int p = static_cast<int>(pos[0]);                // the new position; positions 0 .. p are visible
-  __half* qs = reinterpret_cast<__half*>(attn_smem);     // [g][hd]
-  __half* ks = qs + g * hd;                              // [hd]
-  __half* vs = ks + hd;                                  // [hd]
-  float* sc = reinterpret_cast<float*>(vs + hd);         // [g][S]
-  constexpr int tpd = hd >> 1, nsl = kAttnThreads / tpd; // threads per P·V slice (one half2 each), slices
-  float* red = sc + static_cast<size_t>(g) * S;          // [nsl][g][hd]
-  float* inv = red + static_cast<size_t>(nsl) * g * hd;  // [g]
-  const __half* src = qkv + static_cast<size_t>(b) * (nh + 2 * nkv) * hd;
   const size_t crow = (static_cast<size_t>(b) * nkv + kvh) * S;   // first cache row of this (sequence, kv head)
-  constexpr int half_hd = hd >> 1;
+  const __half* kbase = cache_k + crow * hd + lane * VEC;
+  const __half* vbase = cache_v + crow * hd + lane * VEC;
+  extern __shared__ __align__(16) uint8_t attn_smem[];
+  __half* qs = reinterpret_cast<__half*>(attn_smem);     // [g][hd]
+  __half* ks = qs + g * hd;                              // [hd]   (CTA 0)
+  __half* vs = ks + hd;                                  // [hd]   (CTA 0)
+  float* wm = reinterpret_cast<float*>(vs + hd);         // [warps][g] running max
+  float* wl = wm + kAttnWarps * g;                       // [warps][g] running sum
+  float* wacc = wl + kAttnWarps * g;                     // [warps][g][hd]
+  float* cm = wacc + kAttnWarps * g * hd;                // [cluster][g]      per-CTA triples, gathered in CTA 0 of the cluster
+  float* cl = cm + kAttnMaxSplit * g;                    // [cluster][g]
+  float* cacc = cl + kAttnMaxSplit * g;                  // [cluster][g][hd]
+  const uint32_t bar = qb200::smem_u32(cacc + kAttnMaxSplit * g * hd);   // CTA 0: the other CTAs' triples have landed
+  qb200::pdl_launch_dependents();
+  if (nsplit > 1) {
+    if (rank == 0 && tid == 0) {
+      qb200::mbar_init(bar, 1);
+      qb200::fence_barrier_init();
+    }
+    qb200::cluster_arrive_relaxed();                      // matched by a wait just before the first remote store
+  }
+  {   // L2 prefetch of this warp's cache rows; pos may still be the previous step's value here (harmless, see above)
+    const int pp = min(max(static_cast<int>(pos[0]), 0), S - 1);
+    const int per = (pp + nsplit - 1) / nsplit;
+    const int lo = rank * per, hi = min(pp, lo + per);
+    for (int j = lo + warp; j < hi; j += kAttnWarps) {
+      if (lane * VEC * 2 % 128 == 0) {                   // one prefetch per 128-byte line of the row
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(kbase + static_cast<size_t>(j) * hd));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(vbase + static_cast<size_t>(j) * hd));
+      }
+    }
+  }
+  qb200::pdl_wait_prior_grid();
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) qb200::peer_begin_fill(sig);   // tensor parallel: out is a gathered buffer
+  const int p = static_cast<int>(pos[0]);                // the new position; positions 0 .. p are visible
+  const int per = (p + nsplit - 1) / nsplit;             // cached positions 0 .. p-1 split over the cluster
+  const int lo = rank * per, hi = min(p, lo + per);
 
-  for (int idx = tid; idx < (g + 2) * hd; idx += kAttnThreads) {
+  // first batch of this warp's K / V rows: requested before the rotary phase (they do not depend on this step's q)
+  AttnRow<VEC> kr0[kBatch], vr0[kBatch], kr1[kBatch], vr1[kBatch];   // two batches (named, so they stay in registers)
+  auto load_batch = [&](int j0, AttnRow<VEC> (&kb)[kBatch], AttnRow<VEC> (&vb)[kBatch]) {   // warp-uniform bounds; returns the valid rows
+    int nvalid = 0;
+#pragma unroll
+    for (int t = 0; t < kBatch; ++t) {
+      const int j = j0 + t * kAttnWarps;
+      if (j < hi) {
+        kb[t] = *reinterpret_cast<const AttnRow<VEC>*>(kbase + static_cast<size_t>(j) * hd);
+        vb[t] = *reinterpret_cast<const AttnRow<VEC>*>(vbase + static_cast<size_t>(j) * hd);
+        nvalid = t + 1;
+      } else {
+        kb[t] = AttnRow<VEC>{}; vb[t] = AttnRow<VEC>{};
+      }
+    }
+    return nvalid;
+  };
+  int j0 = lo + warp;
+  int nv = j0 < hi ? load_batch(j0, kr0, vr0) : 0;
+
+  // rotary embedding of the g query heads (every CTA) and of k (CTA 0, which also updates the cache)
+  const __half* src = qkv + static_cast<size_t>(b) * (nh + 2 * nkv) * hd;
+  constexpr int half_hd = hd >> 1;
+  for (int idx = tid; idx < (rank == 0 ? g + 2 : g) * hd; idx += kAttnThreads) {
     const int hl = idx / hd, i = idx - hl * hd;
     if (hl == g + 1) {                                   // value: plain copy
       const __half v = src[static_cast<size_t>(nh + nkv + kvh) * hd + i];
@@ -437,104 +508,158 @@ attn_decode_kernel(const __half* __restrict__ qkv, const __half* __restrict__ co
   }
   __syncthreads();
 
-  {   // scores: a warp per position (one coalesced row read, lane = VEC consecutive dims), kBatch rows in flight per warp
-    float qf[G][VEC];                                    // this lane's slice of every query head of the group
+  // one pass over this warp's cached positions: online softmax, fp32
+  float qf[G][VEC], acc[G][VEC], mx[G], sum[G];
 #pragma unroll
-    for (int h = 0; h < G; ++h)
+  for (int h = 0; h < G; ++h) {
+    mx[h] = -INFINITY; sum[h] = 0.f;
 #pragma unroll
-      for (int u = 0; u < VEC; ++u) qf[h][u] = __half2float(qs[h * hd + lane * VEC + u]);
-    auto score = [&](const float (&kf)[VEC], int j) {
+    for (int u = 0; u < VEC; ++u) { qf[h][u] = __half2float(qs[h * hd + lane * VEC + u]) * scale; acc[h][u] = 0.f; }
+  }
+  auto fold = [&](const AttnRow<VEC> (&kb)[kBatch], const AttnRow<VEC> (&vb)[kBatch], int nvalid) {
+    float s[G][kBatch];
+#pragma unroll
+    for (int t = 0; t < kBatch; ++t) {
+      float kf[VEC];
+      attn_unpack<VEC>(kb[t], kf);
 #pragma unroll
       for (int h = 0; h < G; ++h) {
         float a = 0.f;
 #pragma unroll
         for (int u = 0; u < VEC; ++u) a = fmaf(qf[h][u], kf[u], a);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) sc[static_cast<size_t>(h) * S + j] = a * scale;
+        s[h][t] = a;
       }
-    };
-    const __half* kbase = cache_k + crow * hd + lane * VEC;
-    for (int j0 = warp; j0 < p; j0 += kWarps * kBatch) {            // cached positions 0 .. p-1 (warp-uniform bounds)
-      float kf[kBatch][VEC];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int h = 0; h < G; ++h)
+#pragma unroll
+        for (int t = 0; t < kBatch; ++t) s[h][t] += __shfl_xor_sync(0xffffffffu, s[h][t], o);
+#pragma unroll
+    for (int h = 0; h < G; ++h) {
+      float m_new = mx[h];
+#pragma unroll
+      for (int t = 0; t < kBatch; ++t) if (t < nvalid) m_new = fmaxf(m_new, s[h][t]);
+      const float corr = __expf(mx[h] - m_new);          // first batch: exp(-inf) = 0
+      mx[h] = m_new;
+      sum[h] *= corr;
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) acc[h][u] *= corr;
 #pragma unroll
       for (int t = 0; t < kBatch; ++t) {
-        const int j = j0 + t * kWarps;
-        if (j < p) attn_load_row<VEC>(kbase + static_cast<size_t>(j) * hd, kf[t]);
+        s[h][t] = t < nvalid ? __expf(s[h][t] - m_new) : 0.f;
+        sum[h] += s[h][t];
       }
+    }
 #pragma unroll
-      for (int t = 0; t < kBatch; ++t) {
-        const int j = j0 + t * kWarps;
-        if (j < p) score(kf[t], j);
-      }
+    for (int t = 0; t < kBatch; ++t) {
+      float vf[VEC];
+      attn_unpack<VEC>(vb[t], vf);
+#pragma unroll
+      for (int h = 0; h < G; ++h)
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) acc[h][u] = fmaf(s[h][t], vf[u], acc[h][u]);
     }
-    if (warp == 0) {                                     // the new position, from shared memory
-      float kf[VEC];
-      attn_load_row<VEC>(ks + lane * VEC, kf);
-      score(kf, p);
+  };
+  {
+    constexpr int kStep = kAttnWarps * kBatch;
+    while (nv > 0) {                                       // warp-uniform; the next batch is in flight while this one is folded
+      j0 += kStep;
+      const int n1 = j0 < hi ? load_batch(j0, kr1, vr1) : 0;
+      fold(kr0, vr0, nv);
+      if (n1 == 0) break;
+      j0 += kStep;
+      nv = j0 < hi ? load_batch(j0, kr0, vr0) : 0;
+      fold(kr1, vr1, n1);
     }
+    if (rank == 0 && warp == 0) {                          // the new position, from shared memory
+#pragma unroll
+      for (int t = 0; t < kBatch; ++t) { kr0[t] = AttnRow<VEC>{}; vr0[t] = AttnRow<VEC>{}; }
+      kr0[0] = *reinterpret_cast<const AttnRow<VEC>*>(ks + lane * VEC);
+      vr0[0] = *reinterpret_cast<const AttnRow<VEC>*>(vs + lane * VEC);
+      fold(kr0, vr0, 1);
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < G; ++h) {
+    if (lane == 0) { wm[warp * g + h] = mx[h]; wl[warp * g + h] = sum[h]; }
+#pragma unroll
+    for (int u = 0; u < VEC; ++u) wacc[(warp * g + h) * hd + lane * VEC + u] = acc[h][u];
   }
   __syncthreads();
 
-  const int L = p + 1;
-  if (warp < g) {                                         // softmax of head `warp` over L scores, fp32
-    float* row = sc + static_cast<size_t>(warp) * S;
-    float m = -INFINITY;
-    for (int j = lane; j < L; j += 32) m = fmaxf(m, row[j]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    float sum = 0.f;
-    for (int j = lane; j < L; j += 32) {
-      const float e = __expf(row[j] - m);
-      row[j] = e;
-      sum += e;
+  auto store_out = [&](int h, int d, float val) {
+    const __half v = __float2half_rn(val);
+    if (dst.n == 0) {
+      out[static_cast<size_t>(b) * nh * hd + static_cast<size_t>(kvh * g + h) * hd + d] = v;
+    } else {   // tensor parallel: this rank's heads go to column col0 of every rank's [B][ld] attention buffer
+      const size_t off = static_cast<size_t>(b) * dst.ld + dst.col0 + static_cast<size_t>(kvh * g + h) * hd + d;
+      for (int pr = 0; pr < dst.n; ++pr) dst.peer[pr][off] = v;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) inv[warp] = 1.f / sum;
+  };
+  // merge the eight warps: (max, sum, P·V) of this CTA's positions -> slot `rank` of CTA 0's gather buffers
+  // (st.async through distributed shared memory, completion counted on CTA 0's mbarrier; CTA 0 writes its own slot)
+  uint32_t r_cm = 0, r_cl = 0, r_cacc = 0, r_bar = 0;
+  if (nsplit > 1 && rank != 0) {
+    qb200::cluster_wait();                                 // CTA 0 has initialised its mbarrier
+    r_cm = qb200::mapa_shared(qb200::smem_u32(cm + rank * g), 0);
+    r_cl = qb200::mapa_shared(qb200::smem_u32(cl + rank * g), 0);
+    r_cacc = qb200::mapa_shared(qb200::smem_u32(cacc + rank * g * hd), 0);
+    r_bar = qb200::mapa_shared(bar, 0);
   }
-  __syncthreads();
-
-  {   // P·V: slice sl takes cached positions sl, sl + nsl, ... (8 rows in flight); thread = one half2 of the head dim
-    const int sl = tid / tpd, dl = (tid - sl * tpd) * 2;
-    constexpr int kPV = 8;
-    float2 acc[G];
-#pragma unroll
-    for (int h = 0; h < G; ++h) acc[h] = make_float2(0.f, 0.f);
-    auto fma_row = [&](float2 vf, int j) {
-#pragma unroll
-      for (int h = 0; h < G; ++h) {
-        const float pj = sc[static_cast<size_t>(h) * S + j];
-        acc[h].x = fmaf(pj, vf.x, acc[h].x);
-        acc[h].y = fmaf(pj, vf.y, acc[h].y);
-      }
-    };
-    const __half* vbase = cache_v + crow * hd + dl;
-    for (int j0 = sl; j0 < p; j0 += nsl * kPV) {
-      __half2 v2[kPV];
-#pragma unroll
-      for (int t = 0; t < kPV; ++t) {
-        const int j = j0 + t * nsl;
-        if (j < p) v2[t] = *reinterpret_cast<const __half2*>(vbase + static_cast<size_t>(j) * hd);
-      }
-#pragma unroll
-      for (int t = 0; t < kPV; ++t) {
-        const int j = j0 + t * nsl;
-        if (j < p) fma_row(__half22float2(v2[t]), j);
-      }
-    }
-    if (sl == 0) fma_row(__half22float2(*reinterpret_cast<const __half2*>(vs + dl)), p);   // the new position
-#pragma unroll
-    for (int h = 0; h < G; ++h) *reinterpret_cast<float2*>(red + (static_cast<size_t>(sl) * g + h) * hd + dl) = acc[h];
-  }
-  __syncthreads();
-
   for (int idx = tid; idx < g * hd; idx += kAttnThreads) {
     const int h = idx / hd, d = idx - h * hd;
-    float t = 0.f;
+    float M = -INFINITY;
 #pragma unroll
-    for (int sl = 0; sl < nsl; ++sl) t += red[(static_cast<size_t>(sl) * g + h) * hd + d];
-    out[static_cast<size_t>(b) * nh * hd + static_cast<size_t>(kvh * g + h) * hd + d] = __float2half_rn(t * inv[h]);
+    for (int w = 0; w < kAttnWarps; ++w) M = fmaxf(M, wm[w * g + h]);
+    float L = 0.f, A = 0.f;
+    if (M != -INFINITY) {
+#pragma unroll
+      for (int w = 0; w < kAttnWarps; ++w) {
+        const float mw = wm[w * g + h];
+        const float e = mw == -INFINITY ? 0.f : __expf(mw - M);
+        L = fmaf(wl[w * g + h], e, L);
+        A = fmaf(wacc[(w * g + h) * hd + d], e, A);
+      }
+    }
+    if (nsplit == 1) {
+      store_out(h, d, A / L);                              // the new position is always present: L > 0
+    } else if (rank == 0) {
+      cacc[h * hd + d] = A;
+      if (d == 0) { cm[h] = M; cl[h] = L; }
+    } else {
+      uint32_t w = __float_as_uint(A);
+      qb200::st_async<1>(r_cacc + (h * hd + d) * 4, &w, r_bar);
+      if (d == 0) {
+        w = __float_as_uint(M); qb200::st_async<1>(r_cm + h * 4, &w, r_bar);
+        w = __float_as_uint(L); qb200::st_async<1>(r_cl + h * 4, &w, r_bar);
+      }
+    }
+  }
+  if (nsplit == 1 || rank != 0) return;                    // outbound st.async data is in flight from registers
+
+  // CTA 0: wait for the other CTAs' triples, merge, store
+  qb200::cluster_wait();                                   // (pairs with the arrive at the top; every thread waits once)
+  if (tid == 0) qb200::mbar_arrive_expect_tx(bar, static_cast<uint32_t>((nsplit - 1) * (g * hd * 4 + g * 8)));
+  __syncthreads();                                         // own slot written
+  qb200::mbar_wait_cluster(bar, 0);
+  for (int idx = tid; idx < g * hd; idx += kAttnThreads) {
+    const int h = idx / hd, d = idx - h * hd;
+    float M = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < kAttnMaxSplit; ++r) if (r < nsplit) M = fmaxf(M, cm[r * g + h]);
+    float L = 0.f, A = 0.f;
+#pragma unroll
+    for (int r = 0; r < kAttnMaxSplit; ++r) {
+      if (r < nsplit) {
+        const float mr = cm[r * g + h];
+        const float e = mr == -INFINITY ? 0.f : __expf(mr - M);
+        L = fmaf(cl[r * g + h], e, L);
+        A = fmaf(cacc[(r * g + h) * hd + d], e, A);
+      }
+    }
+    store_out(h, d, A / L);
   }
 }
 
@@ -582,18 +707,6 @@ __global__ void silu_mul_pairs_kernel(const __half* __restrict__ gu, __half* __r
   *reinterpret_cast<uint4*>(act + idx) = o;
 }
 
-// Destination of a column slab that every rank needs (tensor parallel): the [rows][ld] buffers of all ranks at column
-// col0 — ONE multimem.st per 16-byte chunk through the NVSwitch multicast mapping when there is one, else a loop of
-// peer stores.
-struct PeerDst {
-  __half* peer[8];
-  __half* mc;
-  int n, ld, col0;
-};
-__device__ __forceinline__ void store16_all(const PeerDst& d, size_t off, uint4 v) {
-  if (d.mc != nullptr) qb200::multimem_st_v4(d.mc + off, v);
-  else for (int p = 0; p < d.n; ++p) *reinterpret_cast<uint4*>(d.peer[p] + off) = v;
-}
 // act[rows][I] = silu(g) * u of this rank's gate|up slab [rows][2 I], written to every rank's [rows][ld] activation
 // buffer at column col0 (the input of the column-parallel down projection), then published.
 __global__ void silu_mul_scatter_kernel(const __half* __restrict__ gu, size_t M, int I, const PeerDst dst, const qb200::PeerSignal sig) {
@@ -963,6 +1076,21 @@ void plan(int M, int K, int N, int split_hint, unsigned flags, int* tok_out, int
 }  // namespace
 
 namespace {
+int make_peer_dst(PeerDst* d, void* const* peers, void* mc, int n_peers, int ld, int col0, int width) {
+  if (n_peers < 1 || n_peers > 8 || peers == nullptr) return fail(QB200_EINVAL, "1..8 peer buffers required");
+  if (ld < col0 + width || col0 < 0 || (ld % 8) != 0 || (col0 % 8) != 0 || (width % 8) != 0) return fail(QB200_EINVAL, "bad ld / col0 / width");
+  for (int p = 0; p < 8; ++p) {
+    d->peer[p] = p < n_peers ? reinterpret_cast<__half*>(peers[p]) : nullptr;
+    if (p < n_peers && (peers[p] == nullptr || (reinterpret_cast<uintptr_t>(peers[p]) & 15))) return fail(QB200_EINVAL, "peer buffer %d is null or unaligned", p);
+  }
+  if (mc != nullptr && (reinterpret_cast<uintptr_t>(mc) & 15)) return fail(QB200_EINVAL, "multicast pointer unaligned");
+  d->mc = reinterpret_cast<__half*>(mc);
+  d->n = n_peers; d->ld = ld; d->col0 = col0;
+  return QB200_OK;
+}
+}  // namespace
+
+namespace {
 int gemm_impl(const void* A, const uint32_t* wq, const uint32_t* sz, const void* bias, const void* residual, void* C,
               void* const* C_peers, int n_peers, int ld_c, int col0, int M, int K, int N, int G, int tok, int split,
               unsigned flags, void* stream, const qb200_peer_wait* wait = nullptr, const qb200_peer_signal* signal = nullptr);
@@ -1298,18 +1426,38 @@ int qb200_attn_decode_smem_bytes(int nh, int nkv, int hd, int S) {
   if (nh <= 0 || nkv <= 0 || nh % nkv != 0 || (hd != 64 && hd != 128 && hd != 256) || S <= 0) return -1;
   const int grp = nh / nkv;
   if (grp != 1 && grp != 2 && grp != 4 && grp != 8) return -1;     // instantiated query-group sizes
-  const size_t need = attn_decode_smem(nh / nkv, hd, S);
-  return need <= 200 * 1024 ? static_cast<int>(need) : -1;
+  return static_cast<int>(attn_decode_smem(grp, hd));               // independent of the cache length
 }
+
+static int attn_decode_impl(const void* qkv, const void* cos_table, const void* sin_table, const long long* pos, void* out,
+                            void* cache_k, void* cache_v, int B, int nh, int nkv, int hd, int S, float scale, const PeerDst& dst,
+                            const qb200_peer_signal* signal, void* stream);
 
 int qb200_attn_decode(const void* qkv, const void* cos_table, const void* sin_table, const long long* pos, void* out,
                       void* cache_k, void* cache_v, int B, int nh, int nkv, int hd, int S, float scale, void* stream) {
+  PeerDst none{};
+  return attn_decode_impl(qkv, cos_table, sin_table, pos, out, cache_k, cache_v, B, nh, nkv, hd, S, scale, none, nullptr, stream);
+}
+
+int qb200_attn_decode_tp(const void* qkv, const void* cos_table, const void* sin_table, const long long* pos, void* cache_k,
+                         void* cache_v, int B, int nh, int nkv, int hd, int S, float scale, void* const* out_peers, int n_peers,
+                         int ld, int col0, const qb200_peer_signal* signal, void* stream) {
+  PeerDst d;
+  int rc = make_peer_dst(&d, out_peers, nullptr, n_peers, ld, col0, nh * hd);
+  if (rc) return rc;
+  return attn_decode_impl(qkv, cos_table, sin_table, pos, nullptr, cache_k, cache_v, B, nh, nkv, hd, S, scale, d, signal, stream);
+}
+
+static int attn_decode_impl(const void* qkv, const void* cos_table, const void* sin_table, const long long* pos, void* out,
+                            void* cache_k, void* cache_v, int B, int nh, int nkv, int hd, int S, float scale, const PeerDst& dst,
+                            const qb200_peer_signal* signal, void* stream) {
   const int smem = qb200_attn_decode_smem_bytes(nh, nkv, hd, S);
   if (B <= 0 || B > 65535 || smem < 0)
-    return fail(QB200_EINVAL, "attn_decode: needs nh / nkv in {1, 2, 4, 8}, hd in {64, 128, 256} and a cache that fits shared memory (g*S*4 bytes <= ~190 KB)");
+    return fail(QB200_EINVAL, "attn_decode: needs nh / nkv in {1, 2, 4, 8} and hd in {64, 128, 256}");
   if ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(cache_k) | reinterpret_cast<uintptr_t>(cache_v)) & 15)
     return fail(QB200_EINVAL, "attn_decode: pointers must be 16-byte aligned");
-  using AttnFn = void (*)(const __half*, const __half*, const __half*, const long long*, __half*, __half*, __half*, int, int, int, float);
+  using AttnFn = void (*)(const __half*, const __half*, const __half*, const long long*, __half*, __half*, __half*, int, int, int, float,
+                          int, const PeerDst, const qb200::PeerSignal);
   static const AttnFn table[3][4] = {
       {attn_decode_kernel<64, 1>, attn_decode_kernel<64, 2>, attn_decode_kernel<64, 4>, attn_decode_kernel<64, 8>},
       {attn_decode_kernel<128, 1>, attn_decode_kernel<128, 2>, attn_decode_kernel<128, 4>, attn_decode_kernel<128, 8>},
@@ -1319,20 +1467,42 @@ int qb200_attn_decode(const void* qkv, const void* cos_table, const void* sin_ta
   const int hi = hd == 64 ? 0 : hd == 128 ? 1 : 2, gi = grp == 1 ? 0 : grp == 2 ? 1 : grp == 4 ? 2 : 3;
   const AttnFn kfn = table[hi][gi];
   const int ki = hi * 4 + gi;
-  QB_CUDA(attr_once[ki].ensure([&] { return cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); }));
+  QB_CUDA(attr_once[ki].ensure([&] { return cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); }));
+  // Positions of one (kv head, sequence) split over a cluster of nsplit CTAs: enough CTAs to cover the SMs a few times
+  // over (the kernel is latency-bound: one round of row loads per warp is the goal), at least 32 cache positions each.
+  // The cache LENGTH decides, not the current position (a device value under CUDA-graph replay).
+  int nsplit = 1;
+  {
+    const char* env = std::getenv("QB200_ATTN_SPLIT");             // tests / tuning: force the cluster size
+    const int forced = env ? std::atoi(env) : 0;
+    const long long base = static_cast<long long>(nkv) * B;
+    const int target = 4 * device_sm_count();
+    while (nsplit < 8 && base * nsplit * 2 <= target && S / (nsplit * 2) >= 32) nsplit *= 2;
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8) nsplit = forced;
+  }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(nkv, B);
+  cfg.gridDim = dim3(nkv, B, nsplit);
   cfg.blockDim = dim3(kAttnThreads);
   cfg.dynamicSmemBytes = static_cast<size_t>(smem);
   cfg.stream = as_stream(stream);
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (nsplit > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = static_cast<unsigned>(nsplit);
+    ++na;
+  }
+  if (use_pdl()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = use_pdl() ? 1 : 0;
+  cfg.numAttrs = na;
   QB_CUDA(cudaLaunchKernelEx(&cfg, kfn, reinterpret_cast<const __half*>(qkv), reinterpret_cast<const __half*>(cos_table),
                              reinterpret_cast<const __half*>(sin_table), pos, reinterpret_cast<__half*>(out),
-                             reinterpret_cast<__half*>(cache_k), reinterpret_cast<__half*>(cache_v), nh, nkv, S, scale));
+                             reinterpret_cast<__half*>(cache_k), reinterpret_cast<__half*>(cache_v), nh, nkv, S, scale, nsplit, dst,
+                             make_signal(signal)));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return QB200_OK;
 }
@@ -1360,22 +1530,7 @@ int qb200_silu_mul_interleaved(const void* gate_up, void* act, long long rows, i
   return QB200_OK;
 }
 
-}  // extern "C"
-namespace {
-int make_peer_dst(PeerDst* d, void* const* peers, void* mc, int n_peers, int ld, int col0, int width) {
-  if (n_peers < 1 || n_peers > 8 || peers == nullptr) return fail(QB200_EINVAL, "1..8 peer buffers required");
-  if (ld < col0 + width || col0 < 0 || (ld % 8) != 0 || (col0 % 8) != 0 || (width % 8) != 0) return fail(QB200_EINVAL, "bad ld / col0 / width");
-  for (int p = 0; p < 8; ++p) {
-    d->peer[p] = p < n_peers ? reinterpret_cast<__half*>(peers[p]) : nullptr;
-    if (p < n_peers && (peers[p] == nullptr || (reinterpret_cast<uintptr_t>(peers[p]) & 15))) return fail(QB200_EINVAL, "peer buffer %d is null or unaligned", p);
-  }
-  if (mc != nullptr && (reinterpret_cast<uintptr_t>(mc) & 15)) return fail(QB200_EINVAL, "multicast pointer unaligned");
-  d->mc = reinterpret_cast<__half*>(mc);
-  d->n = n_peers; d->ld = ld; d->col0 = col0;
-  return QB200_OK;
-}
-}  // namespace
-extern "C" {
+
 
 int qb200_silu_mul_tp(const void* gate_up, long long rows, int I, void* const* act_peers, void* act_multicast, int n_peers, int ld,
                       int col0, const qb200_peer_signal* signal, void* stream) {

@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -235,6 +236,21 @@ def silu_mul_tp(gate_up: torch.Tensor, dst, col0: int) -> None:
     with torch.cuda.device(gate_up.device):
         _lib.check(lib.qb200_silu_mul_tp(_ptr(gate_up), rows, I, dst.buf_ptrs, dst.multicast_ptr, dst.world, dst.width, col0,
                                          C.byref(dst.signal), _stream_ptr()))
+
+
+def attn_decode_tp(qkv: torch.Tensor, cos_table: torch.Tensor, sin_table: torch.Tensor, pos: torch.Tensor, cache_k: torch.Tensor,
+                   cache_v: torch.Tensor, nh: int, nkv: int, dst, col0: int) -> None:
+    """qb200_attn_decode_tp: one-token attention of this rank's heads (rotary + KV-cache update + attention over the cache)
+    whose output [B, nh*hd] lands at column col0 of every rank's copy of dst (a GatheredBuffer)."""
+    _require_cuda(qkv, cache_k, cache_v)
+    lib = _lib.load()
+    B, S, hd = cache_k.shape[0], cache_k.shape[2], cache_k.shape[3]
+    assert qkv.is_contiguous() and qkv.dtype == torch.float16 and qkv.numel() == B * (nh + 2 * nkv) * hd
+    assert cache_k.is_contiguous() and cache_v.is_contiguous() and pos.dtype == torch.long and pos.numel() == 1
+    with torch.cuda.device(qkv.device):
+        _lib.check(lib.qb200_attn_decode_tp(_ptr(qkv), _ptr(cos_table), _ptr(sin_table), _ptr(pos), _ptr(cache_k), _ptr(cache_v), B, nh, nkv,
+                                            hd, S, float(np.float32(1.0) / np.sqrt(np.float32(hd))), dst.buf_ptrs, dst.world, dst.width, col0, C.byref(dst.signal),
+                                            _stream_ptr()))
 
 
 def scatter_cols(src: torch.Tensor, dst, col0: int) -> None:

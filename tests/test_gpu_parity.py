@@ -530,13 +530,42 @@ def test_attn_decode_matches_rope_cache_update_plus_sdpa(ops, nh, nkv, hd):
     beyond the current one hold NaN: they must never be read."""
     import quick_kernels
     import torch.nn.functional as F
-    S = 96
     g = torch.Generator(device="cuda").manual_seed(nh * 131 + nkv)
+    # cache lengths / forced cluster sizes: 96 positions -> the launcher's own choice (2 CTAs per kv head), 600 -> 8 CTAs per
+    # kv head, and every cluster size forced on the short cache (CTAs without positions, p = 0 included)
+    for S, split in ((96, None), (600, None), (96, 1), (96, 4), (96, 8)):
+        _attn_decode_case(nh, nkv, hd, S, split, g)
+    # unsupported shapes report so (the runner then keeps rope_kv_update + SDPA): group 16, group 3, head dim 96
+    assert not any(quick_kernels.attn_decode_supported(*c) for c in ((32, 2, 128, 96), (24, 8, 128, 96), (32, 8, 96, 96)))
+    assert quick_kernels.attn_decode_supported(64, 8, 128, 8192)        # no limit on the cache length
+    S = 96
+    cos = torch.zeros(S, hd, device="cuda", dtype=torch.float16)
+    with pytest.raises(Exception):
+        quick_kernels.attn_decode(torch.zeros(1, 2, (nh + 2 * nkv) * hd, device="cuda", dtype=torch.float16), cos, cos,
+                                  torch.tensor([0], device="cuda"), torch.zeros(1, nkv, S, hd, device="cuda", dtype=torch.float16),
+                                  torch.zeros(1, nkv, S, hd, device="cuda", dtype=torch.float16), nh, nkv)
+
+
+def _attn_decode_case(nh, nkv, hd, S, split, g):
+    import os
+    import quick_kernels
+    import torch.nn.functional as F
     inv = 1.0 / (10000.0 ** (torch.arange(0, hd, 2, device="cuda").float() / hd))
     ang = torch.outer(torch.arange(S, device="cuda").float(), inv)
     ang = torch.cat((ang, ang), dim=-1)
     cos, sin = ang.cos().half(), ang.sin().half()
     assert quick_kernels.attn_decode_supported(nh, nkv, hd, S)
+    if split is not None:
+        os.environ["QB200_ATTN_SPLIT"] = str(split)
+    try:
+        _attn_decode_positions(nh, nkv, hd, S, g, cos, sin)
+    finally:
+        os.environ.pop("QB200_ATTN_SPLIT", None)
+
+
+def _attn_decode_positions(nh, nkv, hd, S, g, cos, sin):
+    import quick_kernels
+    import torch.nn.functional as F
     for B in (1, 3):
         for p in (0, 1, 37, S - 1):
             qkv = torch.randn(B, 1, (nh + 2 * nkv) * hd, device="cuda", generator=g).half()
@@ -564,11 +593,6 @@ def test_attn_decode_matches_rope_cache_update_plus_sdpa(ops, nh, nkv, hd):
             sd = F.scaled_dot_product_attention(q, torch.nan_to_num(ck_ref), torch.nan_to_num(cv_ref), attn_mask=mask, enable_gqa=(nkv != nh))
             sd = sd.transpose(1, 2).reshape(B, 1, nh * hd)
             assert (out.float() - sd.float()).abs().max().item() <= 1e-2 * rms + 5e-4, f"B={B} p={p}: differs from the SDPA path"
-    # unsupported shapes report so (the runner then keeps rope_kv_update + SDPA): group 16, group 3, head dim 96, cache too long
-    assert not any(quick_kernels.attn_decode_supported(*c) for c in ((32, 2, 128, 96), (24, 8, 128, 96), (32, 8, 96, 96), (64, 8, 128, 8192)))
-    with pytest.raises(Exception):
-        quick_kernels.attn_decode(torch.zeros(1, 2, (nh + 2 * nkv) * hd, device="cuda", dtype=torch.float16), cos, sin,
-                                  torch.tensor([0], device="cuda"), ck_new[:1], cv_new[:1], nh, nkv)
 
 
 @pytest.mark.parametrize("K,I,G", [(512, 256, 128), (4096, 11008, 128), (1024, 1408 - 128, 64)], ids=["small", "llama7b_gate_up", "g64"])
