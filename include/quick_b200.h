@@ -108,6 +108,30 @@ int qb200_gemm_w4a16_fused(const void* A_fp16, const uint32_t* wq, const uint32_
                            const void* residual_fp16_or_null, void* C_fp16, int M, int K, int N, int G, int tok, int split,
                            unsigned flags, void* stream);
 
+/* RMSNorm folded around the GEMMs of a decoder layer (reference modules/fused/block.py:61-74 and
+ * norm.py:16-19 run norm -> linear as separate kernels).  With x·W' where x = rmsnorm(h) = h · rstd(h) ⊙ gamma:
+ *     rmsnorm(h) · W  ==  rstd(h) · ((h ⊙ gamma) · W)            (rstd is a per-row scalar),
+ * so the GEMM that PRODUCES h (o_proj / down_proj with the fused residual) also emits h ⊙ gamma and the row's sum of
+ * squares, and the GEMM that CONSUMES the normed rows scales its output rows by rstd — no RMSNorm kernel in between.
+ *   producer side:  gamma_fp16 [N] != NULL -> the epilogue writes C as usual, normed_out[M][N] = fp16(C ⊙ gamma) and
+ *                   ssq_out[N/128][M] (fp32): per 128-column tile, the sum of squares of the fp16 values stored to C
+ *                   (fixed summation order: bit-reproducible).  Not with QB200_GEMM_SILU_MUL / gathered outputs.
+ *   consumer side:  ssq_in [ssq_parts][M] != NULL (A is a producer's normed_out, ssq_parts = K / 128): every output row m
+ *                   becomes  rsqrt(sum_p ssq_in[p][m] / K + eps) · (A·W)[m] + bias  (then SiLU·up / residual as usual).
+ * Rounding differs from rmsnorm-then-GEMM only in where the fp16 roundings sit (one of h·gamma instead of one of
+ * h·rstd and one of ·gamma); tests bound it against the unfused pair.  Either side may be used alone. */
+typedef struct qb200_norm_fusion {
+  const void* gamma_fp16;   /* producer: weight of the RMSNorm that reads C next, or NULL */
+  void* normed_out_fp16;    /* producer: [M][N] */
+  float* ssq_out;           /* producer: [N/128][M] */
+  const float* ssq_in;      /* consumer: [ssq_parts][M], or NULL */
+  int ssq_parts;            /* consumer: K / 128 */
+  float eps;                /* consumer: the RMSNorm's epsilon */
+} qb200_norm_fusion;
+int qb200_gemm_w4a16_norm(const void* A_fp16, const uint32_t* wq, const uint32_t* sz, const void* bias_fp16_or_null,
+                          const void* residual_fp16_or_null, void* C_fp16, int M, int K, int N, int G, int tok, int split,
+                          unsigned flags, const qb200_norm_fusion* norm, void* stream);
+
 /* Fused GEMM + all-gather for column-parallel (tensor-parallel) linears: this rank computes its N output columns and the
  * epilogue stores the slab straight into the full-width buffers of ALL ranks — C_peers[r] is rank r's [rows][ld_c] buffer
  * mapped into this process (CUDA IPC / torch symmetric memory; C_peers[rank] is the local one), the slab lands at column

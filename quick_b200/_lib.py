@@ -15,7 +15,7 @@ SYMBOLS = [
     "qb200_version", "qb200_last_error", "qb200_wq_bytes", "qb200_sz_bytes", "qb200_check_shape",
     "qb200_relayout_from_quick", "qb200_pack_quick", "qb200_awq_gemm_to_quick", "qb200_relayout_from_awq_gemm",
     "qb200_dequantize", "qb200_gemm_w4a16",
-    "qb200_gemm_w4a16_cfg", "qb200_gemm_w4a16_ex", "qb200_gemm_w4a16_fused", "qb200_attn_decode", "qb200_attn_decode_smem_bytes", "qb200_rmsnorm", "qb200_rope_kv_update",
+    "qb200_gemm_w4a16_cfg", "qb200_gemm_w4a16_ex", "qb200_gemm_w4a16_fused", "qb200_gemm_w4a16_norm", "qb200_attn_decode", "qb200_attn_decode_smem_bytes", "qb200_rmsnorm", "qb200_rope_kv_update",
     "qb200_silu_mul", "qb200_silu_mul_interleaved", "qb200_gemm_w4a16_allgather", "qb200_peer_barrier",
     "qb200_gemm_w4a16_tp", "qb200_rmsnorm_tp", "qb200_silu_mul_tp", "qb200_scatter_cols", "qb200_attn_decode_tp", "qb200_gemm_plan", "qb200_gemm_plan_ex", "qb200_gemm_forward_quick", "qb200_gemm_w4a16_simt",
     "qb200_linear_create", "qb200_linear_forward_host", "qb200_linear_forward_host_async", "qb200_linear_synchronize",

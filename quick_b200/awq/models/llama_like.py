@@ -28,13 +28,17 @@ FUSED_GLUE = True
 # (qb200_attn_decode) instead of rope_kv_update + mask arithmetic + torch SDPA.  QB200_ATTN_DECODE=0 keeps the SDPA path.
 import os as _os0
 ATTN_DECODE = _os0.environ.get("QB200_ATTN_DECODE", "1") != "0"
-# Measured on B200, Llama-2-7B shapes, cache length 192 (profiles/r1e_*): +1.6 % decode tok/s at batch 1, +2.5 % at 8,
-# -4 % at 64 (one CTA per (kv head, sequence) re-reads nothing but also shares nothing; cuDNN's kernel wins once there
-# are thousands of rows) -> larger batches keep the SDPA path.
-ATTN_DECODE_MAX_BATCH = int(_os0.environ.get("QB200_ATTN_DECODE_MAX_BATCH", "16"))
-# One CTA streams the whole cache of its (kv head, sequence): measured at a cache of 192 positions only; long caches
-# want the positions split over several CTAs (flash-decoding), which SDPA does -> keep it for caches beyond this.
-ATTN_DECODE_MAX_CACHE = int(_os0.environ.get("QB200_ATTN_DECODE_MAX_CACHE", "1024"))
+# Measured on B200, Llama-2-7B shapes (round 2, cluster flash-decoding kernel; gpurun logs under profiles/r2b_*): against
+# the rope_kv_update + SDPA path the decode step is 17 % faster at batch 1, 10 % at 32, 6 % at 64 (cache 256), 8 % faster
+# at batch 1 with a 2048-position cache but 6 % slower at batch 8 there (a warp's serial chain of row batches grows with
+# the cache; cuDNN's split wins once there are thousands of long rows) -> long caches keep SDPA above a few sequences.
+ATTN_DECODE_MAX_BATCH = int(_os0.environ.get("QB200_ATTN_DECODE_MAX_BATCH", "64"))
+ATTN_DECODE_MAX_CACHE = int(_os0.environ.get("QB200_ATTN_DECODE_MAX_CACHE", "1024"))          # ... for batches above
+ATTN_DECODE_LONG_CACHE_BATCH = int(_os0.environ.get("QB200_ATTN_DECODE_LONG_CACHE_BATCH", "4"))  # ... this many sequences
+# RMSNorm folded around the GEMMs (qb200_gemm_w4a16_norm): o_proj / down_proj also emit h * gamma and the rows' sums of
+# squares, q|k|v and gate|up scale their rows by 1/rms — the two RMSNorm kernels of a layer disappear (single GPU;
+# the first layer's norm_1 and the final norm stay kernels).  QB200_NORM_FUSION=0 keeps the qb200_rmsnorm kernels.
+NORM_FUSION = _os0.environ.get("QB200_NORM_FUSION", "1") != "0"
 # SiLU(gate)·up inside the gate|up GEMM's epilogue (QB200_GEMM_SILU_MUL) instead of a separate qb200_silu_mul kernel.
 FUSED_SILU = _os0.environ.get("QB200_FUSED_SILU", "1") != "0"
 
@@ -221,7 +225,18 @@ def _linear(m: WQLinear_QUICK, x, ref_mod=None, residual=None):
     return out if residual is None else residual + out
 
 
+class NormCarry:
+    """What a layer's down_proj hands to the next layer when the RMSNorm is folded around the GEMMs: the hidden state
+    scaled by the next norm_1 weight and its rows' per-tile sums of squares (WQLinear_QUICK.forward_norm_out)."""
+    __slots__ = ("scaled", "ssq")
+
+    def __init__(self, scaled, ssq):
+        self.scaled, self.ssq = scaled, ssq
+
+
 class Block(nn.Module):
+    next_norm = None      # norm_1 of the following layer (set by the model; None for the last layer)
+
     def __init__(self, cfg: LlamaLikeConfig, dev, gen, batch: int, tp: Optional["TensorParallel"] = None, parts=None):
         """parts: {"qkv_proj", "o_proj", "gate_up_proj", "down_proj": WQLinear_QUICK, "norm_1", "norm_2": fp16 weight}
         taken from a loaded checkpoint (fuse_hf_model); without it the weights are random-init.
@@ -297,8 +312,20 @@ class Block(nn.Module):
         cfg = self.cfg
         B, T, _ = x.shape
         fused_decode = T == 1 and attn_mask is None
-        qkv = _linear(self.qkv_proj, self.norm_1(x), ref_mod)
+        # RMSNorm folded around the GEMMs: x_src carries (h * gamma_1, sums of squares) from the previous layer's down_proj
+        norm_fusion = NORM_FUSION and FUSED_GLUE and FUSED_SILU and x.is_cuda and ref_mod is None
+        if isinstance(x_src, NormCarry):
+            qkv = self.qkv_proj.forward_normed(x_src.scaled, x_src.ssq, self.norm_1.eps)
+        else:
+            qkv = _linear(self.qkv_proj, self.norm_1(x), ref_mod)
         o = self._attention(qkv, cos, sin, pos_idx, attn_mask, rope, fused_decode)
+        if norm_fusion:
+            x, xg, ssq = self.o_proj.forward_norm_out(o, x, self.norm_2.weight)
+            act = self.gate_up_proj.enable_silu_mul().forward_silu_mul(xg, ssq, self.norm_2.eps)
+            if self.next_norm is not None:
+                x, xg, ssq = self.down_proj.forward_norm_out(act, x, self.next_norm.weight)
+                return x, NormCarry(xg, ssq)
+            return _linear(self.down_proj, act, ref_mod, residual=x), None
         x = _linear(self.o_proj, o, ref_mod, residual=x)
         if FUSED_GLUE and FUSED_SILU and x.is_cuda and ref_mod is None:
             # SiLU(gate)·up inside the gate|up GEMM's epilogue (gate / up channels interleaved once, at first use)
@@ -393,6 +420,8 @@ class LlamaLikeQuickModel(nn.Module):
             self.norm = RMSNorm(cfg.hidden_size, cfg.rms_eps, dev)
             self.norm.weight.data = parts["norm"].detach().to(dev, torch.float16).contiguous()
             self.lm_head = parts["lm_head"]
+        for blk, nxt in zip(self.blocks[:-1], self.blocks[1:]):
+            blk.__dict__["next_norm"] = nxt.norm_1      # plain reference (not a registered submodule): norm folded around the GEMMs
         inv = 1.0 / (cfg.rope_theta ** (torch.arange(0, cfg.head_dim, 2, device=dev).float() / cfg.head_dim))
         ang = torch.outer(torch.arange(cfg.max_seq_len, device=dev).float(), inv)
         ang = torch.cat((ang, ang), dim=-1)
@@ -406,7 +435,8 @@ class LlamaLikeQuickModel(nn.Module):
         rope_kv_update + SDPA path."""
         cfg = self.cfg
         if not (ATTN_DECODE and FUSED_GLUE and x.is_cuda and x.shape[1] == 1 and x.shape[0] == self.batch
-                and self.batch <= ATTN_DECODE_MAX_BATCH and cfg.max_seq_len <= ATTN_DECODE_MAX_CACHE):
+                and self.batch <= ATTN_DECODE_MAX_BATCH
+                and (cfg.max_seq_len <= ATTN_DECODE_MAX_CACHE or self.batch <= ATTN_DECODE_LONG_CACHE_BATCH)):
             return False
         if self._attn_decode_supported is None:
             R = self.tp.world if self.tp is not None else 1      # tensor parallel: this rank's heads only
@@ -431,7 +461,7 @@ class LlamaLikeQuickModel(nn.Module):
         src = None        # tensor parallel, peer mode: the gathered buffer the hidden state lives in
         for blk in self.blocks:
             x, src = blk(x, cos, sin, pos_idx, attn_mask, self.ref_mod, (self.rope_cos, self.rope_sin), src)
-        if src is not None:
+        if src is not None and not isinstance(src, NormCarry):
             # the final norm is the consumer of the last gathered hidden state: it meets the ranks inside the kernel, so
             # it runs on all rows (no torch op may touch gathered rows before a wait) and the last position is sliced after
             from ... import ops

@@ -120,20 +120,51 @@ class WQLinear_QUICK(nn.Module):
         return self
 
     @torch.no_grad()
-    def forward_silu_mul(self, x):
-        """silu(gate(x)) * up(x) -> (..., out_features / 2), bit-identical to forward + qb200_silu_mul."""
+    def forward_silu_mul(self, x, ssq=None, eps=1e-6):
+        """silu(gate(x)) * up(x) -> (..., out_features / 2), bit-identical to forward + qb200_silu_mul.
+        ssq (fp32 [K/128, rows]): x is the gamma-scaled copy a ``forward_norm_out`` producer wrote — the RMSNorm in front
+        of this projection is applied inside the kernel (rows scaled by 1/rms before the SiLU)."""
         assert getattr(self, "gated_pairs", False), "call enable_silu_mul() first"
         wq, sz = self._b200
         x2d = x.reshape(-1, x.shape[-1])
-        if x2d.shape[0] > self.SILU_FUSED_MAX_ROWS:
-            # large token tiles: the epilogue's SiLU math would idle the tensor pipe (prefill -4 % measured on 7B shapes);
-            # run the GEMM plain (its output columns are the interleaved pairs) and one elementwise kernel behind it
-            from .... import ops
-            out = ops.silu_mul_interleaved(quick_kernels.gemm_forward_b200(x2d, wq, sz, self._pair_bias, self.out_features, self.group_size,
-                                                                            False, None, False))
+        fused = x2d.shape[0] <= self.SILU_FUSED_MAX_ROWS
+        # large token tiles: the epilogue's SiLU math would idle the tensor pipe (prefill -4 % measured on 7B shapes);
+        # run the GEMM plain (its output columns are the interleaved pairs) and one elementwise kernel behind it
+        if ssq is None:
+            out = quick_kernels.gemm_forward_b200(x2d, wq, sz, self._pair_bias, self.out_features, self.group_size, False, None, fused)
         else:
-            out = quick_kernels.gemm_forward_b200(x2d, wq, sz, self._pair_bias, self.out_features, self.group_size, False, None, True)
+            out = quick_kernels.gemm_forward_b200_norm(x2d, wq, sz, self._pair_bias, self.out_features, self.group_size, None, fused,
+                                                       None, ssq, eps)[0]
+        if not fused:
+            from .... import ops
+            out = ops.silu_mul_interleaved(out)
         return out.reshape(x.shape[:-1] + (self.out_features // 2,))
+
+    @torch.no_grad()
+    def forward_norm_out(self, x, residual, gamma):
+        """RMSNorm folded around the GEMMs (qb200_gemm_w4a16_norm, producer side): h = residual + linear(x) as ``forward``
+        does, plus what the RMSNorm with weight ``gamma`` that reads h next needs — returns (h, h * gamma in fp16,
+        per-128-column-tile sums of squares fp32 [out_features / 128, rows]).  Feed the last two to ``forward_normed`` /
+        ``forward_silu_mul(ssq=…)`` of the projection behind that norm."""
+        if getattr(self, "gated_pairs", False):
+            raise RuntimeError("forward_norm_out is not available on an interleaved gate|up module")
+        wq, sz = self._prepacked()
+        res2d = None if residual is None else residual.reshape(-1, self.out_features)
+        out, normed, ssq = quick_kernels.gemm_forward_b200_norm(x.reshape(-1, x.shape[-1]), wq, sz, self.bias, self.out_features,
+                                                                self.group_size, res2d, False, gamma, None, 0.0)
+        shape = x.shape[:-1] + (self.out_features,)
+        return out.reshape(shape), normed.reshape(shape), ssq
+
+    @torch.no_grad()
+    def forward_normed(self, x_gamma, ssq, eps, residual=None):
+        """Consumer side: linear(rmsnorm(h)) from a producer's (h * gamma, ssq) — rows scaled by 1/rms inside the kernel."""
+        if getattr(self, "gated_pairs", False):
+            raise RuntimeError("this gate|up module has interleaved output channels: use forward_silu_mul(ssq=...)")
+        wq, sz = self._prepacked()
+        res2d = None if residual is None else residual.reshape(-1, self.out_features)
+        out = quick_kernels.gemm_forward_b200_norm(x_gamma.reshape(-1, x_gamma.shape[-1]), wq, sz, self.bias, self.out_features,
+                                                   self.group_size, res2d, False, None, ssq, eps)[0]
+        return out.reshape(x_gamma.shape[:-1] + (self.out_features,))
 
     def release_quick_buffers(self, drop=False):
         """Inference-only deployments: keep the B200 copy on the GPU and move the QUICK-layout buffers (qweight /

@@ -1093,7 +1093,8 @@ int make_peer_dst(PeerDst* d, void* const* peers, void* mc, int n_peers, int ld,
 namespace {
 int gemm_impl(const void* A, const uint32_t* wq, const uint32_t* sz, const void* bias, const void* residual, void* C,
               void* const* C_peers, int n_peers, int ld_c, int col0, int M, int K, int N, int G, int tok, int split,
-              unsigned flags, void* stream, const qb200_peer_wait* wait = nullptr, const qb200_peer_signal* signal = nullptr);
+              unsigned flags, void* stream, const qb200_peer_wait* wait = nullptr, const qb200_peer_signal* signal = nullptr,
+              const qb200_norm_fusion* norm = nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1229,6 +1230,12 @@ int qb200_gemm_w4a16_fused(const void* A, const uint32_t* wq, const uint32_t* sz
   return gemm_impl(A, wq, sz, bias, residual, C, nullptr, 0, N, 0, M, K, N, G, tok, split, flags, stream);
 }
 
+int qb200_gemm_w4a16_norm(const void* A, const uint32_t* wq, const uint32_t* sz, const void* bias, const void* residual, void* C,
+                          int M, int K, int N, int G, int tok, int split, unsigned flags, const qb200_norm_fusion* norm,
+                          void* stream) {
+  return gemm_impl(A, wq, sz, bias, residual, C, nullptr, 0, N, 0, M, K, N, G, tok, split, flags, stream, nullptr, nullptr, norm);
+}
+
 int qb200_gemm_w4a16_allgather(const void* A, const uint32_t* wq, const uint32_t* sz, const void* bias, const void* residual,
                                void* const* C_peers, void* C_multicast, int n_peers, int ld_c, int col0, int M, int K, int N,
                                int G, int tok, int split, unsigned flags, void* stream) {
@@ -1262,7 +1269,8 @@ int qb200_gemm_w4a16_tp(const void* A, const uint32_t* wq, const uint32_t* sz, c
 namespace {
 int gemm_impl(const void* A, const uint32_t* wq, const uint32_t* sz, const void* bias, const void* residual, void* C,
               void* const* C_peers, int n_peers, int ld_c, int col0, int M, int K, int N, int G, int tok, int split,
-              unsigned flags, void* stream, const qb200_peer_wait* wait, const qb200_peer_signal* signal) {
+              unsigned flags, void* stream, const qb200_peer_wait* wait, const qb200_peer_signal* signal,
+              const qb200_norm_fusion* norm) {
   int rc = qb200_check_shape(M, K, N, G);
   if (rc) return rc;
   if (M == 0) return (wait || signal) ? fail(QB200_EINVAL, "tensor-parallel GEMM with M = 0") : QB200_OK;
@@ -1318,6 +1326,25 @@ int gemm_impl(const void* A, const uint32_t* wq, const uint32_t* sz, const void*
   args.flags = flags;
   args.wait = make_wait(wait);
   args.signal = make_signal(signal);
+  args.norm_gamma = nullptr; args.norm_out = nullptr; args.ssq_out = nullptr; args.ssq_in = nullptr; args.ssq_parts = 0; args.rms_eps = 0.f;
+  if (norm != nullptr && norm->gamma_fp16 != nullptr) {
+    if ((flags & (QB200_GEMM_SILU_MUL | QB200_GEMM_INDEPENDENT)) || n_peers > 0)
+      return fail(QB200_EINVAL, "fused RMSNorm (producer side) needs a plain local output: no SiLU, no gathered buffer, ordered launch");
+    if (norm->normed_out_fp16 == nullptr || norm->ssq_out == nullptr ||
+        ((reinterpret_cast<uintptr_t>(norm->gamma_fp16) | reinterpret_cast<uintptr_t>(norm->normed_out_fp16) | reinterpret_cast<uintptr_t>(C)) & 15))
+      return fail(QB200_EINVAL, "fused RMSNorm: gamma, normed_out (16-byte aligned) and ssq_out required");
+    args.norm_gamma = reinterpret_cast<const __half*>(norm->gamma_fp16);
+    args.norm_out = reinterpret_cast<__half*>(norm->normed_out_fp16);
+    args.ssq_out = norm->ssq_out;
+  }
+  if (norm != nullptr && norm->ssq_in != nullptr) {
+    if ((flags & QB200_GEMM_INDEPENDENT) || (wait != nullptr && wait->epoch != nullptr))
+      return fail(QB200_EINVAL, "fused RMSNorm (consumer side) needs an ordered, local launch");
+    if (norm->ssq_parts != K / 128 || K % 128 != 0) return fail(QB200_EINVAL, "fused RMSNorm: ssq_parts must be K / 128");
+    args.ssq_in = norm->ssq_in;
+    args.ssq_parts = norm->ssq_parts;
+    args.rms_eps = norm->eps;
+  }
   args.launch_id = static_cast<unsigned>(g_launches.load(std::memory_order_relaxed));
   args.trace = g_trace;
   cudaStream_t st = as_stream(stream);
@@ -1468,16 +1495,25 @@ static int attn_decode_impl(const void* qkv, const void* cos_table, const void* 
   const AttnFn kfn = table[hi][gi];
   const int ki = hi * 4 + gi;
   QB_CUDA(attr_once[ki].ensure([&] { return cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); }));
-  // Positions of one (kv head, sequence) split over a cluster of nsplit CTAs: enough CTAs to cover the SMs a few times
-  // over (the kernel is latency-bound: one round of row loads per warp is the goal), at least 32 cache positions each.
-  // The cache LENGTH decides, not the current position (a device value under CUDA-graph replay).
+  // Positions of one (kv head, sequence) split over a cluster of nsplit CTAs: the largest cluster for which every CTA of
+  // the launch is still resident at once (SMs x occupancy of this instantiation) — the kernel is latency-bound, a
+  // second wave costs more than shorter per-CTA ranges gain (tools/tune_attn.py) — and at least 16 cache positions per
+  // CTA.  The cache LENGTH decides, not the current position (a device value under CUDA-graph replay).
   int nsplit = 1;
   {
+    static int occ[12][64];                                          // CTAs per SM of the instantiation, per device
+    const int dev = current_device();
+    int* o = &occ[ki][dev >= 0 && dev < 64 ? dev : 0];
+    if (*o == 0) {
+      int n = 0;
+      QB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kfn, kAttnThreads, static_cast<size_t>(smem)));
+      *o = n > 0 ? n : 1;
+    }
+    const long long resident = static_cast<long long>(device_sm_count()) * *o;
+    const long long base = static_cast<long long>(nkv) * B;
+    while (nsplit < kAttnMaxSplit && base * nsplit * 2 <= resident && S / (nsplit * 2) >= 16) nsplit *= 2;
     const char* env = std::getenv("QB200_ATTN_SPLIT");             // tests / tuning: force the cluster size
     const int forced = env ? std::atoi(env) : 0;
-    const long long base = static_cast<long long>(nkv) * B;
-    const int target = 4 * device_sm_count();
-    while (nsplit < 8 && base * nsplit * 2 <= target && S / (nsplit * 2) >= 32) nsplit *= 2;
     if (forced == 1 || forced == 2 || forced == 4 || forced == 8) nsplit = forced;
   }
   cudaLaunchConfig_t cfg{};

@@ -178,6 +178,65 @@ torch::Tensor gemm_forward_b200(torch::Tensor in_feats, torch::Tensor wq, torch:
   return out;
 }
 
+// GEMM with an RMSNorm folded around it (C-ABI qb200_gemm_w4a16_norm, include/quick_b200.h):
+//   norm_gamma given -> producer side: returns {out, out ⊙ gamma (fp16 [M, N]), per-tile sums of squares (fp32 [N/128, M])}
+//   ssq_in given     -> consumer side: in_feats is a producer's gamma-scaled copy, rows are scaled by 1/rms before the bias
+std::vector<torch::Tensor> gemm_forward_b200_norm(torch::Tensor in_feats, torch::Tensor wq, torch::Tensor sz,
+                                                  c10::optional<torch::Tensor> bias, int64_t N, int64_t G,
+                                                  c10::optional<torch::Tensor> residual, bool silu_mul,
+                                                  c10::optional<torch::Tensor> norm_gamma, c10::optional<torch::Tensor> ssq_in,
+                                                  double eps) {
+  TORCH_CHECK(in_feats.dim() == 2 && in_feats.is_cuda(), "in_feats must be a 2-D CUDA tensor (there is no CPU path)");
+  const at::cuda::OptionalCUDAGuard device_guard(device_of(in_feats));
+  torch::Tensor x = in_feats.contiguous();
+  const int M = static_cast<int>(x.size(0)), K = static_cast<int>(x.size(1));
+  check(qb200_check_shape(M, K, static_cast<int>(N), static_cast<int>(G)));
+  TORCH_CHECK(static_cast<size_t>(wq.numel()) * 4 == qb200_wq_bytes(K, N), "wq size mismatch");
+  TORCH_CHECK(static_cast<size_t>(sz.numel()) * 4 == qb200_sz_bytes(K, N, G), "sz size mismatch");
+  const void* bias_ptr = nullptr;
+  torch::Tensor b, r, gam, sq;
+  if (bias.has_value() && bias->defined()) {
+    b = bias->contiguous();
+    TORCH_CHECK(b.numel() == N && b.scalar_type() == torch::kHalf, "bias must be fp16 [N]");
+    bias_ptr = b.data_ptr<at::Half>();
+  }
+  const void* res_ptr = nullptr;
+  if (residual.has_value() && residual->defined()) {
+    r = residual->contiguous();
+    TORCH_CHECK(r.numel() == static_cast<int64_t>(M) * N && r.scalar_type() == torch::kHalf && r.is_cuda(), "residual must be CUDA fp16 [M, N]");
+    res_ptr = r.data_ptr<at::Half>();
+  }
+  TORCH_CHECK(!(silu_mul && res_ptr != nullptr), "silu_mul takes no residual");
+  qb200_norm_fusion nf{};
+  torch::Tensor out = torch::empty({M, silu_mul ? N / 2 : N}, x.options());
+  std::vector<torch::Tensor> ret{out};
+  if (norm_gamma.has_value() && norm_gamma->defined()) {
+    gam = norm_gamma->contiguous();
+    TORCH_CHECK(gam.numel() == N && gam.scalar_type() == torch::kHalf && gam.is_cuda() && !silu_mul, "norm_gamma must be CUDA fp16 [N] (no silu_mul)");
+    torch::Tensor normed = torch::empty({M, N}, x.options());
+    torch::Tensor parts = torch::empty({N / 128, M}, x.options().dtype(torch::kFloat));
+    nf.gamma_fp16 = gam.data_ptr<at::Half>();
+    nf.normed_out_fp16 = normed.data_ptr<at::Half>();
+    nf.ssq_out = parts.data_ptr<float>();
+    ret.push_back(normed);
+    ret.push_back(parts);
+  }
+  if (ssq_in.has_value() && ssq_in->defined()) {
+    sq = ssq_in->contiguous();
+    TORCH_CHECK(sq.scalar_type() == torch::kFloat && sq.is_cuda() && sq.dim() == 2 && sq.size(0) == K / 128 && sq.size(1) == M,
+                "ssq_in must be CUDA fp32 [K/128, M]");
+    nf.ssq_in = sq.data_ptr<float>();
+    nf.ssq_parts = static_cast<int>(sq.size(0));
+    nf.eps = static_cast<float>(eps);
+  }
+  auto stream = at::cuda::getCurrentCUDAStream();
+  check(qb200_gemm_w4a16_norm(x.data_ptr<at::Half>(), reinterpret_cast<const uint32_t*>(wq.data_ptr<int>()),
+                              reinterpret_cast<const uint32_t*>(sz.data_ptr<int>()), bias_ptr, res_ptr, out.data_ptr<at::Half>(), M, K,
+                              static_cast<int>(N), static_cast<int>(G), /*tok*/ 0, /*split*/ 0, silu_mul ? QB200_GEMM_SILU_MUL : 0u, &nf,
+                              stream.stream()));
+  return ret;
+}
+
 // ---- decoder-layer glue (C-ABI qb200_rmsnorm / qb200_rope_kv_update / qb200_silu_mul) ----
 torch::Tensor rmsnorm(torch::Tensor x, torch::Tensor weight, double eps) {
   TORCH_CHECK(x.is_cuda() && x.scalar_type() == torch::kHalf && weight.scalar_type() == torch::kHalf, "rmsnorm: CUDA fp16 tensors required");
@@ -251,6 +310,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("rmsnorm", &rmsnorm, "RMSNorm (fp16 in/out, fp32 statistics)");
   m.def("rope_kv_update", &rope_kv_update, "rotary embedding of q/k + static KV-cache update; returns q [B, nh, T, hd]");
   m.def("silu_mul", &silu_mul, "silu(gate) * up for rows [gate | up]");
+  m.def("gemm_forward_b200_norm", &gemm_forward_b200_norm,
+        "GEMM with an RMSNorm folded around it: producer side (norm_gamma) returns [out, out*gamma, ssq parts], consumer side (ssq_in) scales rows by 1/rms",
+        py::arg("in_feats"), py::arg("wq"), py::arg("sz"), py::arg("bias"), py::arg("N"), py::arg("G"), py::arg("residual") = py::none(),
+        py::arg("silu_mul") = false, py::arg("norm_gamma") = py::none(), py::arg("ssq_in") = py::none(), py::arg("eps") = 1e-6);
   m.def("attn_decode", &attn_decode, "one-token attention fused with rotary embedding + static KV-cache update; returns [B, 1, nh*hd]");
   m.def("attn_decode_supported", [](int64_t nh, int64_t nkv, int64_t hd, int64_t S) {
     return qb200_attn_decode_smem_bytes(static_cast<int>(nh), static_cast<int>(nkv), static_cast<int>(hd), static_cast<int>(S)) >= 0;

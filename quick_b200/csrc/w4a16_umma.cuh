@@ -403,6 +403,7 @@ struct TileCfg {
   static_assert(kNI == 1 || kNB % kNumWG == 0, "two issuers: every free barrier must be observed by one dequant warpgroup");
   static constexpr int kNumBars = kDS + 2 * kNB + 2;
   static constexpr int kBarBytes = kNumBars * 8 + 16;
+  static constexpr int kRstdBytes = TOK * 4 + 128 + 16;        // fused RMSNorm (GemmArgs): per-token 1/rms + 128 B of sum-of-squares scratch
   static constexpr int kPipeBytes = kD2 * kXStageBytes + kDS * kWStage;
   // split-K exchange: TOK <= 64 sends register fragments with st.async straight into the owner's receive
   // buffer; larger tiles stage packed fp16 slices and move them with one TMA bulk DSMEM copy per owner.
@@ -417,7 +418,7 @@ struct TileCfg {
     return split > 1 ? (split - 1) * kChan * slice(split) * elem_bytes(split) : 0;
   }
   __host__ __device__ static constexpr int smem_bytes(int split) {
-    return kPipeBytes + kBarBytes + (kDedicatedRecv ? recv_bytes(split) + 16 : 0) + 1024;   // + 1024-B alignment slack
+    return kPipeBytes + kBarBytes + kRstdBytes + (kDedicatedRecv ? recv_bytes(split) + 16 : 0) + 1024;   // + 1024-B alignment slack
   }
   // two CTAs per SM: 233472 B per SM, 1 KB reserved per CTA
   static_assert(smem_bytes(4) <= 232448, "shared-memory budget (227 KB per CTA)");
@@ -516,6 +517,18 @@ struct GemmArgs {
   unsigned flags;     // QB200_GEMM_* (include/quick_b200.h)
   PeerWait wait;      // tensor parallel: A lives in a gathered buffer — meet its producers before the first load
   PeerSignal signal;  // tensor parallel: C is a gathered buffer — publish once every CTA has stored its slab
+  // RMSNorm folded around the GEMM (reference modules/fused/block.py:61-74, norm.py:16-19: norm -> linear).
+  //   producer side (C is the residual stream that an RMSNorm with weight gamma reads next): the epilogue also writes
+  //     norm_out = fp16(C * gamma) and, per 128-channel tile, the sum of squares of its C values per row
+  //     (ssq_out [N/128][M] fp32, fixed summation order: bit-reproducible);
+  //   consumer side (A is such a norm_out): every output row is scaled by rsqrt(sum of the row's ssq parts / K + eps)
+  //     before the bias — x·rstd·gamma·W == rstd · ((x·gamma)·W), so the RMSNorm kernel between the two GEMMs disappears.
+  const __half* norm_gamma;
+  __half* norm_out;
+  float* ssq_out;
+  const float* ssq_in;
+  int ssq_parts;
+  float rms_eps;
   unsigned launch_id; // host-side launch counter (QB200_TRACE builds: row of the cross-launch timeline)
   long long* trace;   // debug (QB200_TRACE builds only): clock64 stamps of CTA (0,0,0)
 };
@@ -669,22 +682,48 @@ __device__ __forceinline__ void stage_out(uint32_t smem_out, int row, int ch, in
     sts_u16(smem_out + static_cast<uint32_t>((row * kChan + ch) * 2), __half_as_ushort(__float2half_rn(acc)));
   }
 }
-// called by the 256 epilogue threads after the tile has been staged (and a barrier)
-__device__ __forceinline__ void store_tile(const GemmArgs& args, uint32_t smem_out, int rows, int m_base, int n0, bool silu_mul) {
+__device__ __forceinline__ uint4 hmul2x4(uint4 a, uint4 b) {
+  uint4 r;
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r.x) : "r"(a.x), "r"(b.x));
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r.y) : "r"(a.y), "r"(b.y));
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r.z) : "r"(a.z), "r"(b.z));
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r.w) : "r"(a.w), "r"(b.w));
+  return r;
+}
+__device__ __forceinline__ float sumsq8(uint4 v) {
+  const float2 a = unpack_half2(v.x), b = unpack_half2(v.y), c = unpack_half2(v.z), d = unpack_half2(v.w);
+  return ((a.x * a.x + a.y * a.y) + (b.x * b.x + b.y * b.y)) + ((c.x * c.x + c.y * c.y) + (d.x * d.x + d.y * d.y));
+}
+// called by the 256 epilogue threads after the tile has been staged (and a barrier); rows is even, so the two rows a warp
+// covers per iteration (16 lanes each) exist or not together and the shuffles below see full warps
+__device__ __forceinline__ void store_tile(const GemmArgs& args, uint32_t smem_out, int rows, int m_base, int n0, int nt, bool silu_mul) {
   const int tid = threadIdx.x;             // 0..255
   const int cpr = silu_mul ? 8 : 16;       // 16-byte chunks per staged row (128 B of products, or 256 B)
   const int chunk = tid % cpr;
   const int nbase = silu_mul ? (n0 >> 1) : n0;
+  const bool normed = args.norm_gamma != nullptr && !silu_mul;
+  uint4 gam = make_uint4(0, 0, 0, 0);
+  if (normed) gam = *reinterpret_cast<const uint4*>(args.norm_gamma + nbase + chunk * 8);
 #pragma unroll 1
   for (int row = tid / cpr; row < rows; row += (kEpilogueWarps * 32) / cpr) {
     const int m = m_base + row;
+    float sq = 0.f;
     if (m < args.M) {
       uint4 v = lds128(smem_out + static_cast<uint32_t>((row * cpr + chunk) * 16));
       const size_t off = static_cast<size_t>(m) * args.ldc + args.col0 + nbase + chunk * 8;
       if (args.residual != nullptr) v = hadd2x4(*reinterpret_cast<const uint4*>(args.residual + off), v);
+      if (normed) {   // fused RMSNorm, producer side (GemmArgs): gamma-scaled copy + sum of squares of the row's 128 channels
+        *reinterpret_cast<uint4*>(args.norm_out + off) = hmul2x4(v, gam);
+        sq = sumsq8(v);
+      }
       if (args.n_peers == 0) *reinterpret_cast<uint4*>(args.C + off) = v;
       else if (args.mcC != nullptr) multimem_st_v4(args.mcC + off, v);
       else for (int p = 0; p < args.n_peers; ++p) *reinterpret_cast<uint4*>(args.peerC[p] + off) = v;
+    }
+    if (normed) {     // 16 lanes = one row: fixed-order butterfly
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      if (chunk == 0 && m < args.M) args.ssq_out[static_cast<size_t>(nt) * args.M + m] = sq;
     }
   }
 }
@@ -736,7 +775,9 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
   const uint32_t bar_accum = bar_free + 8 * NB;                        // all MMAs of the tile done
   const uint32_t bar_recv = bar_accum + 8;                             // split-K partials from the other ranks landed
   const uint32_t tmem_ptr_smem = bar_recv + 8;
-  const uint32_t smem_recv = Cfg::kDedicatedRecv ? ((tmem_ptr_smem + 16 + 15) & ~15u) : smem_x;
+  const uint32_t smem_rstd = (tmem_ptr_smem + 16 + 15) & ~15u;         // [TOK] fp32
+  const uint32_t smem_ssq = smem_rstd + TOK * 4;                       // [8 warps][<= 4 rows] fp32 (producer side, direct stores)
+  const uint32_t smem_recv = Cfg::kDedicatedRecv ? ((smem_ssq + 128 + 15) & ~15u) : smem_x;
   const uint32_t smem_stage = Cfg::kDedicatedRecv ? smem_x : smem_x + kRecvBytes;   // bulk path only
   const uint32_t smem_out = kAsync ? smem_x : smem_stage + kRecvBytes;
 
@@ -1011,6 +1052,30 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
   const float bias_v = (args.bias != nullptr && is_epi) ? __half2float(args.bias[n0 + ch]) : 0.f;
   const int m_base = mt * TOK + rank * SLICE;
 
+  // Fused RMSNorm, consumer side: 1/rms of this tile's token rows from the producer's per-tile sums of squares (they are
+  // final once the previous grid has completed), computed while the last MMAs drain.  The 256 epilogue threads split
+  // into TOK tokens x P part-slices (P adjacent lanes per token): all of a thread's loads are independent (one round of
+  // L2 latency), the slices are added by a butterfly over the P lanes — a fixed order, bit-reproducible.
+  const bool has_rstd = args.ssq_in != nullptr;
+  if (has_rstd && is_epi) {
+    pdl_wait_prior_grid();
+    constexpr int P = (kEpilogueWarps * 32) / TOK >= 32 ? 16 : (kEpilogueWarps * 32) / TOK;   // 16, 8 (TOK 32), 4, 2, 1
+    constexpr int kTokPerPass = (kEpilogueWarps * 32) / P;
+    const int slice = threadIdx.x % P;
+#pragma unroll 1
+    for (int tk = threadIdx.x / P; tk < TOK; tk += kTokPerPass) {      // one pass unless TOK = 16 (P capped at 16)
+      float sq = 0.f;
+      if (tk < valid) {
+        const float* src = args.ssq_in + (mt * TOK + tk);
+#pragma unroll 8
+        for (int part = slice; part < args.ssq_parts; part += P) sq += __ldcg(src + static_cast<size_t>(part) * args.M);
+      }
+#pragma unroll
+      for (int o = P / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      if (slice == 0 && tk < valid) sts_u32(smem_rstd + tk * 4, __float_as_uint(rsqrtf(sq / static_cast<float>(args.K) + args.rms_eps)));
+    }
+    named_bar_sync(1, kEpilogueWarps * 32);
+  }
   if (is_epi) {
     mbar_wait(bar_accum, 0, 5, nst);   // every TMA write landed and every MMA read of this CTA's smem is complete
     tc_fence_after();
@@ -1066,7 +1131,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
         tmem_ld_acc<PIECE, kNI>(d_tmem + rank * SLICE + j0, TOK, has_d1, v);
         float acc[PIECE];
 #pragma unroll
-        for (int i = 0; i < PIECE; ++i) acc[i] = __uint_as_float(v[i]) + bias_v;
+        for (int i = 0; i < PIECE; ++i) acc[i] = __uint_as_float(v[i]) + (has_rstd ? 0.f : bias_v);
         if constexpr (SPLIT > 1) {
 #pragma unroll
           for (int r = 0; r < SPLIT - 1; ++r) {
@@ -1094,6 +1159,10 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
             }
           }
         }
+        if (has_rstd) {   // fused RMSNorm: scale the row by its 1/rms, then the bias
+#pragma unroll
+          for (int i = 0; i < PIECE; ++i) acc[i] = fmaf(acc[i], lds_f32(smem_rstd + (rank * SLICE + j0 + i) * 4), bias_v);
+        }
         if constexpr (kDirectStore) {
           // 32 lanes = 32 consecutive channels of one token row: 64-byte runs, no staging round trip
 #pragma unroll
@@ -1118,6 +1187,16 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
               const size_t off = static_cast<size_t>(m) * args.ldc + args.col0 + n0 + ch;
               __half h = __float2half_rn(acc[i]);
               if (args.residual != nullptr) h = __hadd(args.residual[off], h);
+              if (args.norm_gamma != nullptr) {
+                // fused RMSNorm, producer side: gamma-scaled copy + this warp's (32 channels) sum of squares of the row;
+                // the four warps of the warpgroup (= the tile's 128 channels) are added in a fixed order below
+                args.norm_out[off] = __hmul(h, args.norm_gamma[n0 + ch]);
+                const float hf = __half2float(h);
+                float sq = hf * hf;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                if (lane == 0) sts_u32(smem_ssq + ((wg * 4 + quad) * PIECE + i) * 4, __float_as_uint(sq));
+              }
               if (args.n_peers == 0) {
                 args.C[off] = h;
               } else if (args.mcC != nullptr) {
@@ -1130,6 +1209,16 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
               }
             }
           }
+          if (args.norm_gamma != nullptr) {
+            static_assert(!kDirectStore || PIECE == CH, "direct store: one piece per thread");
+            named_bar_sync(3 + wg, 128);          // the warpgroup's four warps (ids 3 + wg: the dequant loop is over)
+            if (quad == 0 && lane < PIECE && m_base + j0 + lane < args.M) {
+              float sq = 0.f;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) sq += lds_f32(smem_ssq + ((wg * 4 + q) * PIECE + lane) * 4);
+              args.ssq_out[static_cast<size_t>(nt) * args.M + m_base + j0 + lane] = sq;
+            }
+          }
         } else {
 #pragma unroll
           for (int i = 0; i < PIECE; ++i)
@@ -1138,7 +1227,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
       }
       if constexpr (!kDirectStore) {
         named_bar_sync(1, kEpilogueWarps * 32);
-        store_tile(args, smem_out, SLICE, m_base, n0, silu_mul);
+        store_tile(args, smem_out, SLICE, m_base, n0, nt, silu_mul);
       }
       if (threadIdx.x == 0) QB_TRACE(3, 0, 3);
     }
@@ -1204,7 +1293,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
         tmem_ld_acc<PIECE, kNI>(d_tmem + rank * SLICE + j0, TOK, has_d1, v);
         float acc[PIECE];
 #pragma unroll
-        for (int i = 0; i < PIECE; ++i) acc[i] = __uint_as_float(v[i]) + bias_v;
+        for (int i = 0; i < PIECE; ++i) acc[i] = __uint_as_float(v[i]) + (has_rstd ? 0.f : bias_v);
         if constexpr (SPLIT > 1) {
 #pragma unroll
           for (int r = 0; r < SPLIT - 1; ++r) {
@@ -1219,6 +1308,10 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
             }
           }
         }
+        if (has_rstd) {
+#pragma unroll
+          for (int i = 0; i < PIECE; ++i) acc[i] = fmaf(acc[i], lds_f32(smem_rstd + (rank * SLICE + j0 + i) * 4), bias_v);
+        }
 #pragma unroll
         for (int i = 0; i < PIECE; ++i)
           stage_out(smem_out, j0 + i, ch, lane, acc[i], silu_mul);
@@ -1229,7 +1322,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmArgs arg
       // lane's wait (its X loads fed the MMAs whose completion barrier these warps have observed), i.e. after the
       // previous grid has completed and flushed; in independent mode the caller has declared C unrelated.
       // coalesced 16-byte stores: 16 threads cover one 256-byte token row of the tile
-      store_tile(args, smem_out, SLICE, m_base, n0, silu_mul);
+      store_tile(args, smem_out, SLICE, m_base, n0, nt, silu_mul);
       if (threadIdx.x == 0) QB_TRACE(3, 0, 3);
     }
     if constexpr (SPLIT > 1) cluster_wait();

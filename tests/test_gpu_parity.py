@@ -627,3 +627,58 @@ def test_silu_mul_fused_into_the_gate_up_epilogue_is_bit_identical(ops, K, I, G)
     y = A.double() @ W16.double()
     g, u = y[:, :I].half().double(), y[:, I:].half().double()
     assert_close(ops.gemm_tp(A, wq_i, sz_i, N, G, silu_mul=True), (g / (1 + torch.exp(-g))) * u, "fused SwiGLU vs fp64")
+
+
+@pytest.mark.parametrize("H,I,G", [(512, 384, 128), (4096, 11008, 128), (1024, 640, 64)], ids=["small", "llama7b", "g64"])
+def test_rmsnorm_folded_around_the_gemms(ops, H, I, G):
+    """SURVEY §8 f4 / reference modules/fused/block.py:61-74 + norm.py:16-19 (x + o_proj(...) -> RMSNorm -> gate|up):
+    qb200_gemm_w4a16_norm — the producing GEMM (residual fused) also emits h * gamma and per-tile sums of squares, the
+    consuming GEMM scales its rows by 1/rms — against the unfused sequence GEMM -> qb200_rmsnorm -> GEMM (+ SiLU·up) and
+    against the fp64 definition.  h must be bit-identical, h * gamma must be torch's fp16 product, the sums of squares the
+    fp32 sums of h² per 128-column tile, and the consumer's output within fp16 rounding of both references, for every
+    tile configuration the planner picks (direct stores, staged tiles, one and several token tiles)."""
+    import quick_kernels
+    from quick_b200.awq.modules.linear.quick import WQLinear_QUICK
+    eps = 1e-5
+    gen = torch.Generator(device="cuda").manual_seed(H + I)
+    _, _, _, qw1, qz1, sc1, Wp = make_gpu_case(ops, H, H, G, seed=11)             # producer: an o_proj-like H -> H linear
+    _, _, _, qw2, qz2, sc2, Wc = make_gpu_case(ops, H, 2 * I, G, seed=12)         # consumer: gate|up, H -> 2 I
+    prod, cons, cons_silu = (WQLinear_QUICK(4, G, H, n, False, "cuda") for n in (H, 2 * I, 2 * I))
+    prod.qweight, prod.qzeros, prod.scales = qw1, qz1, sc1
+    for m in (cons, cons_silu):
+        m.qweight, m.qzeros, m.scales = qw2, qz2, sc2
+    cons_silu.enable_silu_mul()
+    gamma = (1.0 + 0.2 * torch.randn(H, device="cuda", generator=gen)).half()
+    for M in (1, 3, 8, 16, 17, 64, 100, 300):
+        a = torch.from_numpy(qo.make_activations(M, H, seed=M)).cuda()
+        res = torch.randn(M, H, device="cuda", generator=gen).half()
+        h_ref = prod(a, res)
+        h, hg, ssq = prod.forward_norm_out(a, res, gamma)
+        assert torch.equal(h, h_ref), M
+        assert torch.equal(hg, h_ref * gamma), M
+        assert ssq.shape == (H // 128, M) and ssq.dtype == torch.float32
+        want_ssq = h_ref.float().pow(2).view(M, H // 128, 128).sum(-1).t()
+        assert torch.allclose(ssq, want_ssq, rtol=1e-5, atol=0), M
+        # the unfused sequence and the fp64 definition of norm -> linear
+        xn = quick_kernels.rmsnorm(h_ref, gamma, eps)
+        hd = h_ref.double()
+        xn64 = hd * torch.rsqrt(hd.pow(2).mean(-1, keepdim=True) + eps) * gamma.double()
+        y_unfused, y64 = cons(xn), xn64 @ Wc.double()
+        y = cons.forward_normed(hg, ssq, eps)
+        assert_close(y, y64, f"M={M} fused norm -> linear vs fp64")
+        rms = y64.pow(2).mean().sqrt().item()
+        # against the unfused kernels: the fp16 roundings of the normed inputs sit in different places (h * gamma vs
+        # h * rstd, then * gamma) and the outputs are rounded independently -> half a percent, relative + rms floor
+        diff = (y.double() - y_unfused.double()).abs()
+        assert bool((diff <= 5e-3 * y_unfused.double().abs() + 5e-3 * rms).all()), f"M={M}: differs from rmsnorm kernel + GEMM by {diff.max().item():.3g}"
+        # consumer with SiLU·up in the epilogue
+        g64, u64 = y64[:, :I].half().double(), y64[:, I:].half().double()
+        act = cons_silu.forward_silu_mul(hg, ssq, eps)
+        assert_close(act, (g64 / (1 + torch.exp(-g64))) * u64, f"M={M} fused norm -> gate|up -> SiLU·up vs fp64")
+        assert torch.equal(act, quick_kernels.silu_mul(y)), M      # same rows, same rounding as the unfused SiLU kernel
+        # determinism (fixed summation order everywhere)
+        h2, hg2, ssq2 = prod.forward_norm_out(a, res, gamma)
+        assert torch.equal(ssq2, ssq) and torch.equal(cons.forward_normed(hg2, ssq2, eps), y)
+    # argument checks: producer side refuses SiLU outputs
+    with pytest.raises(Exception):
+        quick_kernels.gemm_forward_b200_norm(a, *cons_silu._b200, None, 2 * I, G, None, True, gamma, None, eps)
