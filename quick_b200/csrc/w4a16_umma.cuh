@@ -704,7 +704,7 @@ __device__ __forceinline__ void store_tile(const GemmArgs& args, uint32_t smem_o
   const bool normed = args.norm_gamma != nullptr && !silu_mul;
   uint4 gam = make_uint4(0, 0, 0, 0);
   if (normed) gam = *reinterpret_cast<const uint4*>(args.norm_gamma + nbase + chunk * 8);
-#pragma unroll 1
+#pragma unroll 4
   for (int row = tid / cpr; row < rows; row += (kEpilogueWarps * 32) / cpr) {
     const int m = m_base + row;
     float sq = 0.f;
