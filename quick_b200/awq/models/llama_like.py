@@ -33,6 +33,9 @@ ATTN_DECODE = _os0.environ.get("QB200_ATTN_DECODE", "1") != "0"
 # at batch 1 with a 2048-position cache but 6 % slower at batch 8 there (a warp's serial chain of row batches grows with
 # the cache; cuDNN's split wins once there are thousands of long rows) -> long caches keep SDPA above a few sequences.
 ATTN_DECODE_MAX_BATCH = int(_os0.environ.get("QB200_ATTN_DECODE_MAX_BATCH", "64"))
+# grouped-query shapes (>= 4 query heads per kv head: the fp32 score path is instruction-bound there; Mistral-7B at batch
+# 64: -6 % against SDPA, +2.5 % at 32)
+ATTN_DECODE_MAX_BATCH_GQA = int(_os0.environ.get("QB200_ATTN_DECODE_MAX_BATCH_GQA", "32"))
 ATTN_DECODE_MAX_CACHE = int(_os0.environ.get("QB200_ATTN_DECODE_MAX_CACHE", "1024"))          # ... for batches above
 ATTN_DECODE_LONG_CACHE_BATCH = int(_os0.environ.get("QB200_ATTN_DECODE_LONG_CACHE_BATCH", "4"))  # ... this many sequences
 # RMSNorm folded around the GEMMs (qb200_gemm_w4a16_norm): o_proj / down_proj also emit h * gamma and the rows' sums of
@@ -435,7 +438,7 @@ class LlamaLikeQuickModel(nn.Module):
         rope_kv_update + SDPA path."""
         cfg = self.cfg
         if not (ATTN_DECODE and FUSED_GLUE and x.is_cuda and x.shape[1] == 1 and x.shape[0] == self.batch
-                and self.batch <= ATTN_DECODE_MAX_BATCH
+                and self.batch <= (ATTN_DECODE_MAX_BATCH if cfg.num_heads // cfg.num_kv_heads < 4 else ATTN_DECODE_MAX_BATCH_GQA)
                 and (cfg.max_seq_len <= ATTN_DECODE_MAX_CACHE or self.batch <= ATTN_DECODE_LONG_CACHE_BATCH)):
             return False
         if self._attn_decode_supported is None:
