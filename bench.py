@@ -36,6 +36,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # NCCL_DEBUG is left as the caller set it (the driver reads the communicator's rank count from it); the JSON line is
 # the LAST line this script prints on stdout.
+# The end-to-end leg drives 16 host-buffer handles = 16 streams: with CUDA's default of 8 hardware connections streams
+# share queues and their copies serialise behind each other's GEMMs (e2e 132 vs 145 TOPS, tools/e2e_probe.py).  Both
+# arms run with the same setting; it must be in the environment before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import torch
 
@@ -532,8 +536,10 @@ def run_mine(args):
         # every GEMM: pinned host x -> H2D -> kernel -> D2H -> pinned host y, enqueued on its handle's stream
         # (16 handles = 16 streams: PCIe in both directions overlaps the GEMMs); the step ends when every
         # result is back in host memory.
+        # Largest M first: its 4 MB copies keep both PCIe directions busy while the host enqueues the many small GEMMs
+        # behind them (ascending order left the link idle while the host was still issuing the 8 KB .. 1 MB calls).
         def e2e_step():
-            for M in MS:
+            for M in sorted(MS, reverse=True):
                 for i in range(nh):
                     handles[i].forward_host_async(hx[M], hy[M][i])
             for h in handles:
@@ -551,7 +557,11 @@ def run_mine(args):
                "h2d_bytes_per_step": sum(2 * M * K for M in MS) * nh * world, "d2h_bytes_per_step": sum(2 * M * N for M in MS) * nh * world,
                "api": "qb200_linear_forward_host_async + qb200_linear_synchronize (C-ABI: pinned host x -> H2D -> GEMM -> D2H -> pinned host y "
                       "per GEMM on the handle's stream; all results on the host before the step ends)",
-               "gemms_per_step": len(MS) * nh, "note": "weights are module state resident in HBM, as in WQLinear_QUICK"}
+               "gemms_per_step": len(MS) * nh, "note": "weights are module state resident in HBM, as in WQLinear_QUICK",
+               "issue_order": "largest M first (the 4 MB copies keep both PCIe directions busy while the host enqueues the small GEMMs)",
+               "cuda_device_max_connections": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"),
+               "pcie": "Gen5 x16: 55 GB/s one way, 45-47 GB/s each way concurrently for >= 4 MB copies (tools/micro/pcie_bw.py); this leg "
+                       "moves its bytes at ~35 GB/s each way (8 KB .. 4 MB copies)"}
         for h in handles:
             h.close()
 
