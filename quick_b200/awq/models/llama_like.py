@@ -42,6 +42,10 @@ ATTN_DECODE_LONG_CACHE_BATCH = int(_os0.environ.get("QB200_ATTN_DECODE_LONG_CACH
 # squares, q|k|v and gate|up scale their rows by 1/rms — the two RMSNorm kernels of a layer disappear (single GPU;
 # the first layer's norm_1 and the final norm stay kernels).  QB200_NORM_FUSION=0 keeps the qb200_rmsnorm kernels.
 NORM_FUSION = _os0.environ.get("QB200_NORM_FUSION", "1") != "0"
+# Prefill through a CUDA graph once a (batch, length) shape repeats (forward()); QB200_PREFILL_GRAPH=0 keeps it eager.
+PREFILL_GRAPH = _os0.environ.get("QB200_PREFILL_GRAPH", "1") != "0"
+PREFILL_GRAPH_MAX_ROWS = int(_os0.environ.get("QB200_PREFILL_GRAPH_MAX_ROWS", "4096"))   # above: GPU-bound anyway
+PREFILL_GRAPH_KEEP = 4
 # SiLU(gate)·up inside the gate|up GEMM's epilogue (QB200_GEMM_SILU_MUL) instead of a separate qb200_silu_mul kernel.
 FUSED_SILU = _os0.environ.get("QB200_FUSED_SILU", "1") != "0"
 
@@ -406,6 +410,7 @@ class LlamaLikeQuickModel(nn.Module):
         super().__init__()
         self.cfg, self.batch = cfg, batch
         self._decode_graph = None
+        self._prefill_graphs = {}         # (shape, all_logits) -> CUDA graph of a multi-token forward, see forward()
         self._attn_decode_supported = None
         self.start_pos = 0        # next free cache slot for the stateful HF-style calls (fuse_hf_model) and generate()
         import torch.distributed as dist
@@ -450,7 +455,43 @@ class LlamaLikeQuickModel(nn.Module):
     @torch.no_grad()
     def forward(self, input_ids: torch.Tensor, pos_idx: torch.Tensor, all_logits: bool = False):
         """input_ids (B, T); pos_idx (T,) int64 device tensor of the cache positions being written.  Returns the logits
-        of the last position (B, 1, V), or of every position with all_logits (perplexity-style evaluation)."""
+        of the last position (B, 1, V), or of every position with all_logits (perplexity-style evaluation).
+        Multi-token calls (prefill) of up to PREFILL_GRAPH_MAX_ROWS rows are host-bound when run eagerly (≈ 270 launches
+        for a 7B model); a (batch, length) shape seen for the second time is captured into a CUDA graph and replayed from
+        then on (a few shapes are kept)."""
+        if (PREFILL_GRAPH and input_ids.is_cuda and input_ids.dim() == 2 and input_ids.shape[1] > 1 and self.tp is None
+                and self.ref_mod is None and input_ids.numel() <= PREFILL_GRAPH_MAX_ROWS and pos_idx.is_cuda
+                and not torch.cuda.is_current_stream_capturing()):
+            return self._forward_prefill_graphed(input_ids, pos_idx, all_logits)
+        return self._forward(input_ids, pos_idx, all_logits)
+
+    def _forward_prefill_graphed(self, input_ids, pos_idx, all_logits):
+        # the module-level switches (and a monkey-patched _linear: the tests' dense reference) select different kernels
+        key = (tuple(input_ids.shape), bool(all_logits), FUSED_GLUE, FUSED_SILU, NORM_FUSION, id(_linear))
+        st = self._prefill_graphs.get(key)
+        if st is None:                                   # first sighting: run eagerly, remember the shape
+            self._prefill_graphs[key] = {"graph": None}
+            while len(self._prefill_graphs) > PREFILL_GRAPH_KEEP:
+                self._prefill_graphs.pop(next(iter(self._prefill_graphs)))
+            return self._forward(input_ids, pos_idx, all_logits)
+        if st["graph"] is None:                          # second sighting: capture
+            dev = input_ids.device
+            st["ids"], st["pos"] = input_ids.clone(), pos_idx.clone()
+            torch.cuda.synchronize(dev)
+            side, graph = torch.cuda.Stream(dev), torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                self._forward(st["ids"], st["pos"], all_logits)          # warm-up on the capture stream (idempotent)
+                torch.cuda.synchronize(dev)
+                with torch.cuda.graph(graph, stream=side):
+                    st["out"] = self._forward(st["ids"], st["pos"], all_logits)
+            torch.cuda.synchronize(dev)
+            st["graph"] = graph
+        st["ids"].copy_(input_ids)
+        st["pos"].copy_(pos_idx)
+        st["graph"].replay()
+        return st["out"].clone()                         # the graph's output buffer is reused by the next replay
+
+    def _forward(self, input_ids: torch.Tensor, pos_idx: torch.Tensor, all_logits: bool = False):
         cfg = self.cfg
         x = self.embed(input_ids)
         if self._fused_decode_ok(x):
