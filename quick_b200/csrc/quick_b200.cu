@@ -1065,6 +1065,10 @@ void plan(int M, int K, int N, int split_hint, unsigned flags, int* tok_out, int
       const long cost = waves2 * (stages * 600L + 2500L + 300L * (s - 1));
       if (best < 0 || cost < best) { best = cost; split = s; }
     }
+    // More tiles than CTA slots (Llama-2-70B gate|up on one GPU: 448 tiles, K = 8192): the model over-rates the fixed
+    // cost of a CTA once the SMs are throughput-bound (a starting CTA's prologue overlaps its neighbour's streaming);
+    // measured 77.9 us unsplit vs 70.1 with split 2 (tools/tune_shapes.py, SHAPES=70b).
+    if (split == 1 && tiles > slots && KB >= 64) split = 2;
   } else {
     // one CTA per SM: grow the cluster while the grid still under-fills the machine and every rank keeps >= 4 k-blocks
     while (split * 2 <= max_split && tiles * split * 2 <= sms + sms / 4 && KB / (split * 2) >= 4) split *= 2;
