@@ -26,6 +26,8 @@ def time_graph(fn_i, n_launch, reps=10):
         best = min(best, a.elapsed_time(b) * 1e-3 / (reps * n_launch))
     return best
 shapes = [(4096, 12288), (4096, 22016), (11008, 4096), (4096, 4096), (8192, 1280), (8192, 7168), (28672, 1024)]
+if os.environ.get("SHAPES") == "mistral":     # Mistral-7B: q|k|v (GQA), gate|up, down
+    shapes = [(4096, 6144), (4096, 28672), (14336, 4096)]
 if os.environ.get("SHAPES") == "70b":     # Llama-2-70B on one GPU and its 2 / 4-GPU shards (q|k|v, o, gate|up, down)
     shapes = [(8192, 10240), (8192, 8192), (8192, 57344), (28672, 8192), (8192, 5120), (8192, 4096), (8192, 28672), (28672, 4096),
               (8192, 2560), (8192, 2048), (8192, 14336), (28672, 2048)]
