@@ -682,3 +682,42 @@ def test_rmsnorm_folded_around_the_gemms(ops, H, I, G):
     # argument checks: producer side refuses SiLU outputs
     with pytest.raises(Exception):
         quick_kernels.gemm_forward_b200_norm(a, *cons_silu._b200, None, 2 * I, G, None, True, gamma, None, eps)
+
+
+def test_attn_decode_tp_stores_the_heads_into_every_peer_buffer(ops):
+    """qb200_attn_decode_tp (tensor parallel: this rank's heads, output stored straight into every rank's attention
+    buffer) with local buffers standing in for the peers: every destination receives exactly what qb200_attn_decode
+    returns at column col0 of its ld-wide rows, nothing else is written, the epoch of the gathered buffer advances and
+    the KV-cache update is the same."""
+    import ctypes as C
+    import quick_kernels
+    from quick_b200 import _lib
+    nh, nkv, hd, S, p = 8, 4, 128, 160, 77
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    ang = torch.outer(torch.arange(S, device="cuda").float(), 1.0 / (10000.0 ** (torch.arange(0, hd, 2, device="cuda").float() / hd)))
+    ang = torch.cat((ang, ang), dim=-1)
+    cos, sin = ang.cos().half(), ang.sin().half()
+
+    class FakeGathered:          # the fields ops.attn_decode_tp reads of a parallel.GatheredBuffer
+        def __init__(self, bufs, width):
+            self.world, self.width = len(bufs), width
+            self.buf_ptrs = (C.c_void_p * len(bufs))(*[b.data_ptr() for b in bufs])
+            self.state = torch.zeros(1, dtype=torch.int32, device="cuda")
+            self.signal = _lib.PeerSignal(self.state.data_ptr())
+
+    for B in (1, 5):
+        qkv = torch.randn(B, 1, (nh + 2 * nkv) * hd, device="cuda", generator=gen).half()
+        ck = torch.randn(B, nkv, S, hd, device="cuda", generator=gen).half()
+        cv = torch.randn(B, nkv, S, hd, device="cuda", generator=gen).half()
+        pos = torch.tensor([p], device="cuda")
+        ck1, cv1, ck2, cv2 = ck.clone(), cv.clone(), ck.clone(), cv.clone()
+        want = quick_kernels.attn_decode(qkv, cos, sin, pos, ck1, cv1, nh, nkv).view(B, nh * hd)
+        ld, col0 = 3 * nh * hd, nh * hd
+        bufs = [torch.full((B, ld), 3.0, device="cuda", dtype=torch.float16) for _ in range(3)]
+        dst = FakeGathered(bufs, ld)
+        ops.attn_decode_tp(qkv, cos, sin, pos, ck2, cv2, nh, nkv, dst, col0)
+        torch.cuda.synchronize()
+        for b in bufs:
+            assert torch.equal(b[:, col0:col0 + nh * hd], want), B
+            assert (b[:, :col0] == 3).all() and (b[:, col0 + nh * hd:] == 3).all()
+        assert torch.equal(ck1, ck2) and torch.equal(cv1, cv2) and dst.state.item() == 1
