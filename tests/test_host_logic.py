@@ -113,6 +113,24 @@ def test_gemm_plan_fills_the_machine(built):
         assert isplit == 1 and itok >= min(M, 256) and ictas == (4096 // 128) * -(-M // itok)
 
 
+def test_gemm_plan_picks_the_measured_optimum_for_the_layer_shapes(built):
+    """Planner vs the split sweeps on B200 (tools/tune_shapes.py, profiles/r2b_tune_shapes_70b.log, r2g_tune_*): the
+    choice for decode-sized M on the Llama-2-7B, Mistral-7B and Llama-2-70B layer shapes is the measured optimum
+    (or within its noise).  Without a GPU the planner assumes 148 SMs."""
+    from quick_b200 import ops
+    want = {  # (K, N): split at M <= 16
+        (4096, 12288): 2, (4096, 4096): 8, (4096, 22016): 2, (11008, 4096): 8,            # 7B q|k|v, o, gate|up, down
+        (4096, 6144): 4, (4096, 28672): 1, (14336, 4096): 8,                              # Mistral-7B
+        (8192, 10240): 4, (8192, 8192): 4, (8192, 57344): 2, (28672, 8192): 4,            # 70B on one GPU
+        (8192, 5120): 4, (8192, 4096): 8, (8192, 28672): 2, (28672, 4096): 8,             # 70B on two GPUs
+    }
+    for (K, N), split in want.items():
+        for M in (1, 16):
+            tok, s, ctas = ops.plan(M, K, N, 128)
+            assert (tok, s) == (16, split), (K, N, M, tok, s)
+            assert ctas == N // 128 * s
+
+
 def test_quick_kernels_module_surface(built):
     """Drop-in boundary: module name and symbol of csrc/pybind.cpp:5-8."""
     import quick_kernels
