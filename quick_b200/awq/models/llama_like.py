@@ -501,7 +501,10 @@ class LlamaLikeQuickModel(nn.Module):
             sin = self.rope_sin.index_select(0, pos_idx)[None, None]
             # causal mask over the static cache: key j visible to query at position p iff j <= p
             keys = torch.arange(cfg.max_seq_len, device=x.device)
-            attn_mask = keys[None, :] <= pos_idx[:, None]
+            visible = keys[None, :] <= pos_idx[:, None]
+            # additive form, built once per forward: a boolean mask makes SDPA convert it in every layer (fill + where)
+            attn_mask = torch.zeros(visible.shape, dtype=x.dtype, device=x.device).masked_fill_(~visible, float("-inf")) \
+                if x.is_cuda else visible
         src = None        # tensor parallel, peer mode: the gathered buffer the hidden state lives in
         for blk in self.blocks:
             x, src = blk(x, cos, sin, pos_idx, attn_mask, self.ref_mod, (self.rope_cos, self.rope_sin), src)

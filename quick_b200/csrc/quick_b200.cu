@@ -339,28 +339,54 @@ __global__ void rmsnorm_kernel(const __half* __restrict__ x, const __half* __res
 
 // qkv [B][T][(nh + 2 nkv) * hd] -> q_rot [B][nh][T][hd]; k_rot, v written into the static caches [B][nkv][S][hd] at pos[t].
 // rope(t) = fp16(fp16(t * cos) + fp16(rot(t) * sin)), rot = (-t2, t1) over the two halves of the head (same as _rope()).
+// One work item = (row b·T + t, head, 8 dims of the lower half + the matching 8 dims of the upper half): 16-byte loads
+// and stores, a grid-strided loop (a prefill of 8192 rows is 6 M items; the first version launched one 128-thread block
+// per (head, row): 786 k blocks).
+__device__ __forceinline__ uint4 rope8(uint4 v, uint4 other, uint4 c, uint4 s, bool negate_other) {
+  uint4 r;
+  const __half2* pv = reinterpret_cast<const __half2*>(&v);
+  const __half2* po = reinterpret_cast<const __half2*>(&other);
+  const __half2* pc = reinterpret_cast<const __half2*>(&c);
+  const __half2* ps = reinterpret_cast<const __half2*>(&s);
+  __half2* pr = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 o = negate_other ? __hneg2(po[i]) : po[i];
+    pr[i] = __hadd2_rn(__hmul2_rn(pv[i], pc[i]), __hmul2_rn(o, ps[i]));   // _rn: no contraction into fma, torch rounds each step
+  }
+  return r;
+}
 __global__ void rope_kv_kernel(const __half* __restrict__ qkv, const __half* __restrict__ cosb, const __half* __restrict__ sinb,
                                const long long* __restrict__ pos, __half* __restrict__ q_out, __half* __restrict__ cache_k,
-                               __half* __restrict__ cache_v, int T, int nh, int nkv, int hd, int S) {
+                               __half* __restrict__ cache_v, int B, int T, int nh, int nkv, int hd, int S) {
   qb200::pdl_launch_dependents();
   qb200::pdl_wait_prior_grid();
-  const int head = blockIdx.x;            // 0 .. nh + 2 nkv - 1
-  const int t = blockIdx.y, b = blockIdx.z;
-  const int width = (nh + 2 * nkv) * hd;
-  const __half* src = qkv + (static_cast<size_t>(b) * T + t) * width + static_cast<size_t>(head) * hd;
-  const long long p = pos[t];
-  const int half_hd = hd >> 1;
-  for (int i = threadIdx.x; i < hd; i += blockDim.x) {
-    const __half v = src[i];
+  const int heads = nh + 2 * nkv, half_hd = hd >> 1, per_head = hd >> 4;     // items per head (hd is a multiple of 16)
+  const long long total = static_cast<long long>(B) * T * heads * per_head;
+  for (long long it = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; it < total;
+       it += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(it % per_head) * 8;
+    long long r = it / per_head;
+    const int head = static_cast<int>(r % heads);
+    r /= heads;
+    const int t = static_cast<int>(r % T), b = static_cast<int>(r / T);
+    const __half* src = qkv + (static_cast<size_t>(b) * T + t) * heads * hd + static_cast<size_t>(head) * hd;
+    const uint4 lo = *reinterpret_cast<const uint4*>(src + c8), hi = *reinterpret_cast<const uint4*>(src + half_hd + c8);
+    const long long p = pos[t];
     if (head >= nh + nkv) {               // value head: plain copy into the cache
-      cache_v[((static_cast<size_t>(b) * nkv + (head - nh - nkv)) * S + p) * hd + i] = v;
+      __half* dst = cache_v + ((static_cast<size_t>(b) * nkv + (head - nh - nkv)) * S + p) * hd;
+      *reinterpret_cast<uint4*>(dst + c8) = lo;
+      *reinterpret_cast<uint4*>(dst + half_hd + c8) = hi;
       continue;
     }
-    const __half c = cosb[static_cast<size_t>(p) * hd + i], sn = sinb[static_cast<size_t>(p) * hd + i];
-    const __half other = i < half_hd ? __hneg(src[i + half_hd]) : src[i - half_hd];
-    const __half r = __hadd_rn(__hmul_rn(v, c), __hmul_rn(other, sn));   // _rn: no contraction into fma, torch rounds each step
-    if (head < nh) q_out[((static_cast<size_t>(b) * nh + head) * T + t) * hd + i] = r;
-    else cache_k[((static_cast<size_t>(b) * nkv + (head - nh)) * S + p) * hd + i] = r;
+    const __half* cp = cosb + static_cast<size_t>(p) * hd;
+    const __half* sp = sinb + static_cast<size_t>(p) * hd;
+    const uint4 out_lo = rope8(lo, hi, *reinterpret_cast<const uint4*>(cp + c8), *reinterpret_cast<const uint4*>(sp + c8), true);
+    const uint4 out_hi = rope8(hi, lo, *reinterpret_cast<const uint4*>(cp + half_hd + c8), *reinterpret_cast<const uint4*>(sp + half_hd + c8), false);
+    __half* dst = head < nh ? q_out + ((static_cast<size_t>(b) * nh + head) * T + t) * hd
+                            : cache_k + ((static_cast<size_t>(b) * nkv + (head - nh)) * S + p) * hd;
+    *reinterpret_cast<uint4*>(dst + c8) = out_lo;
+    *reinterpret_cast<uint4*>(dst + half_hd + c8) = out_hi;
   }
 }
 
@@ -1443,12 +1469,17 @@ int qb200_rmsnorm(const void* x, const void* weight, void* y, int rows, int H, f
 
 int qb200_rope_kv_update(const void* qkv, const void* cos_table, const void* sin_table, const long long* pos, void* q_out,
                          void* cache_k, void* cache_v, int B, int T, int nh, int nkv, int hd, int S, void* stream) {
-  if (B <= 0 || T <= 0 || nh <= 0 || nkv <= 0 || hd <= 0 || hd % 2 != 0 || S <= 0) return fail(QB200_EINVAL, "rope_kv_update: bad dimensions");
-  if (T > 65535 || B > 65535) return fail(QB200_EINVAL, "rope_kv_update: T and B must be <= 65535");
-  QB_CUDA(launch_pdl(rope_kv_kernel, dim3(nh + 2 * nkv, T, B), dim3(hd >= 128 ? 128 : 64), as_stream(stream),
+  if (B <= 0 || T <= 0 || nh <= 0 || nkv <= 0 || hd <= 0 || hd % 16 != 0 || S <= 0)
+    return fail(QB200_EINVAL, "rope_kv_update: bad dimensions (the head dimension must be a multiple of 16)");
+  if ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(cos_table) | reinterpret_cast<uintptr_t>(sin_table) |
+       reinterpret_cast<uintptr_t>(q_out) | reinterpret_cast<uintptr_t>(cache_k) | reinterpret_cast<uintptr_t>(cache_v)) & 15)
+    return fail(QB200_EINVAL, "rope_kv_update: pointers must be 16-byte aligned");
+  const long long items = static_cast<long long>(B) * T * (nh + 2 * nkv) * (hd / 16);
+  const unsigned blocks = static_cast<unsigned>(std::min<long long>((items + 255) / 256, 8LL * device_sm_count()));
+  QB_CUDA(launch_pdl(rope_kv_kernel, dim3(blocks), dim3(256), as_stream(stream),
                      reinterpret_cast<const __half*>(qkv), reinterpret_cast<const __half*>(cos_table),
                      reinterpret_cast<const __half*>(sin_table), pos, reinterpret_cast<__half*>(q_out),
-                     reinterpret_cast<__half*>(cache_k), reinterpret_cast<__half*>(cache_v), T, nh, nkv, hd, S));
+                     reinterpret_cast<__half*>(cache_k), reinterpret_cast<__half*>(cache_v), B, T, nh, nkv, hd, S));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return QB200_OK;
 }
