@@ -210,7 +210,7 @@ int qb200_gemm_w4a16_simt(const void* A_fp16, const uint32_t* wq, const uint32_t
  * modules call awq_ext for these (modules/fused/norm.py:18, attn.py:100-245, mlp.py:52-76); awq_ext is not in its tree. ---- */
 /* y[rows][H] = fp16(fp16(x * rsqrt(mean(x^2) + eps)) * weight), statistics in fp32. */
 int qb200_rmsnorm(const void* x_fp16, const void* weight_fp16, void* y_fp16, int rows, int H, float eps, void* stream);
-/* qkv [B][T][(nh + 2 nkv) hd] -> rotary-embedded q_out [B][nh][T][hd]; rotary k and plain v are written into the static
+/* qkv [B][T][(nh + 2 nkv) hd] -> rotary-embedded q_out [B][T][nh][hd] (token-major); rotary k and plain v are written into the static
  * caches [B][nkv][S][hd] at positions pos[t] (int64 device array); cos/sin tables are [S][hd] fp16.  hd is a multiple of
  * 16 and every pointer 16-byte aligned (16-byte vector accesses). */
 int qb200_rope_kv_update(const void* qkv_fp16, const void* cos_table_fp16, const void* sin_table_fp16, const long long* pos,

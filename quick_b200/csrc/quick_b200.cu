@@ -337,7 +337,9 @@ __global__ void rmsnorm_kernel(const __half* __restrict__ x, const __half* __res
   }
 }
 
-// qkv [B][T][(nh + 2 nkv) * hd] -> q_rot [B][nh][T][hd]; k_rot, v written into the static caches [B][nkv][S][hd] at pos[t].
+// qkv [B][T][(nh + 2 nkv) * hd] -> q_rot [B][T][nh][hd] (token-major, like qkv: attention over the transposed view then
+// returns token-major rows, which o_proj reads without a transpose copy); k_rot, v written into the static caches
+// [B][nkv][S][hd] at pos[t].
 // rope(t) = fp16(fp16(t * cos) + fp16(rot(t) * sin)), rot = (-t2, t1) over the two halves of the head (same as _rope()).
 // One work item = (row b·T + t, head, 8 dims of the lower half + the matching 8 dims of the upper half): 16-byte loads
 // and stores, a grid-strided loop (a prefill of 8192 rows is 6 M items; the first version launched one 128-thread block
@@ -383,7 +385,7 @@ __global__ void rope_kv_kernel(const __half* __restrict__ qkv, const __half* __r
     const __half* sp = sinb + static_cast<size_t>(p) * hd;
     const uint4 out_lo = rope8(lo, hi, *reinterpret_cast<const uint4*>(cp + c8), *reinterpret_cast<const uint4*>(sp + c8), true);
     const uint4 out_hi = rope8(hi, lo, *reinterpret_cast<const uint4*>(cp + half_hd + c8), *reinterpret_cast<const uint4*>(sp + half_hd + c8), false);
-    __half* dst = head < nh ? q_out + ((static_cast<size_t>(b) * nh + head) * T + t) * hd
+    __half* dst = head < nh ? q_out + ((static_cast<size_t>(b) * T + t) * nh + head) * hd
                             : cache_k + ((static_cast<size_t>(b) * nkv + (head - nh)) * S + p) * hd;
     *reinterpret_cast<uint4*>(dst + c8) = out_lo;
     *reinterpret_cast<uint4*>(dst + half_hd + c8) = out_hi;

@@ -261,12 +261,12 @@ torch::Tensor rope_kv_update(torch::Tensor qkv, torch::Tensor cos_table, torch::
   const int hd = static_cast<int>(x.size(2) / (nh + 2 * nkv)), S = static_cast<int>(cache_k.size(2));
   TORCH_CHECK(x.size(2) == (nh + 2 * nkv) * hd && cache_k.size(3) == hd && cache_k.size(1) == nkv && cache_k.size(0) >= B, "rope_kv_update: shape mismatch");
   TORCH_CHECK(c.size(-1) == hd && c.size(0) >= S && p.numel() == T, "rope_kv_update: table / pos shape mismatch");
-  torch::Tensor q = torch::empty({B, nh, T, hd}, x.options());
+  torch::Tensor q = torch::empty({B, T, nh, hd}, x.options());     // token-major memory, returned as the [B, nh, T, hd] view
   check(qb200_rope_kv_update(x.data_ptr<at::Half>(), c.data_ptr<at::Half>(), s.data_ptr<at::Half>(),
                              reinterpret_cast<const long long*>(p.data_ptr<int64_t>()), q.data_ptr<at::Half>(),
                              cache_k.data_ptr<at::Half>(), cache_v.data_ptr<at::Half>(), B, T, static_cast<int>(nh),
                              static_cast<int>(nkv), hd, S, at::cuda::getCurrentCUDAStream().stream()));
-  return q;
+  return q.transpose(1, 2);
 }
 
 // Decode-step attention fused with rotary embedding + KV-cache update (C-ABI qb200_attn_decode): qkv [B, 1, (nh + 2 nkv) hd]
