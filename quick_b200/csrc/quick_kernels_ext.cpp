@@ -178,6 +178,50 @@ torch::Tensor gemm_forward_b200(torch::Tensor in_feats, torch::Tensor wq, torch:
   return out;
 }
 
+// The per-call work of WQLinear_QUICK.forward in one object: holds the B200-layout copy and the bias, flattens the leading
+// dimensions, launches, reshapes — the Python side of a forward is then one method call (the eager module surface is
+// host-bound below M = 64: 14 us per call through the Python-level wrapper).
+struct B200Linear {
+  torch::Tensor wq, sz, bias;
+  int64_t K, N, G;
+  const void* bias_ptr = nullptr;
+  B200Linear(torch::Tensor wq_, torch::Tensor sz_, c10::optional<torch::Tensor> bias_, int64_t K_, int64_t N_, int64_t G_)
+      : wq(std::move(wq_)), sz(std::move(sz_)), K(K_), N(N_), G(G_) {
+    TORCH_CHECK(wq.is_cuda() && sz.is_cuda(), "B200Linear: CUDA tensors required (there is no CPU path)");
+    check(qb200_check_shape(1, static_cast<int>(K), static_cast<int>(N), static_cast<int>(G)));
+    TORCH_CHECK(static_cast<size_t>(wq.numel()) * 4 == qb200_wq_bytes(K, N) && static_cast<size_t>(sz.numel()) * 4 == qb200_sz_bytes(K, N, G),
+                "B200Linear: wq / sz size mismatch");
+    if (bias_.has_value() && bias_->defined()) {
+      bias = bias_->contiguous();
+      TORCH_CHECK(bias.numel() == N && bias.scalar_type() == torch::kHalf && bias.is_cuda(), "bias must be CUDA fp16 [N]");
+      bias_ptr = bias.data_ptr<at::Half>();
+    }
+  }
+  torch::Tensor forward(const torch::Tensor& x_in, const c10::optional<torch::Tensor>& residual) {
+    TORCH_CHECK(x_in.is_cuda() && x_in.scalar_type() == torch::kHalf && x_in.dim() >= 1 && x_in.size(-1) == K,
+                "input must be a CUDA fp16 tensor [..., in_features] (there is no CPU path)");
+    const at::cuda::OptionalCUDAGuard device_guard(device_of(x_in));
+    torch::Tensor x = x_in.contiguous();
+    const int64_t M = x.numel() / K;
+    std::vector<int64_t> shape(x.sizes().begin(), x.sizes().end());
+    shape.back() = N;
+    torch::Tensor out = torch::empty(shape, x.options());
+    const void* res_ptr = nullptr;
+    torch::Tensor r;
+    if (residual.has_value() && residual->defined()) {
+      r = residual->contiguous();
+      TORCH_CHECK(r.numel() == M * N && r.scalar_type() == torch::kHalf && r.is_cuda(), "residual must be CUDA fp16 [..., out_features]");
+      res_ptr = r.data_ptr<at::Half>();
+    }
+    if (M == 0) return out;
+    check(qb200_gemm_w4a16_fused(x.data_ptr<at::Half>(), reinterpret_cast<const uint32_t*>(wq.data_ptr<int>()),
+                                 reinterpret_cast<const uint32_t*>(sz.data_ptr<int>()), bias_ptr, res_ptr, out.data_ptr<at::Half>(),
+                                 static_cast<int>(M), static_cast<int>(K), static_cast<int>(N), static_cast<int>(G), 0, 0, 0u,
+                                 at::cuda::getCurrentCUDAStream().stream()));
+    return out;
+  }
+};
+
 // GEMM with an RMSNorm folded around it (C-ABI qb200_gemm_w4a16_norm, include/quick_b200.h):
 //   norm_gamma given -> producer side: returns {out, out ⊙ gamma (fp16 [M, N]), per-tile sums of squares (fp32 [N/128, M])}
 //   ssq_in given     -> consumer side: in_feats is a producer's gamma-scaled copy, rows are scaled by 1/rms before the bias
@@ -307,6 +351,10 @@ torch::Tensor silu_mul(torch::Tensor gate_up) {
 }
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  py::class_<B200Linear>(m, "B200Linear", "linear(x) (+ bias, + residual) on B200-layout weights: WQLinear_QUICK.forward's per-call work in one call")
+      .def(py::init<torch::Tensor, torch::Tensor, c10::optional<torch::Tensor>, int64_t, int64_t, int64_t>(), py::arg("wq"), py::arg("sz"),
+           py::arg("bias"), py::arg("K"), py::arg("N"), py::arg("G"))
+      .def("forward", &B200Linear::forward, py::arg("x"), py::arg("residual") = py::none());
   m.def("rmsnorm", &rmsnorm, "RMSNorm (fp16 in/out, fp32 statistics)");
   m.def("rope_kv_update", &rope_kv_update, "rotary embedding of q/k + static KV-cache update; returns q [B, nh, T, hd]");
   m.def("silu_mul", &silu_mul, "silu(gate) * up for rows [gate | up]");
