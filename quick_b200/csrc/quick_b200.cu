@@ -511,27 +511,33 @@ attn_decode_kernel(const __half* __restrict__ qkv, const __half* __restrict__ co
   int j0 = lo + warp;
   int nv = j0 < hi ? load_batch(j0, kr0, vr0) : 0;
 
-  // rotary embedding of the g query heads (every CTA) and of k (CTA 0, which also updates the cache)
+  // rotary embedding of the g query heads (every CTA) and of k (CTA 0, which also updates the cache): one item = 8 dims of
+  // the lower half of a head + the matching 8 of the upper half, 16-byte accesses (same arithmetic as rope_kv_kernel)
   const __half* src = qkv + static_cast<size_t>(b) * (nh + 2 * nkv) * hd;
-  constexpr int half_hd = hd >> 1;
-  for (int idx = tid; idx < (rank == 0 ? g + 2 : g) * hd; idx += kAttnThreads) {
-    const int hl = idx / hd, i = idx - hl * hd;
+  constexpr int half_hd = hd >> 1, per_head = hd >> 4;
+  for (int idx = tid; idx < (rank == 0 ? g + 2 : g) * per_head; idx += kAttnThreads) {
+    const int hl = idx / per_head, c8 = (idx - hl * per_head) * 8;
+    const __half* hsrc = src + static_cast<size_t>(hl < g ? kvh * g + hl : hl == g ? nh + kvh : nh + nkv + kvh) * hd;
+    const uint4 lo = *reinterpret_cast<const uint4*>(hsrc + c8), hi = *reinterpret_cast<const uint4*>(hsrc + half_hd + c8);
     if (hl == g + 1) {                                   // value: plain copy
-      const __half v = src[static_cast<size_t>(nh + nkv + kvh) * hd + i];
-      vs[i] = v;
-      cache_v[(crow + p) * hd + i] = v;
+      *reinterpret_cast<uint4*>(vs + c8) = lo;
+      *reinterpret_cast<uint4*>(vs + half_hd + c8) = hi;
+      __half* dstv = cache_v + (crow + p) * hd;
+      *reinterpret_cast<uint4*>(dstv + c8) = lo;
+      *reinterpret_cast<uint4*>(dstv + half_hd + c8) = hi;
       continue;
     }
-    const __half* hsrc = src + static_cast<size_t>(hl < g ? kvh * g + hl : nh + kvh) * hd;
-    const __half v = hsrc[i];
-    const __half c = cosb[static_cast<size_t>(p) * hd + i], sn = sinb[static_cast<size_t>(p) * hd + i];
-    const __half other = i < half_hd ? __hneg(hsrc[i + half_hd]) : hsrc[i - half_hd];
-    const __half r = __hadd_rn(__hmul_rn(v, c), __hmul_rn(other, sn));   // == rope_kv_kernel
-    if (hl < g) {
-      qs[hl * hd + i] = r;
-    } else {
-      ks[i] = r;
-      cache_k[(crow + p) * hd + i] = r;
+    const __half* cp = cosb + static_cast<size_t>(p) * hd;
+    const __half* sp = sinb + static_cast<size_t>(p) * hd;
+    const uint4 out_lo = rope8(lo, hi, *reinterpret_cast<const uint4*>(cp + c8), *reinterpret_cast<const uint4*>(sp + c8), true);
+    const uint4 out_hi = rope8(hi, lo, *reinterpret_cast<const uint4*>(cp + half_hd + c8), *reinterpret_cast<const uint4*>(sp + half_hd + c8), false);
+    __half* dsts = hl < g ? qs + hl * hd : ks;
+    *reinterpret_cast<uint4*>(dsts + c8) = out_lo;
+    *reinterpret_cast<uint4*>(dsts + half_hd + c8) = out_hi;
+    if (hl == g) {
+      __half* dstk = cache_k + (crow + p) * hd;
+      *reinterpret_cast<uint4*>(dstk + c8) = out_lo;
+      *reinterpret_cast<uint4*>(dstk + half_hd + c8) = out_hi;
     }
   }
   __syncthreads();
