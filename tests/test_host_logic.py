@@ -113,6 +113,18 @@ def test_gemm_plan_fills_the_machine(built):
         assert isplit == 1 and itok >= min(M, 256) and ictas == (4096 // 128) * -(-M // itok)
 
 
+def test_module_fast_path_object_refuses_cpu_tensors(built):
+    """quick_kernels.B200Linear (the per-call work of WQLinear_QUICK.forward in one C++ object) has no CPU path either: it
+    refuses CPU weights at construction, and the module's forward on CPU tensors fails loudly instead of falling back."""
+    import quick_kernels
+    from quick_b200.awq.modules.linear.quick import WQLinear_QUICK
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        quick_kernels.B200Linear(torch.zeros(512 * 512 // 8, dtype=torch.int32), torch.zeros(4 * 512, dtype=torch.int32), None, 512, 512, 128)
+    m = WQLinear_QUICK(4, 128, 512, 512, False, "cpu")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(1, 512, dtype=torch.float16))
+
+
 def test_gemm_plan_picks_the_measured_optimum_for_the_layer_shapes(built):
     """Planner vs the split sweeps on B200 (tools/tune_shapes.py, profiles/r2b_tune_shapes_70b.log, r2g_tune_*): the
     choice for decode-sized M on the Llama-2-7B, Mistral-7B and Llama-2-70B layer shapes is the measured optimum
