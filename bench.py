@@ -77,7 +77,7 @@ def peaks():
 
 def ncu_traffic(M):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the GEMM at this M from the committed ncu summary."""
-    for name in ("r2_ncu_full.json", "r1c_ncu_full.json"):
+    for name in ("r2d_ncu_full.json", "r2_ncu_full.json", "r1c_ncu_full.json"):
         p = os.path.join(ROOT, "profiles", name)
         if not os.path.exists(p):
             continue
@@ -512,7 +512,7 @@ def run_mine(args):
     else:
         roof = {"bound": "hbm", "achieved": dom["GBs"], "peak": pk["hbm_gbs"], "unit": "GB/s"}
     # DRAM bytes per launch of the dominant kernel: not observable from inside the run — taken from the committed
-    # `ncu --set full` summary of this same command (profiles/r2_ncu_full.json, per launch) and labelled as such
+    # `ncu --set full` summary of this same command (profiles/r2d_ncu_full.json, per launch) and labelled as such
     traffic, traffic_src = ncu_traffic(dom["M"])
     roof.update({"frac": round(roof["achieved"] / roof["peak"], 4), "traffic": traffic, "traffic_source": traffic_src,
                  "kernel": "w4a16_umma_kernel", "algorithmic_bytes": int(alg_bytes(dom["M"])),
